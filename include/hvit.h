@@ -1,0 +1,171 @@
+/* libhvit_sm100.so - C ABI of the B200 (sm_100a) HybridViT speech-enhancement inference path.
+ *
+ * This is the drop-in boundary for the reference's inference hot path.  The reference is pure Python and has no
+ * FFI of its own; these entry points are what a binding for that path binds (see INTEGRATION.md for the ctypes
+ * stub).  Each function cites the reference interface it replaces (paths relative to the reference repo).
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = ok, negative = HVIT_E_*; hvit_last_error() gives the message
+ *     (thread-local).
+ *   - all pointers named *_dev are CUDA device pointers owned by the caller; nothing is allocated, freed or
+ *     retained beyond the lifetime of the plan that was given them; no hidden device allocation.
+ *   - all work is enqueued asynchronously on the caller's stream (`stream` is a cudaStream_t passed as void*);
+ *     no function synchronises the device, so calls can be captured into a CUDA graph.
+ *   - activations are NHWC internally; the public tensors keep the reference layouts ([B,1,F,T], [B,n]).
+ *   - there is no CPU fallback: on a device that is not sm_100 plan creation fails with HVIT_E_ARCH.
+ */
+#ifndef HVIT_H_
+#define HVIT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HVIT_OK 0
+#define HVIT_E_SHAPE (-1)   /* unsupported or inconsistent shape / configuration */
+#define HVIT_E_ARCH (-2)    /* device is not sm_100 */
+#define HVIT_E_ALLOC (-3)   /* workspace too small / misaligned */
+#define HVIT_E_LAUNCH (-4)  /* CUDA launch or driver error */
+#define HVIT_E_ARG (-5)     /* null pointer or bad argument */
+
+#define HVIT_PREC_FP32 0 /* fp32 CUDA-core arithmetic, fp32 activations (accuracy mode, <= 1e-4)           */
+#define HVIT_PREC_BF16 1 /* bf16 tcgen05 tensor-core contractions, fp32 accumulation / residual / statistics */
+
+#define HVIT_MAX_STAGES 8
+#define HVIT_MAX_LAYERS 48
+
+/* Mirrors HybridViT.__init__ (models/hybrid_vit.py:36-67) after create_hybrid_vit (hybrid_vit.py:492-525). */
+typedef struct hvit_model_cfg {
+  int n_enc;                          /* len(encoder_channels); block 0 is the 1->C stem               */
+  int enc_channels[HVIT_MAX_STAGES];
+  int enc_pool[HVIT_MAX_STAGES];      /* 1 (none) or 2                                                  */
+  int embed_dim, num_heads, num_layers, mlp_hidden, patch_size;
+  int n_dec;                          /* len(decoder_channels); last block is the C->1 tanh head        */
+  int dec_channels[HVIT_MAX_STAGES];
+  int dec_up[HVIT_MAX_STAGES];        /* 1 (none) or 2 (nearest)                                        */
+  int use_skip;
+  int precision;                      /* HVIT_PREC_*                                                    */
+  float ln_eps;
+} hvit_model_cfg;
+
+/* Packed, device-resident weights (derived once from the reference state_dict; the
+ * packing itself is host-side torch code in hvit_b200/models/packing.py).  "act" = bf16 in HVIT_PREC_BF16, fp32 in
+ * HVIT_PREC_FP32.  BatchNorm (eval) is folded into per-channel scale/shift.  Conv weights are [Cout][ky][kx][Cin].
+ * In BF16 mode a decoder block with upsample 2 gets the four pre-summed 2x2 parity kernels [4][Cout][2][2][Cin];
+ * in FP32 mode it keeps the original [Cout][3][3][Cin]. */
+typedef struct hvit_weights {
+  const float* stem_w;      /* [3][3][C0] fp32 */
+  const float* stem_scale;  /* [C0] */
+  const float* stem_shift;  /* [C0] */
+  const void* enc_w[HVIT_MAX_STAGES];      /* act; index i = encoder block i (i >= 1) */
+  const float* enc_scale[HVIT_MAX_STAGES];
+  const float* enc_shift[HVIT_MAX_STAGES];
+  const void* patch_w;      /* act [D][p][p][C] */
+  const float* patch_b;     /* [D] */
+  const float* pos_embed;   /* fp32 [pos_len][D] */
+  int pos_len;
+  const float* ln1_g[HVIT_MAX_LAYERS];
+  const float* ln1_b[HVIT_MAX_LAYERS];
+  const float* ln2_g[HVIT_MAX_LAYERS];
+  const float* ln2_b[HVIT_MAX_LAYERS];
+  const void* qkv_w[HVIT_MAX_LAYERS];   /* act [3D][D] */
+  const float* qkv_b[HVIT_MAX_LAYERS];
+  const void* proj_w[HVIT_MAX_LAYERS];  /* act [D][D] */
+  const float* proj_b[HVIT_MAX_LAYERS];
+  const void* fc1_w[HVIT_MAX_LAYERS];   /* act [hidden][D] */
+  const float* fc1_b[HVIT_MAX_LAYERS];
+  const void* fc2_w[HVIT_MAX_LAYERS];   /* act [D][hidden] */
+  const float* fc2_b[HVIT_MAX_LAYERS];
+  const float* lnf_g;
+  const float* lnf_b;
+  const void* tofm_w;       /* act [Cenc][D] */
+  const float* tofm_b;
+  const void* skip_w[HVIT_MAX_STAGES];  /* act [Cdec_i][Cenc_rev_i] (1x1 conv) */
+  const float* skip_b[HVIT_MAX_STAGES];
+  const void* dec_w[HVIT_MAX_STAGES];   /* act; blocks 0 .. n_dec-2 */
+  const float* dec_scale[HVIT_MAX_STAGES];
+  const float* dec_shift[HVIT_MAX_STAGES];
+  const float* head_w;      /* [3][3][C] fp32, last decoder block */
+} hvit_weights;
+
+typedef struct hvit_plan hvit_plan;
+
+const char* hvit_last_error(void);
+int hvit_version(void);
+/* 1 when the current CUDA device is compute capability 10.x, 0 otherwise, negative on CUDA error. */
+int hvit_device_ok(void);
+
+/* Bytes of device workspace a plan needs.  n_samples > 0 adds the STFT/iSTFT buffers (enhance path) and
+ * requires F == 257, T == 1 + n_samples / 128.  Returns 0 and sets the error string on bad input. */
+size_t hvit_workspace_bytes(const hvit_model_cfg* cfg, int B, int F, int T, int n_samples);
+
+/* Builds the launch plan (layer geometry, TMA tensor maps over `workspace_dev` and the weight buffers).
+ * Replaces the module-construction half of HybridViT.__init__ / AudioEnhancer.__init__
+ * (models/hybrid_vit.py:36-170, inference/enhancer.py:25-53). */
+int hvit_plan_create(const hvit_model_cfg* cfg, const hvit_weights* weights, int B, int F, int T, int n_samples,
+                     void* workspace_dev, size_t workspace_bytes, hvit_plan** plan_out);
+void hvit_plan_destroy(hvit_plan* plan);
+
+/* HybridViT.forward (models/hybrid_vit.py:396-469), eval mode.
+ *   x_dev: fp32 [B,1,F,T]   y_dev: fp32 [B,1,F,T]
+ *   attn_probs_dev: null, or fp32 [num_layers][B][heads][N][N] to receive the softmax maps
+ *                   (return_attentions=True, hybrid_vit.py:422-450). */
+int hvit_forward(hvit_plan* plan, const float* x_dev, float* y_dev, float* attn_probs_dev, void* stream);
+
+/* AudioEnhancer.enhance (inference/enhancer.py:55-135) for a batch of equal-length clips, everything on the
+ * device: peak-normalise -> STFT(512/128/hann, centred) -> |.|, per-clip max-normalise -> HybridViT.forward ->
+ * de-normalise, recombine with the noisy phase -> iSTFT(length=n) -> de-normalise.
+ *   wave_in_dev / wave_out_dev: fp32 [B, n_samples]. */
+int hvit_enhance(hvit_plan* plan, const float* wave_in_dev, float* wave_out_dev, int normalize, void* stream);
+
+/* Introspection for tests: byte offset (into the workspace), and dims of a named internal buffer.
+ * Names: "enc<i>", "tokens", "ln", "qkv", "attn", "mlp", "cat<i>", "dec_last", "logits", "tanh", "model_out",
+ * "mag", "spec", "max_val", "mag_max", "frames".  dims receives up to 4 ints; returns the rank or negative. */
+int hvit_plan_buffer(const hvit_plan* plan, const char* name, size_t* offset, int* dims, int* elem_bytes);
+/* Number of kernels one hvit_forward / hvit_enhance call launches. */
+int hvit_plan_launch_count(const hvit_plan* plan, int enhance);
+/* Token count N and patch grid of the plan. */
+int hvit_plan_tokens(const hvit_plan* plan, int* hp, int* wp);
+
+/* ---- per-kernel entry points (unit tests, microbenchmarks) ------------------------------------------------ */
+
+/* C[M,N] = act(A[M,K] * W[N,K]^T * scale[n] + shift[n]) (+ residual), bf16 operands on tcgen05.
+ * nn.Linear (attention.py:83,109; components.py:223-229; hybrid_vit.py:343).  out is bf16 or fp32 (out_f32). */
+int hvit_gemm_bf16(const void* a_dev, int lda, const void* w_dev, const float* scale_dev, const float* shift_dev,
+                   int act, const float* residual_dev, int ldr, void* out_dev, int ldc, int out_f32, int M, int N,
+                   int K, void* stream);
+/* Same contract on CUDA cores in fp32 (a, w, out fp32). */
+int hvit_gemm_f32(const float* a_dev, int lda, const float* w_dev, const float* scale_dev, const float* shift_dev,
+                  int act, const float* residual_dev, int ldr, float* out_dev, int ldc, int M, int N, int K,
+                  void* stream);
+/* 3x3 / pad 1 conv + per-channel scale/shift + ReLU (+ 2x2 max-pool) on NHWC bf16, tcgen05 implicit GEMM.
+ * ConvBlock / TransposeConvBlock in eval mode (components.py:15-99,102-192).
+ * up2 = 1: nearest x2 upsample first; w_dev then holds the four parity kernels [4][Cout][2][2][Cin]. */
+int hvit_conv3x3_bf16(const void* x_dev, const void* w_dev, const float* scale_dev, const float* shift_dev, int relu,
+                      int pool, int up2, void* out_dev, int B, int H, int W, int Cin, int Cout, void* stream);
+int hvit_conv3x3_f32(const float* x_dev, const float* w_dev, const float* scale_dev, const float* shift_dev,
+                     int relu, int up2, float* out_dev, int B, int H, int W, int Cin, int Cout, void* stream);
+/* Multi-head self-attention core, head_dim 64 (attention.py:86-105). qkv: [B*N, 3D]; out: [B*N, D]. */
+int hvit_attention_bf16(const void* qkv_dev, void* out_dev, int B, int N, int heads, void* stream);
+int hvit_attention_f32(const float* qkv_dev, float* out_dev, float* probs_dev, int B, int N, int heads, void* stream);
+/* nn.LayerNorm over the last dim (attention.py:152-153,258); x fp32, out bf16 (out_bf16=1) or fp32. */
+int hvit_layernorm(const float* x_dev, const float* g_dev, const float* b_dev, void* out_dev, int out_bf16, int rows,
+                   int D, float eps, void* stream);
+/* compute_stft + compute_magnitude_phase + normalize_audio (utils/audio_processing.py:67-98,135-174).
+ *   wave [B,n] -> max_val [B] (u32 bit patterns of the fp32 peaks; 1.0 when normalize=0), spec complex64 [B,257,T],
+ *   mag fp32 [B,257,T] (of the peak-normalised audio), mag_max [B] (u32 bit patterns). */
+int hvit_stft(const float* wave_dev, int B, int n, int normalize, void* max_val_dev, void* spec_dev, float* mag_dev,
+              void* mag_max_dev, void* stream);
+/* reconstruct_from_magnitude_phase + compute_istft (utils/audio_processing.py:101-132,177-193).
+ *   mag_norm [B,257,T] (model output, multiplied by mag_max inside), phase taken from spec; frames_dev is a
+ *   [B,T,512] fp32 scratch. */
+int hvit_istft(const float* mag_norm_dev, const void* spec_dev, const void* mag_max_dev, const void* max_val_dev,
+               float* frames_dev, float* wave_out_dev, int B, int n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HVIT_H_ */

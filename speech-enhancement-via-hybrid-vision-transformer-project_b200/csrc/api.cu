@@ -1,0 +1,827 @@
+// C ABI of libhvit_sm100.so (declared in include/hvit.h): launch plan for HybridViT.forward /
+// AudioEnhancer.enhance, TMA tensor-map construction, per-kernel test entry points, error plumbing.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "hvit.h"
+#include "kernels.h"
+
+namespace hvit {
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[768] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return HVIT_E_LAUNCH;
+  }
+  return HVIT_OK;
+}
+
+// ------------------------------------------------------------------------------------------ tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    const cudaError_t e = cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || p == nullptr) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 tensor, 128-byte swizzle, zero fill out of bounds. dims/box innermost first; strides (bytes) for dims 1..rank-1.
+static int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                     const uint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return HVIT_E_LAUNCH;
+  }
+  cuuint64_t gd[5];
+  cuuint64_t gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gs[i - 1] = strides[i - 1];
+  }
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+                        gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d) rank=%d dims=[%llu,%llu,%llu,...] box=[%u,%u,...]",
+              static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], rank > 1 ? box[1] : 0);
+    return HVIT_E_LAUNCH;
+  }
+  return HVIT_OK;
+}
+
+static int tmap_matrix(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  const uint64_t dims[2] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(rows)};
+  const uint64_t strides[1] = {static_cast<uint64_t>(ld) * 2};
+  const uint32_t box[2] = {64, static_cast<uint32_t>(box_rows)};
+  return make_tmap(m, base, 2, dims, strides, box);
+}
+
+static int tmap_image(CUtensorMap* m, const void* base, int B, int H, int Hpitch, int W, int C, int Wt, int Ht) {
+  const uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                            static_cast<uint64_t>(B)};
+  const uint64_t strides[3] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(W) * C * 2,
+                               static_cast<uint64_t>(Hpitch) * W * C * 2};
+  const uint32_t box[4] = {64, static_cast<uint32_t>(Wt), static_cast<uint32_t>(Ht), 1};
+  return make_tmap(m, base, 4, dims, strides, box);
+}
+
+static int tmap_patch(CUtensorMap* m, const void* base, int B, int Hq, int W, int C, int p, int Wp, int Wt, int Ht) {
+  const uint64_t dims[5] = {static_cast<uint64_t>(C), static_cast<uint64_t>(p), static_cast<uint64_t>(Wp),
+                            static_cast<uint64_t>(p), static_cast<uint64_t>(B) * Hq};
+  const uint64_t strides[4] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(p) * C * 2,
+                               static_cast<uint64_t>(W) * C * 2, static_cast<uint64_t>(p) * W * C * 2};
+  const uint32_t box[5] = {64, 1, static_cast<uint32_t>(Wt), 1, static_cast<uint32_t>(Ht)};
+  return make_tmap(m, base, 5, dims, strides, box);
+}
+
+static int tmap_qkv(CUtensorMap* m, const void* base, int B, int N, int D) {
+  const uint64_t dims[3] = {static_cast<uint64_t>(3) * D, static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
+  const uint64_t strides[2] = {static_cast<uint64_t>(3) * D * 2, static_cast<uint64_t>(N) * 3 * D * 2};
+  const uint32_t box[3] = {64, 128, 1};
+  return make_tmap(m, base, 3, dims, strides, box);
+}
+
+static int pick_block_n(int N) { return N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64); }
+
+static void pick_tile(int H, int W, int* Wt, int* Ht) {
+  const int cand[4][2] = {{128, 1}, {64, 2}, {32, 4}, {16, 8}};
+  long long best = -1;
+  for (int i = 0; i < 4; ++i) {
+    const long long t = static_cast<long long>((W + cand[i][0] - 1) / cand[i][0]) * ((H + cand[i][1] - 1) / cand[i][1]);
+    if (best < 0 || t < best) {
+      best = t;
+      *Wt = cand[i][0];
+      *Ht = cand[i][1];
+    }
+  }
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------ plan
+struct Ctx {
+  const float* x;            // model input [B,F,T]
+  float* y;                  // model output [B,F,T]
+  float* probs;              // optional attention maps
+  const unsigned* mag_max;   // per-clip magnitude max (enhance) or null
+  cudaStream_t stream;
+};
+typedef std::function<int(const Ctx&)> Step;
+
+struct Buf {
+  size_t off;
+  int rank;
+  int dims[4];
+  int es;
+};
+
+struct EncGeo {
+  int H, W, C, pitch;
+};
+struct CatGeo {
+  int H, W, Cx, Ccat;
+};
+
+struct Geometry {
+  int es, B, F, T, n_samples;
+  EncGeo enc[HVIT_MAX_STAGES];
+  int Hp, Wp, Np, M;
+  CatGeo cat[HVIT_MAX_STAGES];  // cat[i] = input of decoder block i
+  std::map<std::string, Buf> bufs;
+  size_t total;
+};
+
+}  // namespace hvit
+
+struct hvit_plan {
+  hvit_model_cfg cfg;
+  hvit_weights w;
+  hvit::Geometry g;
+  uint8_t* ws;
+  std::vector<hvit::Step> steps;
+  int launches_forward;
+};
+
+namespace hvit {
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int build_geometry(const hvit_model_cfg& c, int B, int F, int T, int n_samples, int pos_len, Geometry& g) {
+  if (B < 1 || F < 1 || T < 1) {
+    set_error("bad batch/spectrogram shape B=%d F=%d T=%d", B, F, T);
+    return HVIT_E_SHAPE;
+  }
+  if (c.n_enc < 1 || c.n_enc > HVIT_MAX_STAGES || c.n_dec < 2 || c.n_dec > HVIT_MAX_STAGES || c.num_layers < 0 ||
+      c.num_layers > HVIT_MAX_LAYERS) {
+    set_error("unsupported depth: n_enc=%d n_dec=%d layers=%d", c.n_enc, c.n_dec, c.num_layers);
+    return HVIT_E_SHAPE;
+  }
+  if (c.num_heads < 1 || c.embed_dim != c.num_heads * 64) {
+    set_error("head_dim must be 64: embed_dim=%d num_heads=%d", c.embed_dim, c.num_heads);
+    return HVIT_E_SHAPE;
+  }
+  if (c.patch_size < 1 || c.patch_size > 16) {
+    set_error("unsupported patch_size %d", c.patch_size);
+    return HVIT_E_SHAPE;
+  }
+  const bool bf = c.precision == HVIT_PREC_BF16;
+  const int cmul = bf ? 64 : 16;
+  g.es = bf ? 2 : 4;
+  g.B = B; g.F = F; g.T = T; g.n_samples = n_samples;
+  int H = F, W = T;
+  for (int i = 0; i < c.n_enc; ++i) {
+    const int pool = c.enc_pool[i];
+    if (pool != 1 && pool != 2) {
+      set_error("encoder pool size must be 1 or 2 (block %d: %d)", i, pool);
+      return HVIT_E_SHAPE;
+    }
+    if (c.enc_channels[i] % cmul != 0 || (i == 0 && c.enc_channels[i] > 512)) {
+      set_error("encoder channels must be multiples of %d (block %d: %d)", cmul, i, c.enc_channels[i]);
+      return HVIT_E_SHAPE;
+    }
+    H /= pool;
+    W /= pool;
+    if (H < 1 || W < 1) {
+      set_error("input %dx%d too small for the encoder", F, T);
+      return HVIT_E_SHAPE;
+    }
+    g.enc[i] = {H, W, c.enc_channels[i], H};
+  }
+  EncGeo& last = g.enc[c.n_enc - 1];
+  last.pitch = (last.H + c.patch_size - 1) / c.patch_size * c.patch_size;
+  g.Hp = last.H / c.patch_size;
+  g.Wp = last.W / c.patch_size;
+  g.Np = g.Hp * g.Wp;
+  if (g.Np < 1) {
+    set_error("input %dx%d yields no patches", F, T);
+    return HVIT_E_SHAPE;
+  }
+  if (pos_len > 0 && g.Np > pos_len) {
+    set_error("token count %d exceeds the positional table (%d)", g.Np, pos_len);
+    return HVIT_E_SHAPE;
+  }
+  g.M = B * g.Np;
+  if (c.embed_dim % 64 != 0 || c.mlp_hidden % 64 != 0) {
+    set_error("embed_dim / mlp hidden must be multiples of 64");
+    return HVIT_E_SHAPE;
+  }
+  if (c.dec_channels[0] != last.C) {
+    set_error("decoder_channels[0] (%d) must equal encoder_channels[-1] (%d)", c.dec_channels[0], last.C);
+    return HVIT_E_SHAPE;
+  }
+  if (c.dec_channels[c.n_dec - 1] != 1 || c.dec_up[c.n_dec - 1] != 1) {
+    set_error("the last decoder block must be a 1-channel head without upsampling");
+    return HVIT_E_SHAPE;
+  }
+  int Hx = g.Hp, Wx = g.Wp, Cx = last.C;
+  for (int i = 0; i < c.n_dec; ++i) {
+    const bool final_blk = i == c.n_dec - 1;
+    const bool has_skip = c.use_skip && !final_blk && i < c.n_enc;
+    if (!final_blk && c.dec_channels[i] % cmul != 0) {
+      set_error("decoder channels must be multiples of %d (block %d: %d)", cmul, i, c.dec_channels[i]);
+      return HVIT_E_SHAPE;
+    }
+    g.cat[i] = {Hx, Wx, Cx, Cx + (has_skip ? c.dec_channels[i] : 0)};
+    if (!final_blk) {
+      const int up = c.dec_up[i];
+      if (up != 1 && up != 2) {
+        set_error("decoder upsample factor must be 1 or 2 (block %d: %d)", i, up);
+        return HVIT_E_SHAPE;
+      }
+      Hx *= up;
+      Wx *= up;
+      Cx = c.dec_channels[i];
+    }
+  }
+
+  size_t off = 0;
+  auto add = [&](const std::string& name, int es, int rank, int d0, int d1, int d2, int d3, size_t elems) {
+    Buf b;
+    b.off = off;
+    b.rank = rank;
+    b.dims[0] = d0; b.dims[1] = d1; b.dims[2] = d2; b.dims[3] = d3;
+    b.es = es;
+    g.bufs[name] = b;
+    off = align_up(off + elems * es, 1024);
+  };
+  char nm[32];
+  size_t tmp_elems = 0;
+  {
+    int h = F, w = T;
+    for (int i = 0; i < c.n_enc; ++i) {
+      if (i > 0 && c.enc_pool[i] == 2) tmp_elems = std::max(tmp_elems, static_cast<size_t>(B) * h * w * c.enc_channels[i]);
+      const EncGeo& e = g.enc[i];
+      snprintf(nm, sizeof(nm), "enc%d", i);
+      add(nm, g.es, 4, B, e.pitch, e.W, e.C, static_cast<size_t>(B) * e.pitch * e.W * e.C);
+      h = e.H; w = e.W;
+    }
+  }
+  if (!bf && tmp_elems > 0) add("conv_tmp", 4, 1, static_cast<int>(tmp_elems), 0, 0, 0, tmp_elems);
+  const size_t M = g.M;
+  add("tokens", 4, 2, g.M, c.embed_dim, 0, 0, M * c.embed_dim);
+  add("ln", g.es, 2, g.M, c.embed_dim, 0, 0, M * c.embed_dim);
+  add("qkv", g.es, 2, g.M, 3 * c.embed_dim, 0, 0, M * 3 * c.embed_dim);
+  add("attn", g.es, 2, g.M, c.embed_dim, 0, 0, M * c.embed_dim);
+  add("mlp", g.es, 2, g.M, c.mlp_hidden, 0, 0, M * c.mlp_hidden);
+  size_t samp_elems = 0;
+  for (int i = 0; i < c.n_dec; ++i) {
+    const CatGeo& k = g.cat[i];
+    snprintf(nm, sizeof(nm), "cat%d", i);
+    add(nm, g.es, 4, B, k.H, k.W, k.Ccat, static_cast<size_t>(B) * k.H * k.W * k.Ccat);
+    if (k.Ccat > k.Cx)
+      samp_elems = std::max(samp_elems, static_cast<size_t>(B) * k.H * k.W * c.enc_channels[c.n_enc - 1 - i]);
+  }
+  if (samp_elems > 0) add("samp", g.es, 1, static_cast<int>(samp_elems), 0, 0, 0, samp_elems);
+  const CatGeo& hl = g.cat[c.n_dec - 1];
+  add("logits", 4, 3, B, hl.H, hl.W, 0, static_cast<size_t>(B) * hl.H * hl.W);
+  add("tanh", 4, 3, B, hl.H, hl.W, 0, static_cast<size_t>(B) * hl.H * hl.W);
+  if (n_samples > 0) {
+    if (F != 257 || T != 1 + n_samples / 128) {
+      set_error("enhance plan needs F=257 and T=1+n/128 (got F=%d T=%d n=%d)", F, T, n_samples);
+      return HVIT_E_SHAPE;
+    }
+    add("model_out", 4, 3, B, F, T, 0, static_cast<size_t>(B) * F * T);
+    add("max_val", 4, 1, B, 0, 0, 0, B);
+    add("mag_max", 4, 1, B, 0, 0, 0, B);
+    add("spec", 8, 3, B, F, T, 0, static_cast<size_t>(B) * F * T);
+    add("mag", 4, 3, B, F, T, 0, static_cast<size_t>(B) * F * T);
+    add("frames", 4, 3, B, T, 512, 0, static_cast<size_t>(B) * T * 512);
+  }
+  g.total = off;
+  return HVIT_OK;
+}
+
+template <typename T>
+static T* at(hvit_plan* p, const char* name) {
+  return reinterpret_cast<T*>(p->ws + p->g.bufs.at(name).off);
+}
+
+static IgemmParams ig_zero() {
+  IgemmParams q;
+  memset(&q, 0, sizeof(q));
+  return q;
+}
+
+// plain GEMM step (both precisions)
+static int add_linear(hvit_plan* p, const void* A, int lda, const void* W, const float* shift, int act,
+                      const float* residual, int ldr, int res_mod, void* out, int ldc, int out_f32, int M, int N,
+                      int K) {
+  IgemmParams q = ig_zero();
+  q.mode = IG_PLAIN;
+  q.M = M; q.N = N; q.K = K;
+  q.shift = shift; q.act = act; q.residual = residual; q.ldr = ldr; q.res_mod = res_mod;
+  q.out = out; q.ldc = ldc; q.out_f32 = out_f32;
+  if (p->cfg.precision == HVIT_PREC_BF16) {
+    CUtensorMap ta, tb;
+    const int bn = pick_block_n(N);
+    int r = tmap_matrix(&ta, A, M, K, lda, 128);
+    if (r) return r;
+    r = tmap_matrix(&tb, W, N, K, K, bn);
+    if (r) return r;
+    const int sms = num_sms();
+    p->steps.push_back([=](const Ctx& c) { return launch_igemm_tc(q, ta, tb, bn, sms, c.stream); });
+  } else {
+    q.out_f32 = 1;
+    const float* Af = reinterpret_cast<const float*>(A);
+    const float* Wf = reinterpret_cast<const float*>(W);
+    p->steps.push_back([=](const Ctx& c) { return launch_igemm_f32(q, Af, lda, Wf, c.stream); });
+  }
+  return HVIT_OK;
+}
+
+// 3x3 conv (+ optional fused pool / x2 upsample) step
+static int add_conv(hvit_plan* p, const void* in, int B, int H, int W, int Cin, const void* Wt, const float* scale,
+                    const float* shift, int relu, int pool, int up2, void* out, int ldc, int HoPitch, int Cout,
+                    float* conv_tmp) {
+  IgemmParams q = ig_zero();
+  q.mode = up2 ? IG_UP2 : IG_CONV3;
+  q.B = B; q.H = H; q.W = W; q.Cin = Cin;
+  q.N = Cout;
+  q.scale = scale; q.shift = shift; q.act = relu ? ACT_RELU : ACT_NONE;
+  q.out = out; q.ldc = ldc;
+  const int Hfull = up2 ? 2 * H : H, Wfull = up2 ? 2 * W : W;
+  if (p->cfg.precision == HVIT_PREC_BF16) {
+    q.K = (up2 ? 4 : 9) * Cin;
+    q.pool = pool;
+    q.out_f32 = 0;
+    q.Ho = pool ? H / 2 : Hfull;
+    q.Wo = pool ? W / 2 : Wfull;
+    q.HoPitch = HoPitch;
+    if (pool) {
+      q.Wt = 16; q.Ht = 8;
+    } else {
+      pick_tile(H, W, &q.Wt, &q.Ht);
+    }
+    q.tiles_w = (W + q.Wt - 1) / q.Wt;
+    q.tiles_h = (H + q.Ht - 1) / q.Ht;
+    CUtensorMap ta, tb;
+    const int bn = pick_block_n(Cout);
+    int r = tmap_image(&ta, in, B, H, H, W, Cin, q.Wt, q.Ht);
+    if (r) return r;
+    r = tmap_matrix(&tb, Wt, static_cast<long long>(up2 ? 4 : 1) * Cout, q.K, q.K, bn);
+    if (r) return r;
+    const int sms = num_sms();
+    p->steps.push_back([=](const Ctx& c) { return launch_igemm_tc(q, ta, tb, bn, sms, c.stream); });
+  } else {
+    q.K = 9 * Cin;
+    q.out_f32 = 1;
+    q.Ho = Hfull; q.Wo = Wfull;
+    const float* inf = reinterpret_cast<const float*>(in);
+    const float* wf = reinterpret_cast<const float*>(Wt);
+    if (pool) {
+      q.out = conv_tmp; q.ldc = Cout; q.HoPitch = Hfull;
+      float* dst = reinterpret_cast<float*>(out);
+      p->steps.push_back([=](const Ctx& c) { return launch_igemm_f32(q, inf, Cin, wf, c.stream); });
+      p->steps.push_back([=](const Ctx& c) { return launch_maxpool2(conv_tmp, dst, B, H, W, Cout, c.stream); });
+    } else {
+      q.HoPitch = HoPitch;
+      p->steps.push_back([=](const Ctx& c) { return launch_igemm_f32(q, inf, Cin, wf, c.stream); });
+    }
+  }
+  return HVIT_OK;
+}
+
+static int build_steps(hvit_plan* p) {
+  const hvit_model_cfg& c = p->cfg;
+  const hvit_weights& w = p->w;
+  const Geometry& g = p->g;
+  const int bf = c.precision == HVIT_PREC_BF16 ? 1 : 0;
+  const int B = g.B, D = c.embed_dim;
+  char nm[32], nm2[32];
+  int r;
+
+  // 1. stem (encoder block 0): Conv3x3(1->C0)+BN+ReLU(+pool), CUDA cores, reads the fp32 spectrogram directly
+  {
+    void* out = at<void>(p, "enc0");
+    const int C0 = c.enc_channels[0], pool = c.enc_pool[0], F = g.F, T = g.T;
+    const float *sw = w.stem_w, *ss = w.stem_scale, *sh = w.stem_shift;
+    p->steps.push_back([=](const Ctx& k) { return launch_stem(k.x, k.mag_max, sw, ss, sh, out, bf, B, F, T, C0, pool, k.stream); });
+  }
+  // 2. encoder blocks 1.. : implicit-GEMM 3x3 conv + folded BN + ReLU (+ fused 2x2 max-pool)
+  float* conv_tmp = g.bufs.count("conv_tmp") ? at<float>(p, "conv_tmp") : nullptr;
+  for (int i = 1; i < c.n_enc; ++i) {
+    snprintf(nm, sizeof(nm), "enc%d", i - 1);
+    snprintf(nm2, sizeof(nm2), "enc%d", i);
+    const EncGeo& s = g.enc[i - 1];
+    const EncGeo& d = g.enc[i];
+    r = add_conv(p, at<void>(p, nm), B, s.H, s.W, s.C, w.enc_w[i], w.enc_scale[i], w.enc_shift[i], 1,
+                 c.enc_pool[i] == 2, 0, at<void>(p, nm2), d.C, d.pitch, d.C, conv_tmp);
+    if (r) return r;
+  }
+  // 3. patch embedding (+bias +positional embedding) -> fp32 residual stream
+  {
+    const EncGeo& e = g.enc[c.n_enc - 1];
+    snprintf(nm, sizeof(nm), "enc%d", c.n_enc - 1);
+    IgemmParams q = ig_zero();
+    q.mode = IG_PATCH;
+    q.B = B; q.H = e.H; q.W = e.W; q.Cin = e.C;
+    q.patch = c.patch_size; q.Hq = e.pitch / c.patch_size; q.Hp = g.Hp; q.Wp = g.Wp;
+    q.N = D; q.K = c.patch_size * c.patch_size * e.C;
+    q.shift = w.patch_b; q.residual = w.pos_embed; q.ldr = D; q.res_mod = g.Np;
+    q.out = at<void>(p, "tokens"); q.ldc = D; q.out_f32 = 1;
+    const void* in = at<void>(p, nm);
+    if (bf) {
+      pick_tile(g.Hp, g.Wp, &q.Wt, &q.Ht);
+      q.tiles_w = (g.Wp + q.Wt - 1) / q.Wt;
+      q.tiles_h = (g.Hp + q.Ht - 1) / q.Ht;
+      CUtensorMap ta, tb;
+      const int bn = pick_block_n(D);
+      r = tmap_patch(&ta, in, B, q.Hq, e.W, e.C, c.patch_size, g.Wp, q.Wt, q.Ht);
+      if (r) return r;
+      r = tmap_matrix(&tb, w.patch_w, D, q.K, q.K, bn);
+      if (r) return r;
+      const int sms = num_sms();
+      p->steps.push_back([=](const Ctx& k) { return launch_igemm_tc(q, ta, tb, bn, sms, k.stream); });
+    } else {
+      const float* inf = reinterpret_cast<const float*>(in);
+      const float* wf = reinterpret_cast<const float*>(w.patch_w);
+      const int lda = e.C;
+      p->steps.push_back([=](const Ctx& k) { return launch_igemm_f32(q, inf, lda, wf, k.stream); });
+    }
+  }
+  // 4. transformer blocks (pre-norm), residual stream fp32
+  float* tok = at<float>(p, "tokens");
+  void* ln = at<void>(p, "ln");
+  void* qkv = at<void>(p, "qkv");
+  void* att = at<void>(p, "attn");
+  void* mlp = at<void>(p, "mlp");
+  const int M = g.M, Np = g.Np, heads = c.num_heads;
+  const float scale = 0.125f;  // head_dim^-0.5 with head_dim = 64
+  const float eps = c.ln_eps;
+  CUtensorMap tq;
+  if (bf && c.num_layers > 0) {
+    r = tmap_qkv(&tq, qkv, B, Np, D);
+    if (r) return r;
+  }
+  for (int l = 0; l < c.num_layers; ++l) {
+    const float *g1 = w.ln1_g[l], *b1 = w.ln1_b[l], *g2 = w.ln2_g[l], *b2 = w.ln2_b[l];
+    p->steps.push_back([=](const Ctx& k) { return launch_layernorm(tok, g1, b1, ln, bf, M, D, eps, k.stream); });
+    r = add_linear(p, ln, D, w.qkv_w[l], w.qkv_b[l], ACT_NONE, nullptr, 0, 0, qkv, 3 * D, !bf, M, 3 * D, D);
+    if (r) return r;
+    const size_t probs_off = static_cast<size_t>(l) * B * heads * Np * Np;
+    if (bf) {
+      p->steps.push_back([=](const Ctx& k) {
+        if (k.probs != nullptr) {
+          const int e = launch_attn_probs_bf16(qkv, k.probs + probs_off, B, Np, heads, D, scale, k.stream);
+          if (e) return e;
+        }
+        return launch_attn_tc(tq, att, B, Np, heads, D, scale, k.stream);
+      });
+    } else {
+      p->steps.push_back([=](const Ctx& k) {
+        return launch_attn_f32(reinterpret_cast<const float*>(qkv), reinterpret_cast<float*>(att),
+                               k.probs != nullptr ? k.probs + probs_off : nullptr, B, Np, heads, D, scale, k.stream);
+      });
+    }
+    r = add_linear(p, att, D, w.proj_w[l], w.proj_b[l], ACT_NONE, tok, D, 0, tok, D, 1, M, D, D);
+    if (r) return r;
+    p->steps.push_back([=](const Ctx& k) { return launch_layernorm(tok, g2, b2, ln, bf, M, D, eps, k.stream); });
+    r = add_linear(p, ln, D, w.fc1_w[l], w.fc1_b[l], ACT_GELU, nullptr, 0, 0, mlp, c.mlp_hidden, !bf, M, c.mlp_hidden, D);
+    if (r) return r;
+    r = add_linear(p, mlp, c.mlp_hidden, w.fc2_w[l], w.fc2_b[l], ACT_NONE, tok, D, 0, tok, D, 1, M, D, c.mlp_hidden);
+    if (r) return r;
+  }
+  // 5. final LayerNorm + to_feature_map, written straight into the first decoder concat buffer (NHWC == [B,N,C])
+  {
+    const float *gf = w.lnf_g, *bfp = w.lnf_b;
+    p->steps.push_back([=](const Ctx& k) { return launch_layernorm(tok, gf, bfp, ln, bf, M, D, eps, k.stream); });
+    const CatGeo& k0 = g.cat[0];
+    r = add_linear(p, ln, D, w.tofm_w, w.tofm_b, ACT_NONE, nullptr, 0, 0, at<void>(p, "cat0"), k0.Ccat, !bf, M, k0.Cx, D);
+    if (r) return r;
+  }
+  // 6. decoder blocks with skip connections
+  for (int i = 0; i + 1 < c.n_dec; ++i) {
+    const CatGeo& k = g.cat[i];
+    const CatGeo& kn = g.cat[i + 1];
+    snprintf(nm, sizeof(nm), "cat%d", i);
+    snprintf(nm2, sizeof(nm2), "cat%d", i + 1);
+    uint8_t* cat = at<uint8_t>(p, nm);
+    if (k.Ccat > k.Cx) {
+      const int ei = c.n_enc - 1 - i;
+      const EncGeo& e = g.enc[ei];
+      char en[32];
+      snprintf(en, sizeof(en), "enc%d", ei);
+      const void* src = at<void>(p, en);
+      void* samp = at<void>(p, "samp");
+      const int Hs = e.H, Hpit = e.pitch, Ws = e.W, Cs = e.C, Hd = k.H, Wd = k.W;
+      p->steps.push_back([=](const Ctx& x) { return launch_skip_sample(src, bf, B, Hs, Hpit, Ws, Cs, Hd, Wd, samp, x.stream); });
+      r = add_linear(p, samp, Cs, w.skip_w[i], w.skip_b[i], ACT_NONE, nullptr, 0, 0, cat + static_cast<size_t>(k.Cx) * g.es,
+                     k.Ccat, !bf, B * Hd * Wd, c.dec_channels[i], Cs);
+      if (r) return r;
+    }
+    r = add_conv(p, cat, B, k.H, k.W, k.Ccat, w.dec_w[i], w.dec_scale[i], w.dec_shift[i], 1, 0, c.dec_up[i] == 2,
+                 at<void>(p, nm2), kn.Ccat, kn.H, c.dec_channels[i], nullptr);
+    if (r) return r;
+  }
+  // 7. head conv + tanh, bilinear resize back to [F, T]
+  {
+    const CatGeo& k = g.cat[c.n_dec - 1];
+    snprintf(nm, sizeof(nm), "cat%d", c.n_dec - 1);
+    const void* in = at<void>(p, nm);
+    float* logits = at<float>(p, "logits");
+    float* th = at<float>(p, "tanh");
+    const float* hw = w.head_w;
+    const int H = k.H, W = k.W, C = k.Ccat, F = g.F, T = g.T;
+    p->steps.push_back([=](const Ctx& x) { return launch_head(in, bf, hw, B, H, W, C, logits, th, x.stream); });
+    p->steps.push_back([=](const Ctx& x) { return launch_resize(th, B, H, W, x.y, F, T, x.stream); });
+  }
+  p->launches_forward = static_cast<int>(p->steps.size());
+  return HVIT_OK;
+}
+
+}  // namespace hvit
+
+// ============================================================================================== C ABI
+using namespace hvit;
+
+extern "C" {
+
+const char* hvit_last_error(void) { return g_err; }
+int hvit_version(void) { return 100; }
+
+int hvit_device_ok(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+    set_error("no usable CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+    return HVIT_E_LAUNCH;
+  }
+  return major == 10 ? 1 : 0;
+}
+
+size_t hvit_workspace_bytes(const hvit_model_cfg* cfg, int B, int F, int T, int n_samples) {
+  if (cfg == nullptr) {
+    set_error("null cfg");
+    return 0;
+  }
+  Geometry g;
+  if (build_geometry(*cfg, B, F, T, n_samples, 0, g) != HVIT_OK) return 0;
+  return g.total;
+}
+
+int hvit_plan_create(const hvit_model_cfg* cfg, const hvit_weights* weights, int B, int F, int T, int n_samples,
+                     void* workspace_dev, size_t workspace_bytes, hvit_plan** plan_out) {
+  if (cfg == nullptr || weights == nullptr || workspace_dev == nullptr || plan_out == nullptr) {
+    set_error("hvit_plan_create: null argument");
+    return HVIT_E_ARG;
+  }
+  const int ok = hvit_device_ok();
+  if (ok < 0) return ok;
+  if (ok == 0) {
+    set_error("this library only runs on sm_100 (B200); there is no fallback path");
+    return HVIT_E_ARCH;
+  }
+  hvit_plan* p = new hvit_plan();
+  p->cfg = *cfg;
+  p->w = *weights;
+  p->ws = reinterpret_cast<uint8_t*>(workspace_dev);
+  int r = build_geometry(*cfg, B, F, T, n_samples, weights->pos_len, p->g);
+  if (r == HVIT_OK && (p->g.total > workspace_bytes || (reinterpret_cast<uintptr_t>(workspace_dev) & 1023) != 0)) {
+    set_error("workspace too small or not 1024-byte aligned: need %zu bytes, got %zu", p->g.total, workspace_bytes);
+    r = HVIT_E_ALLOC;
+  }
+  if (r == HVIT_OK) r = build_steps(p);
+  if (r != HVIT_OK) {
+    delete p;
+    return r;
+  }
+  *plan_out = p;
+  return HVIT_OK;
+}
+
+void hvit_plan_destroy(hvit_plan* plan) { delete plan; }
+
+static int run_steps(hvit_plan* p, const Ctx& c) {
+  for (size_t i = 0; i < p->steps.size(); ++i) {
+    const int r = p->steps[i](c);
+    if (r != HVIT_OK) return r;
+  }
+  return HVIT_OK;
+}
+
+int hvit_forward(hvit_plan* plan, const float* x_dev, float* y_dev, float* attn_probs_dev, void* stream) {
+  if (plan == nullptr || x_dev == nullptr || y_dev == nullptr) {
+    set_error("hvit_forward: null argument");
+    return HVIT_E_ARG;
+  }
+  Ctx c;
+  c.x = x_dev; c.y = y_dev; c.probs = attn_probs_dev; c.mag_max = nullptr;
+  c.stream = reinterpret_cast<cudaStream_t>(stream);
+  return run_steps(plan, c);
+}
+
+int hvit_enhance(hvit_plan* plan, const float* wave_in_dev, float* wave_out_dev, int normalize, void* stream) {
+  if (plan == nullptr || wave_in_dev == nullptr || wave_out_dev == nullptr) {
+    set_error("hvit_enhance: null argument");
+    return HVIT_E_ARG;
+  }
+  if (plan->g.n_samples <= 0) {
+    set_error("hvit_enhance: plan was created without n_samples");
+    return HVIT_E_ARG;
+  }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const Geometry& g = plan->g;
+  float* max_val = at<float>(plan, "max_val");
+  unsigned* mag_max = at<unsigned>(plan, "mag_max");
+  float2* spec = at<float2>(plan, "spec");
+  float* mag = at<float>(plan, "mag");
+  float* mo = at<float>(plan, "model_out");
+  int r = launch_peak(wave_in_dev, g.B, g.n_samples, max_val, normalize, s);
+  if (r) return r;
+  r = launch_stft(wave_in_dev, g.B, g.n_samples, g.T, max_val, spec, mag, mag_max, s);
+  if (r) return r;
+  Ctx c;
+  c.x = mag; c.y = mo; c.probs = nullptr; c.mag_max = mag_max; c.stream = s;
+  r = run_steps(plan, c);
+  if (r) return r;
+  return launch_istft(mo, spec, mag_max, max_val, at<float>(plan, "frames"), wave_out_dev, g.B, g.n_samples, g.T, s);
+}
+
+int hvit_plan_buffer(const hvit_plan* plan, const char* name, size_t* offset, int* dims, int* elem_bytes) {
+  if (plan == nullptr || name == nullptr) return HVIT_E_ARG;
+  auto it = plan->g.bufs.find(name);
+  if (it == plan->g.bufs.end()) {
+    set_error("no such buffer: %s", name);
+    return HVIT_E_ARG;
+  }
+  if (offset) *offset = it->second.off;
+  if (dims) memcpy(dims, it->second.dims, sizeof(int) * 4);
+  if (elem_bytes) *elem_bytes = it->second.es;
+  return it->second.rank;
+}
+
+int hvit_plan_launch_count(const hvit_plan* plan, int enhance) {
+  if (plan == nullptr) return HVIT_E_ARG;
+  int n = plan->launches_forward;
+  if (plan->cfg.precision != HVIT_PREC_BF16) {
+    // pooled fp32 convs are two launches but already counted as two steps
+  }
+  if (enhance) n += 2 /*peak*/ + 2 /*stft*/ + 2 /*istft*/;
+  return n;
+}
+
+int hvit_plan_tokens(const hvit_plan* plan, int* hp, int* wp) {
+  if (plan == nullptr) return HVIT_E_ARG;
+  if (hp) *hp = plan->g.Hp;
+  if (wp) *wp = plan->g.Wp;
+  return plan->g.Np;
+}
+
+// ---------------------------------------------------------------------------------------- per-kernel entry points
+static int require_sm100() {
+  const int ok = hvit_device_ok();
+  if (ok < 0) return ok;
+  if (ok == 0) {
+    set_error("this library only runs on sm_100 (B200); there is no fallback path");
+    return HVIT_E_ARCH;
+  }
+  return HVIT_OK;
+}
+
+int hvit_gemm_bf16(const void* a, int lda, const void* w, const float* scale, const float* shift, int act,
+                   const float* residual, int ldr, void* out, int ldc, int out_f32, int M, int N, int K, void* stream) {
+  int r = require_sm100();
+  if (r) return r;
+  IgemmParams q = ig_zero();
+  q.mode = IG_PLAIN;
+  q.M = M; q.N = N; q.K = K;
+  q.scale = scale; q.shift = shift; q.act = act; q.residual = residual; q.ldr = ldr;
+  q.out = out; q.ldc = ldc; q.out_f32 = out_f32;
+  CUtensorMap ta, tb;
+  const int bn = pick_block_n(N);
+  r = tmap_matrix(&ta, a, M, K, lda, 128);
+  if (r) return r;
+  r = tmap_matrix(&tb, w, N, K, K, bn);
+  if (r) return r;
+  return launch_igemm_tc(q, ta, tb, bn, num_sms(), reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hvit_gemm_f32(const float* a, int lda, const float* w, const float* scale, const float* shift, int act,
+                  const float* residual, int ldr, float* out, int ldc, int M, int N, int K, void* stream) {
+  int r = require_sm100();
+  if (r) return r;
+  IgemmParams q = ig_zero();
+  q.mode = IG_PLAIN;
+  q.M = M; q.N = N; q.K = K;
+  q.scale = scale; q.shift = shift; q.act = act; q.residual = residual; q.ldr = ldr;
+  q.out = out; q.ldc = ldc; q.out_f32 = 1;
+  return launch_igemm_f32(q, a, lda, w, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hvit_conv3x3_bf16(const void* x, const void* w, const float* scale, const float* shift, int relu, int pool,
+                      int up2, void* out, int B, int H, int W, int Cin, int Cout, void* stream) {
+  int r = require_sm100();
+  if (r) return r;
+  if (pool && up2) {
+    set_error("conv3x3: pool and up2 are exclusive");
+    return HVIT_E_SHAPE;
+  }
+  hvit_plan tmp;
+  tmp.cfg.precision = HVIT_PREC_BF16;
+  const int Ho = pool ? H / 2 : (up2 ? 2 * H : H);
+  r = add_conv(&tmp, x, B, H, W, Cin, w, scale, shift, relu, pool, up2, out, Cout, Ho, Cout, nullptr);
+  if (r) return r;
+  Ctx c;
+  memset(&c, 0, sizeof(c));
+  c.stream = reinterpret_cast<cudaStream_t>(stream);
+  return tmp.steps[0](c);
+}
+
+int hvit_conv3x3_f32(const float* x, const float* w, const float* scale, const float* shift, int relu, int up2,
+                     float* out, int B, int H, int W, int Cin, int Cout, void* stream) {
+  int r = require_sm100();
+  if (r) return r;
+  hvit_plan tmp;
+  tmp.cfg.precision = HVIT_PREC_FP32;
+  r = add_conv(&tmp, x, B, H, W, Cin, w, scale, shift, relu, 0, up2, out, Cout, up2 ? 2 * H : H, Cout, nullptr);
+  if (r) return r;
+  Ctx c;
+  memset(&c, 0, sizeof(c));
+  c.stream = reinterpret_cast<cudaStream_t>(stream);
+  return tmp.steps[0](c);
+}
+
+int hvit_attention_bf16(const void* qkv, void* out, int B, int N, int heads, void* stream) {
+  int r = require_sm100();
+  if (r) return r;
+  CUtensorMap tq;
+  r = tmap_qkv(&tq, qkv, B, N, heads * 64);
+  if (r) return r;
+  return launch_attn_tc(tq, out, B, N, heads, heads * 64, 0.125f, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hvit_attention_f32(const float* qkv, float* out, float* probs, int B, int N, int heads, void* stream) {
+  int r = require_sm100();
+  if (r) return r;
+  return launch_attn_f32(qkv, out, probs, B, N, heads, heads * 64, 0.125f, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hvit_layernorm(const float* x, const float* g, const float* b, void* out, int out_bf16, int rows, int D, float eps,
+                   void* stream) {
+  int r = require_sm100();
+  if (r) return r;
+  return launch_layernorm(x, g, b, out, out_bf16, rows, D, eps, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hvit_stft(const float* wave, int B, int n, int normalize, void* max_val, void* spec, float* mag, void* mag_max,
+              void* stream) {
+  int r = require_sm100();
+  if (r) return r;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  r = launch_peak(wave, B, n, reinterpret_cast<float*>(max_val), normalize, s);
+  if (r) return r;
+  return launch_stft(wave, B, n, 1 + n / 128, reinterpret_cast<const float*>(max_val), reinterpret_cast<float2*>(spec),
+                     mag, reinterpret_cast<unsigned*>(mag_max), s);
+}
+
+int hvit_istft(const float* mag_norm, const void* spec, const void* mag_max, const void* max_val, float* frames,
+               float* wave_out, int B, int n, void* stream) {
+  int r = require_sm100();
+  if (r) return r;
+  return launch_istft(mag_norm, reinterpret_cast<const float2*>(spec), reinterpret_cast<const unsigned*>(mag_max),
+                      reinterpret_cast<const float*>(max_val), frames, wave_out, B, n, 1 + n / 128,
+                      reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

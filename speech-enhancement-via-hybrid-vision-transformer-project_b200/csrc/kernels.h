@@ -1,0 +1,92 @@
+// Internal launcher interface shared by the .cu translation units of libhvit_sm100.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hvit {
+
+// ---------------------------------------------------------------------------------------------
+// Implicit-GEMM problem description (used by both the tcgen05 bf16 kernel and the fp32 SIMT kernel)
+//   C[m, n] = epilogue( sum_k A(m, k) * Wt[n, k] )
+// A-operand addressing modes (activations are NHWC):
+//   IG_PLAIN : A is a row-major [M, K] matrix
+//   IG_CONV3 : 3x3 / pad 1 convolution, k = (ky*3+kx)*Cin + c, m = output pixel
+//   IG_UP2   : nearest x2 upsample followed by 3x3 / pad 1 conv, evaluated as four 2x2 convolutions on the
+//              low-resolution input (one per output parity class) with pre-summed weights;
+//              k = (a*2+b)*Cin + c, weight rows [parity*N + n]
+//   IG_PATCH : p x p / stride p convolution (patch embedding), k = (ky*p+kx)*Cin + c, m = token
+// ---------------------------------------------------------------------------------------------
+enum { IG_PLAIN = 0, IG_CONV3 = 1, IG_UP2 = 2, IG_PATCH = 3 };
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+
+struct IgemmParams {
+  int mode;
+  int M, N, K;          // IG_PLAIN: M rows. All modes: N output channels, K reduction length
+  // conv geometry (input image, NHWC, channel stride == lda)
+  int B, H, W, Cin;
+  int Hq;               // IG_PATCH: rows of patch positions per image in the (padded) input buffer = Hpad / p
+  int patch;            // IG_PATCH: patch size p
+  int Hp, Wp;           // IG_PATCH: valid patch grid
+  int Wt, Ht;           // spatial tile (Wt * Ht == 128)
+  int tiles_w, tiles_h;
+  // epilogue
+  const float* scale;   // [N] or null (== 1)
+  const float* shift;   // [N] or null (== 0): folded BN shift or linear bias
+  int act;
+  const float* residual;  // fp32 [*, ldr] added after activation, or null
+  int ldr;
+  int res_mod;          // > 0: residual row = out_row % res_mod (positional-embedding table)
+  int pool;             // 1: fused 2x2 max-pool (IG_CONV3 only)
+  void* out;
+  int ldc;              // elements between consecutive output rows
+  int out_f32;          // 1: fp32 output, 0: bf16 output
+  int Ho, Wo;           // valid output image dims (conv modes)
+  int HoPitch;          // image row pitch of the output buffer in pixel rows (>= Ho)
+};
+
+// tcgen05 path. A / Wt are described by TMA tensor maps built on the host (see tmap.cpp).
+int launch_igemm_tc(const IgemmParams& p, const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, int block_n,
+                    int num_sms, cudaStream_t stream);
+
+// fp32 SIMT path (precision = fp32 mode, also the on-device cross-check of the tcgen05 kernels).
+// A and Wt are fp32; for IG_UP2 the weights are the ORIGINAL 3x3 weights [N, 9*Cin] (direct y//2 gather).
+int launch_igemm_f32(const IgemmParams& p, const float* A, int lda, const float* Wt, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
+// Attention. qkv: [B*N, 3*D] (q | k | v, head h at columns h*64 .. h*64+63 of each third), out: [B*N, D].
+// ---------------------------------------------------------------------------------------------
+int launch_attn_tc(const CUtensorMap& tmap_qkv, void* out_bf16, int B, int N, int heads, int D, float scale,
+                   cudaStream_t stream);
+int launch_attn_f32(const float* qkv, float* out, float* probs /*nullable [B,h,N,N]*/, int B, int N, int heads, int D,
+                    float scale, cudaStream_t stream);
+// probabilities only (return_attentions=True slow path) from bf16 qkv
+int launch_attn_probs_bf16(const void* qkv_bf16, float* probs, int B, int N, int heads, int D, float scale,
+                           cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
+// Bandwidth-bound glue kernels.  `T` is selected by `act_bf16` (1: bf16 activations, 0: fp32).
+// ---------------------------------------------------------------------------------------------
+int launch_peak(const float* wave, int B, int n, float* max_val /*[B]*/, int normalize, cudaStream_t s);
+int launch_stft(const float* wave, int B, int n, int T, const float* max_val, float2* spec /*[B,257,T]*/,
+                float* mag /*[B,257,T]*/, unsigned* mag_max_bits /*[B]*/, cudaStream_t s);
+int launch_istft(const float* model_out /*[B,257,T] in [-1,1]*/, const float2* spec, const unsigned* mag_max_bits,
+                 const float* max_val, float* frames /*[B,T,512] scratch*/, float* wave_out, int B, int n, int T,
+                 cudaStream_t s);
+int launch_stem(const float* x /*[B,H,W]*/, const unsigned* mag_max_bits /*nullable*/, const float* w /*[9][C]*/,
+                const float* scale, const float* shift, void* out, int act_bf16, int B, int H, int W, int C, int pool,
+                cudaStream_t s);
+int launch_layernorm(const float* x, const float* g, const float* b, void* out, int act_bf16, int rows, int D,
+                     float eps, cudaStream_t s);
+int launch_skip_sample(const void* src, int act_bf16, int B, int Hs, int HsPitch, int Ws, int C, int Hd, int Wd,
+                       void* dst, cudaStream_t s);
+int launch_head(const void* x, int act_bf16, const float* w /*[9][C]*/, int B, int H, int W, int C, float* logits,
+                float* out_tanh, cudaStream_t s);
+int launch_resize(const float* src, int B, int Hs, int Ws, float* dst, int Hd, int Wd, cudaStream_t s);
+int launch_maxpool2(const float* src, float* dst, int B, int H, int W, int C, cudaStream_t s);
+
+// error plumbing (api.cu)
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+}  // namespace hvit

@@ -1,0 +1,213 @@
+"""-m gpu: the product path (hvit_b200.HybridViT.forward / AudioEnhancer.enhance -> C ABI -> CUDA kernels)
+against the CPU oracle on the same seeded weights and clips, and against the golden fixtures produced by the
+reference itself.  Tolerances are the north star's: max-rel spectrogram error <= 1e-4 (fp32 mode), <= 1e-2 (bf16),
+SI-SDR delta <= 0.05 dB."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TINY = dict(encoder_channels=[64, 64, 128], embed_dim=128, num_heads=2, num_layers=2, decoder_channels=[128, 64, 64, 1])
+TOL = {"fp32": 1e-4, "bf16": 1e-2}
+
+
+def _model(oracle, over, seed, precision):
+    from hvit_b200.models import HybridViT
+    cfg = oracle.full_cfg(over)
+    sd = oracle.make_state_dict(cfg, seed=seed)
+    kw = {k: cfg[k] for k in ("encoder_channels", "embed_dim", "num_heads", "num_layers", "decoder_channels")}
+    m = HybridViT(precision=precision, **kw)
+    m.load_state_dict(sd, strict=True)
+    return cfg, sd, m.cuda().eval()
+
+
+def _nchw(buf, H=None, C=None):
+    t = buf.float()
+    if H is not None:
+        t = t[:, :H]
+    if C is not None:
+        t = t[..., :C]
+    return t.permute(0, 3, 1, 2).cpu()
+
+
+def _stage_report(oracle, model, plan, stages, cfg):
+    """per-stage rms-rel error of the internal buffers vs the oracle's stages (diagnosis aid)."""
+    rep = {}
+    n_enc, n_dec = len(cfg["encoder_channels"]), len(cfg["decoder_channels"])
+    for i in range(n_enc):
+        ref = stages[f"encoder.{i}"]
+        rep[f"encoder.{i}"] = oracle.rms_rel_err(_nchw(plan.buffer(f"enc{i}"), H=ref.shape[2]).numpy(), ref.numpy())
+    L = cfg["num_layers"]
+    ref = stages[f"transformer.blocks.{L - 1}"]
+    rep["transformer.last_block"] = oracle.rms_rel_err(plan.buffer("tokens").float().cpu().view(ref.shape).numpy(), ref.numpy())
+    ref = stages["transformer"]
+    rep["transformer.norm"] = oracle.rms_rel_err(plan.buffer("ln").float().cpu().view(ref.shape).numpy(), ref.numpy())
+    ref = stages["to_feature_map"]
+    rep["to_feature_map"] = oracle.rms_rel_err(_nchw(plan.buffer("cat0"), C=ref.shape[1]).numpy(), ref.numpy())
+    for i in range(n_dec - 1):
+        ref = stages[f"decoder.{i}"]
+        rep[f"decoder.{i}"] = oracle.rms_rel_err(_nchw(plan.buffer(f"cat{i + 1}"), C=ref.shape[1]).numpy(), ref.numpy())
+    ref = stages[f"decoder.{n_dec - 1}.pre_tanh"]
+    rep["head.pre_tanh"] = oracle.rms_rel_err(plan.buffer("logits").cpu().numpy(), ref[:, 0].numpy())
+    return rep
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name,over,shape", [("tiny", TINY, (2, 1, 257, 63)), ("tiny_odd", TINY, (1, 1, 257, 90)),
+                                             ("default", {}, (2, 1, 257, 126)), ("default_4s", {}, (1, 1, 257, 501))])
+def test_forward_matches_oracle(oracle, precision, name, over, shape):
+    cfg, sd, model = _model(oracle, over, seed=21, precision=precision)
+    x = torch.rand(*shape, generator=torch.Generator().manual_seed(1))
+    stages = {}
+    with torch.no_grad():
+        ref = oracle.hybrid_vit_forward(sd, x, cfg, stages=stages)
+    y = model(x.cuda())
+    torch.cuda.synchronize()
+    plan = model.plan_for(shape[0], shape[2], shape[3])
+    rep = _stage_report(oracle, model, plan, stages, cfg)
+    print(f"\n[{name}/{precision}] per-stage rms-rel:", {k: f"{v:.2e}" for k, v in rep.items()})
+    err = oracle.max_rel_err(y.cpu().numpy(), ref.numpy())
+    print(f"[{name}/{precision}] output max-rel {err:.3e}  (std of ref output {float(ref.std()):.3f})")
+    assert y.shape == x.shape and y.dtype == torch.float32
+    stage_tol = 2e-5 if precision == "fp32" else 2e-2
+    for k, v in rep.items():
+        assert v < stage_tol, (k, v)
+    assert err <= TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_return_attentions(oracle, precision):
+    cfg, sd, model = _model(oracle, TINY, seed=5, precision=precision)
+    x = torch.rand(2, 1, 257, 70, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        ref, rattn = oracle.hybrid_vit_forward(sd, x, cfg, return_attentions=True)
+    y, attn = model(x.cuda(), return_attentions=True)
+    assert len(attn) == cfg["num_layers"] and attn[0].shape == rattn[0].shape
+    for a, r in zip(attn, rattn):
+        assert float((a.cpu() - r).abs().max()) < (1e-5 if precision == "fp32" else 5e-3)
+        assert torch.allclose(a.sum(-1).cpu(), torch.ones(a.shape[:-1]), atol=1e-4)
+    assert oracle.max_rel_err(y.cpu().numpy(), ref.numpy()) <= TOL[precision]
+    y2 = model(x.cuda())
+    assert torch.equal(y, y2)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["tiny_0p5s", "tiny_ragged", "default_1s", "default_2s"])
+def test_enhance_matches_reference_golden(oracle, golden, precision, name):
+    """AudioEnhancer.enhance vs the waveform the reference's own enhancer produced (tests/golden)."""
+    from hvit_b200.inference import AudioEnhancer
+    arrays, meta = golden
+    m = meta[name]
+    cfg, sd, model = _model(oracle, m["cfg"], seed=m["weight_seed"], precision=precision)
+    assert oracle.state_dict_digest(sd) == m["weights_sha256"]
+    clean, noisy = oracle.synth_clip(seconds=m["seconds"] or 1.0, seed=m["clip_seed"], n_samples=m["n_samples"])
+    enh = AudioEnhancer(model, device="cuda")
+    y = enh.enhance(noisy, normalize=True)
+    ref_y = arrays[f"{name}/waveform"]
+    assert y.shape == ref_y.shape and y.dtype == np.float32
+    # enhanced magnitude spectrogram (de-normalised): ours vs reference
+    n = len(noisy)
+    plan = model.plan_for(1, 257, 1 + n // 128, n_samples=n)
+    ours_mag = plan.buffer("model_out")[0].cpu().numpy()
+    ref_mag = arrays[f"{name}/model_out"]
+    err = oracle.max_rel_err(ours_mag, ref_mag)
+    d_sisdr = abs(oracle.si_sdr(clean, y) - m["sisdr_clean_vs_ref"])
+    print(f"\n[{name}/{precision}] spectrogram max-rel {err:.3e}  waveform max-rel {oracle.max_rel_err(y, ref_y):.3e} "
+          f" dSI-SDR {d_sisdr:.4f} dB  SI-SDR(ref,ours) {oracle.si_sdr(ref_y, y):.1f} dB")
+    assert err <= TOL[precision]
+    assert oracle.max_rel_err(y, ref_y) <= TOL[precision] * 2
+    assert d_sisdr <= 0.05
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_enhance_edge_cases(oracle, precision):
+    from hvit_b200.inference import AudioEnhancer
+    cfg, sd, model = _model(oracle, TINY, seed=3, precision=precision)
+    enh = AudioEnhancer(model, device="cuda")
+    # all-zero clip: both "<= 1e-8 -> 1.0" guards fire (reference enhancer.py:74-79,97-101)
+    z = np.zeros(4096, dtype=np.float32)
+    y = enh.enhance(z)
+    ref = oracle.enhance(sd, z, cfg)
+    assert np.isfinite(y).all() and np.abs(y - ref).max() <= 1e-5 + TOL[precision] * np.abs(ref).max()
+    # single impulse, normalize=False, n not a multiple of the hop
+    imp = np.zeros(5000, dtype=np.float32)
+    imp[1234] = 0.7
+    y = enh.enhance(imp, normalize=False)
+    ref = oracle.enhance(sd, imp, cfg, normalize=False)
+    assert oracle.max_rel_err(y, ref) <= TOL[precision] * 2
+    with pytest.raises(ValueError):
+        enh.enhance(np.zeros(0, dtype=np.float32))
+    with pytest.raises(Exception):
+        enh.enhance(np.zeros(300, dtype=np.float32))   # too short for the 16x downsampling + 4x4 patches
+    # float64 input is accepted and cast
+    _, noisy = oracle.synth_clip(seconds=0.5, seed=9)
+    assert np.array_equal(enh.enhance(noisy.astype(np.float64)), enh.enhance(noisy))
+
+
+def test_batch_properties_bf16(oracle):
+    """Size-independent properties at a larger batch: clips are processed independently (batch == singles),
+    permutation equivariance, and peak-normalisation makes enhance() homogeneous of degree 1."""
+    from hvit_b200.inference import AudioEnhancer
+    cfg, sd, model = _model(oracle, {}, seed=2, precision="bf16")
+    enh = AudioEnhancer(model, device="cuda")
+    B, n = 8, 16000
+    clips = np.stack([oracle.synth_clip(seed=100 + i, n_samples=n)[1] for i in range(B)])
+    yb = enh.enhance_batch(clips)
+    perm = np.random.default_rng(0).permutation(B)
+    assert np.array_equal(enh.enhance_batch(clips[perm]), yb[perm])
+    for i in (0, 3, 7):
+        assert np.array_equal(enh.enhance(clips[i]), yb[i])
+    y2 = enh.enhance_batch(clips * 0.5)     # exact power-of-two scaling commutes with every rounding step
+    assert np.array_equal(y2, yb * 0.5)
+
+
+def test_headline_shape_runs_and_is_consistent(oracle):
+    """BASELINE.json configs[1]: default model, batch 64 x 4 s.  Parity through properties: batch rows equal the
+    single-clip results, and clip 0 matches the CPU oracle within the bf16 tolerance."""
+    from hvit_b200.inference import AudioEnhancer
+    cfg, sd, model = _model(oracle, {}, seed=0, precision="bf16")
+    enh = AudioEnhancer(model, device="cuda")
+    B, n = 64, 64000
+    clips = np.stack([oracle.synth_clip(seed=i, n_samples=n)[1] for i in range(B)])
+    yb = enh.enhance_batch(clips)
+    assert yb.shape == (B, n) and np.isfinite(yb).all()
+    assert np.array_equal(enh.enhance(clips[17]), yb[17])
+    dbg = {}
+    ref = oracle.enhance(sd, clips[0], cfg, debug=dbg)
+    plan = model.plan_for(B, 257, 501, n_samples=n)
+    err = oracle.max_rel_err(plan.buffer("model_out")[0].cpu().numpy(), dbg["model_out"])
+    print(f"\n[bs64 x 4s] clip-0 spectrogram max-rel {err:.3e}; waveform max-rel {oracle.max_rel_err(yb[0], ref):.3e}")
+    assert err <= TOL["bf16"]
+
+
+def test_widened_variant_runs(oracle):
+    """BASELINE.json configs[4] architecture (12 layers, 768-d, 12 heads) at a small batch."""
+    over = dict(embed_dim=768, num_heads=12, num_layers=12)
+    cfg, sd, model = _model(oracle, over, seed=4, precision="bf16")
+    x = torch.rand(1, 1, 257, 126, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        ref = oracle.hybrid_vit_forward(sd, x, cfg)
+    y = model(x.cuda())
+    assert oracle.max_rel_err(y.cpu().numpy(), ref.numpy()) <= TOL["bf16"]
+
+
+def test_model_guards(oracle):
+    from hvit_b200.models import HybridViT
+    cfg, sd, model = _model(oracle, TINY, seed=1, precision="bf16")
+    with pytest.raises(RuntimeError):
+        model.train()(torch.rand(1, 1, 257, 63).cuda())
+    model.eval()
+    with pytest.raises(RuntimeError):
+        model(torch.rand(1, 1, 257, 63))          # CPU tensor: no fallback
+    with pytest.raises(ValueError):
+        model(torch.rand(1, 2, 257, 63).cuda())
+    with pytest.raises(Exception):
+        model(torch.rand(1, 1, 257, 8).cuda())    # no patches
+    # weights changed in place -> repacked
+    x = torch.rand(1, 1, 257, 63).cuda()
+    y0 = model(x)
+    with torch.no_grad():
+        model.decoder[3].block[0].weight.mul_(0.5)
+    y1 = model(x)
+    assert not torch.equal(y0, y1)
