@@ -33,6 +33,8 @@ extern "C" {
 
 #define HVIT_PREC_FP32 0 /* fp32 CUDA-core arithmetic, fp32 activations (accuracy mode, <= 1e-4)           */
 #define HVIT_PREC_BF16 1 /* bf16 tcgen05 tensor-core contractions, fp32 accumulation / residual / statistics */
+#define HVIT_PREC_FP16 2 /* same kernels and tensor-core rate with fp16 operands / activations (3 more mantissa   */
+                         /* bits; saturating conversions) - the 16-bit mode that meets the 1e-2 parity bar        */
 
 #define HVIT_MAX_STAGES 8
 #define HVIT_MAX_LAYERS 48
@@ -52,9 +54,9 @@ typedef struct hvit_model_cfg {
 } hvit_model_cfg;
 
 /* Packed, device-resident weights (derived once from the reference state_dict; the
- * packing itself is host-side torch code in hvit_b200/models/packing.py).  "act" = bf16 in HVIT_PREC_BF16, fp32 in
+ * packing itself is host-side torch code in hvit_b200/models/packing.py).  "act" = bf16 / fp16 in HVIT_PREC_BF16 / HVIT_PREC_FP16, fp32 in
  * HVIT_PREC_FP32.  BatchNorm (eval) is folded into per-channel scale/shift.  Conv weights are [Cout][ky][kx][Cin].
- * In BF16 mode a decoder block with upsample 2 gets the four pre-summed 2x2 parity kernels [4][Cout][2][2][Cin];
+ * In the 16-bit modes a decoder block with upsample 2 gets the four pre-summed 2x2 parity kernels [4][Cout][2][2][Cin];
  * in FP32 mode it keeps the original [Cout][3][3][Cin]. */
 typedef struct hvit_weights {
   const float* stem_w;      /* [3][3][C0] fp32 */
@@ -132,27 +134,28 @@ int hvit_plan_tokens(const hvit_plan* plan, int* hp, int* wp);
 
 /* ---- per-kernel entry points (unit tests, microbenchmarks) ------------------------------------------------ */
 
-/* C[M,N] = act(A[M,K] * W[N,K]^T * scale[n] + shift[n]) (+ residual), bf16 operands on tcgen05.
- * nn.Linear (attention.py:83,109; components.py:223-229; hybrid_vit.py:343).  out is bf16 or fp32 (out_f32). */
-int hvit_gemm_bf16(const void* a_dev, int lda, const void* w_dev, const float* scale_dev, const float* shift_dev,
-                   int act, const float* residual_dev, int ldr, void* out_dev, int ldc, int out_f32, int M, int N,
-                   int K, void* stream);
+/* C[M,N] = act(A[M,K] * W[N,K]^T * scale[n] + shift[n]) (+ residual), 16-bit operands on tcgen05
+ * (f16 = 0: bf16, 1: fp16).  nn.Linear (attention.py:83,109; components.py:223-229; hybrid_vit.py:343).
+ * out is 16-bit (same type as the operands) or fp32 (out_f32). */
+int hvit_gemm_16(const void* a_dev, int lda, const void* w_dev, const float* scale_dev, const float* shift_dev,
+                 int act, const float* residual_dev, int ldr, void* out_dev, int ldc, int out_f32, int M, int N,
+                 int K, int f16, void* stream);
 /* Same contract on CUDA cores in fp32 (a, w, out fp32). */
 int hvit_gemm_f32(const float* a_dev, int lda, const float* w_dev, const float* scale_dev, const float* shift_dev,
                   int act, const float* residual_dev, int ldr, float* out_dev, int ldc, int M, int N, int K,
                   void* stream);
-/* 3x3 / pad 1 conv + per-channel scale/shift + ReLU (+ 2x2 max-pool) on NHWC bf16, tcgen05 implicit GEMM.
+/* 3x3 / pad 1 conv + per-channel scale/shift + ReLU (+ 2x2 max-pool) on NHWC bf16/fp16, tcgen05 implicit GEMM.
  * ConvBlock / TransposeConvBlock in eval mode (components.py:15-99,102-192).
  * up2 = 1: nearest x2 upsample first; w_dev then holds the four parity kernels [4][Cout][2][2][Cin]. */
-int hvit_conv3x3_bf16(const void* x_dev, const void* w_dev, const float* scale_dev, const float* shift_dev, int relu,
-                      int pool, int up2, void* out_dev, int B, int H, int W, int Cin, int Cout, void* stream);
+int hvit_conv3x3_16(const void* x_dev, const void* w_dev, const float* scale_dev, const float* shift_dev, int relu,
+                    int pool, int up2, void* out_dev, int B, int H, int W, int Cin, int Cout, int f16, void* stream);
 int hvit_conv3x3_f32(const float* x_dev, const float* w_dev, const float* scale_dev, const float* shift_dev,
                      int relu, int up2, float* out_dev, int B, int H, int W, int Cin, int Cout, void* stream);
 /* Multi-head self-attention core, head_dim 64 (attention.py:86-105). qkv: [B*N, 3D]; out: [B*N, D]. */
-int hvit_attention_bf16(const void* qkv_dev, void* out_dev, int B, int N, int heads, void* stream);
+int hvit_attention_16(const void* qkv_dev, void* out_dev, int B, int N, int heads, int f16, void* stream);
 int hvit_attention_f32(const float* qkv_dev, float* out_dev, float* probs_dev, int B, int N, int heads, void* stream);
-/* nn.LayerNorm over the last dim (attention.py:152-153,258); x fp32, out bf16 (out_bf16=1) or fp32. */
-int hvit_layernorm(const float* x_dev, const float* g_dev, const float* b_dev, void* out_dev, int out_bf16, int rows,
+/* nn.LayerNorm over the last dim (attention.py:152-153,258); x fp32, out_dtype 0 = fp32, 1 = bf16, 2 = fp16. */
+int hvit_layernorm(const float* x_dev, const float* g_dev, const float* b_dev, void* out_dev, int out_dtype, int rows,
                    int D, float eps, void* stream);
 /* compute_stft + compute_magnitude_phase + normalize_audio (utils/audio_processing.py:67-98,135-174).
  *   wave [B,n] -> max_val [B] (u32 bit patterns of the fp32 peaks; 1.0 when normalize=0), spec complex64 [B,257,T],

@@ -11,6 +11,7 @@ MAX_STAGES = 8
 MAX_LAYERS = 48
 PREC_FP32 = 0
 PREC_BF16 = 1
+PREC_FP16 = 2
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 
 _VP = C.c_void_p
@@ -58,11 +59,11 @@ SYMBOLS = {
     "hvit_plan_buffer": (_I, [_VP, C.c_char_p, C.POINTER(_SZ), C.POINTER(_I * 4), C.POINTER(_I)]),
     "hvit_plan_launch_count": (_I, [_VP, _I]),
     "hvit_plan_tokens": (_I, [_VP, C.POINTER(_I), C.POINTER(_I)]),
-    "hvit_gemm_bf16": (_I, [_VP, _I, _VP, _VP, _VP, _I, _VP, _I, _VP, _I, _I, _I, _I, _I, _VP]),
+    "hvit_gemm_16": (_I, [_VP, _I, _VP, _VP, _VP, _I, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, _VP]),
     "hvit_gemm_f32": (_I, [_VP, _I, _VP, _VP, _VP, _I, _VP, _I, _VP, _I, _I, _I, _I, _VP]),
-    "hvit_conv3x3_bf16": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP, _I, _I, _I, _I, _I, _VP]),
+    "hvit_conv3x3_16": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP, _I, _I, _I, _I, _I, _I, _VP]),
     "hvit_conv3x3_f32": (_I, [_VP, _VP, _VP, _VP, _I, _I, _VP, _I, _I, _I, _I, _I, _VP]),
-    "hvit_attention_bf16": (_I, [_VP, _VP, _I, _I, _I, _VP]),
+    "hvit_attention_16": (_I, [_VP, _VP, _I, _I, _I, _I, _VP]),
     "hvit_attention_f32": (_I, [_VP, _VP, _VP, _I, _I, _I, _VP]),
     "hvit_layernorm": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _F, _VP]),
     "hvit_stft": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP]),

@@ -52,7 +52,10 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// bf16 tensor, 128-byte swizzle, zero fill out of bounds. dims/box innermost first; strides (bytes) for dims 1..rank-1.
+// element type of the tensor maps being built (set by the plan / entry point before encoding)
+static thread_local int g_tmap_f16 = 0;
+
+// 16-bit tensor (bf16 or fp16), 128-byte swizzle, zero fill out of bounds. dims/box innermost first; strides (bytes) for dims 1..rank-1.
 static int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
                      const uint32_t* box) {
   EncodeTiledFn fn = encode_fn();
@@ -69,7 +72,7 @@ static int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t*
     es[i] = 1;
     if (i > 0) gs[i - 1] = strides[i - 1];
   }
-  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+  const CUresult r = fn(m, g_tmap_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
                         gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -205,7 +208,11 @@ static int build_geometry(const hvit_model_cfg& c, int B, int F, int T, int n_sa
     set_error("unsupported patch_size %d", c.patch_size);
     return HVIT_E_SHAPE;
   }
-  const bool bf = c.precision == HVIT_PREC_BF16;
+  if (c.precision != HVIT_PREC_FP32 && c.precision != HVIT_PREC_BF16 && c.precision != HVIT_PREC_FP16) {
+    set_error("unknown precision %d", c.precision);
+    return HVIT_E_SHAPE;
+  }
+  const bool bf = c.precision != HVIT_PREC_FP32;  // 16-bit tensor-core path
   const int cmul = bf ? 64 : 16;
   g.es = bf ? 2 : 4;
   g.B = B; g.F = F; g.T = T; g.n_samples = n_samples;
@@ -352,9 +359,11 @@ static int add_linear(hvit_plan* p, const void* A, int lda, const void* W, const
   q.M = M; q.N = N; q.K = K;
   q.shift = shift; q.act = act; q.residual = residual; q.ldr = ldr; q.res_mod = res_mod;
   q.out = out; q.ldc = ldc; q.out_f32 = out_f32;
-  if (p->cfg.precision == HVIT_PREC_BF16) {
+  q.f16 = p->cfg.precision == HVIT_PREC_FP16;
+  if (p->cfg.precision != HVIT_PREC_FP32) {
     CUtensorMap ta, tb;
     const int bn = pick_block_n(N);
+    g_tmap_f16 = q.f16;
     int r = tmap_matrix(&ta, A, M, K, lda, 128);
     if (r) return r;
     r = tmap_matrix(&tb, W, N, K, K, bn);
@@ -381,7 +390,9 @@ static int add_conv(hvit_plan* p, const void* in, int B, int H, int W, int Cin, 
   q.scale = scale; q.shift = shift; q.act = relu ? ACT_RELU : ACT_NONE;
   q.out = out; q.ldc = ldc;
   const int Hfull = up2 ? 2 * H : H, Wfull = up2 ? 2 * W : W;
-  if (p->cfg.precision == HVIT_PREC_BF16) {
+  q.f16 = p->cfg.precision == HVIT_PREC_FP16;
+  if (p->cfg.precision != HVIT_PREC_FP32) {
+    g_tmap_f16 = q.f16;
     q.K = (up2 ? 4 : 9) * Cin;
     q.pool = pool;
     q.out_f32 = 0;
@@ -426,7 +437,10 @@ static int build_steps(hvit_plan* p) {
   const hvit_model_cfg& c = p->cfg;
   const hvit_weights& w = p->w;
   const Geometry& g = p->g;
-  const int bf = c.precision == HVIT_PREC_BF16 ? 1 : 0;
+  const int bf = c.precision != HVIT_PREC_FP32 ? 1 : 0;  // 16-bit tensor-core path
+  const int f16 = c.precision == HVIT_PREC_FP16 ? 1 : 0;
+  const int dt = c.precision == HVIT_PREC_FP32 ? DT_F32 : (f16 ? DT_F16 : DT_BF16);
+  g_tmap_f16 = f16;
   const int B = g.B, D = c.embed_dim;
   char nm[32], nm2[32];
   int r;
@@ -436,7 +450,7 @@ static int build_steps(hvit_plan* p) {
     void* out = at<void>(p, "enc0");
     const int C0 = c.enc_channels[0], pool = c.enc_pool[0], F = g.F, T = g.T;
     const float *sw = w.stem_w, *ss = w.stem_scale, *sh = w.stem_shift;
-    p->steps.push_back([=](const Ctx& k) { return launch_stem(k.x, k.mag_max, sw, ss, sh, out, bf, B, F, T, C0, pool, k.stream); });
+    p->steps.push_back([=](const Ctx& k) { return launch_stem(k.x, k.mag_max, sw, ss, sh, out, dt, B, F, T, C0, pool, k.stream); });
   }
   // 2. encoder blocks 1.. : implicit-GEMM 3x3 conv + folded BN + ReLU (+ fused 2x2 max-pool)
   float* conv_tmp = g.bufs.count("conv_tmp") ? at<float>(p, "conv_tmp") : nullptr;
@@ -460,6 +474,7 @@ static int build_steps(hvit_plan* p) {
     q.N = D; q.K = c.patch_size * c.patch_size * e.C;
     q.shift = w.patch_b; q.residual = w.pos_embed; q.ldr = D; q.res_mod = g.Np;
     q.out = at<void>(p, "tokens"); q.ldc = D; q.out_f32 = 1;
+    q.f16 = f16;
     const void* in = at<void>(p, nm);
     if (bf) {
       pick_tile(g.Hp, g.Wp, &q.Wt, &q.Ht);
@@ -496,17 +511,17 @@ static int build_steps(hvit_plan* p) {
   }
   for (int l = 0; l < c.num_layers; ++l) {
     const float *g1 = w.ln1_g[l], *b1 = w.ln1_b[l], *g2 = w.ln2_g[l], *b2 = w.ln2_b[l];
-    p->steps.push_back([=](const Ctx& k) { return launch_layernorm(tok, g1, b1, ln, bf, M, D, eps, k.stream); });
+    p->steps.push_back([=](const Ctx& k) { return launch_layernorm(tok, g1, b1, ln, dt, M, D, eps, k.stream); });
     r = add_linear(p, ln, D, w.qkv_w[l], w.qkv_b[l], ACT_NONE, nullptr, 0, 0, qkv, 3 * D, !bf, M, 3 * D, D);
     if (r) return r;
     const size_t probs_off = static_cast<size_t>(l) * B * heads * Np * Np;
     if (bf) {
       p->steps.push_back([=](const Ctx& k) {
         if (k.probs != nullptr) {
-          const int e = launch_attn_probs_bf16(qkv, k.probs + probs_off, B, Np, heads, D, scale, k.stream);
+          const int e = launch_attn_probs_16(qkv, f16, k.probs + probs_off, B, Np, heads, D, scale, k.stream);
           if (e) return e;
         }
-        return launch_attn_tc(tq, att, B, Np, heads, D, scale, k.stream);
+        return launch_attn_tc(tq, att, f16, B, Np, heads, D, scale, k.stream);
       });
     } else {
       p->steps.push_back([=](const Ctx& k) {
@@ -516,7 +531,7 @@ static int build_steps(hvit_plan* p) {
     }
     r = add_linear(p, att, D, w.proj_w[l], w.proj_b[l], ACT_NONE, tok, D, 0, tok, D, 1, M, D, D);
     if (r) return r;
-    p->steps.push_back([=](const Ctx& k) { return launch_layernorm(tok, g2, b2, ln, bf, M, D, eps, k.stream); });
+    p->steps.push_back([=](const Ctx& k) { return launch_layernorm(tok, g2, b2, ln, dt, M, D, eps, k.stream); });
     r = add_linear(p, ln, D, w.fc1_w[l], w.fc1_b[l], ACT_GELU, nullptr, 0, 0, mlp, c.mlp_hidden, !bf, M, c.mlp_hidden, D);
     if (r) return r;
     r = add_linear(p, mlp, c.mlp_hidden, w.fc2_w[l], w.fc2_b[l], ACT_NONE, tok, D, 0, tok, D, 1, M, D, c.mlp_hidden);
@@ -525,7 +540,7 @@ static int build_steps(hvit_plan* p) {
   // 5. final LayerNorm + to_feature_map, written straight into the first decoder concat buffer (NHWC == [B,N,C])
   {
     const float *gf = w.lnf_g, *bfp = w.lnf_b;
-    p->steps.push_back([=](const Ctx& k) { return launch_layernorm(tok, gf, bfp, ln, bf, M, D, eps, k.stream); });
+    p->steps.push_back([=](const Ctx& k) { return launch_layernorm(tok, gf, bfp, ln, dt, M, D, eps, k.stream); });
     const CatGeo& k0 = g.cat[0];
     r = add_linear(p, ln, D, w.tofm_w, w.tofm_b, ACT_NONE, nullptr, 0, 0, at<void>(p, "cat0"), k0.Ccat, !bf, M, k0.Cx, D);
     if (r) return r;
@@ -545,7 +560,7 @@ static int build_steps(hvit_plan* p) {
       const void* src = at<void>(p, en);
       void* samp = at<void>(p, "samp");
       const int Hs = e.H, Hpit = e.pitch, Ws = e.W, Cs = e.C, Hd = k.H, Wd = k.W;
-      p->steps.push_back([=](const Ctx& x) { return launch_skip_sample(src, bf, B, Hs, Hpit, Ws, Cs, Hd, Wd, samp, x.stream); });
+      p->steps.push_back([=](const Ctx& x) { return launch_skip_sample(src, dt, B, Hs, Hpit, Ws, Cs, Hd, Wd, samp, x.stream); });
       r = add_linear(p, samp, Cs, w.skip_w[i], w.skip_b[i], ACT_NONE, nullptr, 0, 0, cat + static_cast<size_t>(k.Cx) * g.es,
                      k.Ccat, !bf, B * Hd * Wd, c.dec_channels[i], Cs);
       if (r) return r;
@@ -563,7 +578,7 @@ static int build_steps(hvit_plan* p) {
     float* th = at<float>(p, "tanh");
     const float* hw = w.head_w;
     const int H = k.H, W = k.W, C = k.Ccat, F = g.F, T = g.T;
-    p->steps.push_back([=](const Ctx& x) { return launch_head(in, bf, hw, B, H, W, C, logits, th, x.stream); });
+    p->steps.push_back([=](const Ctx& x) { return launch_head(in, dt, hw, B, H, W, C, logits, th, x.stream); });
     p->steps.push_back([=](const Ctx& x) { return launch_resize(th, B, H, W, x.y, F, T, x.stream); });
   }
   p->launches_forward = static_cast<int>(p->steps.size());
@@ -694,9 +709,6 @@ int hvit_plan_buffer(const hvit_plan* plan, const char* name, size_t* offset, in
 int hvit_plan_launch_count(const hvit_plan* plan, int enhance) {
   if (plan == nullptr) return HVIT_E_ARG;
   int n = plan->launches_forward;
-  if (plan->cfg.precision != HVIT_PREC_BF16) {
-    // pooled fp32 convs are two launches but already counted as two steps
-  }
   if (enhance) n += 2 /*peak*/ + 2 /*stft*/ + 2 /*istft*/;
   return n;
 }
@@ -719,11 +731,14 @@ static int require_sm100() {
   return HVIT_OK;
 }
 
-int hvit_gemm_bf16(const void* a, int lda, const void* w, const float* scale, const float* shift, int act,
-                   const float* residual, int ldr, void* out, int ldc, int out_f32, int M, int N, int K, void* stream) {
+int hvit_gemm_16(const void* a, int lda, const void* w, const float* scale, const float* shift, int act,
+                 const float* residual, int ldr, void* out, int ldc, int out_f32, int M, int N, int K, int f16,
+                 void* stream) {
   int r = require_sm100();
   if (r) return r;
+  g_tmap_f16 = f16 ? 1 : 0;
   IgemmParams q = ig_zero();
+  q.f16 = f16 ? 1 : 0;
   q.mode = IG_PLAIN;
   q.M = M; q.N = N; q.K = K;
   q.scale = scale; q.shift = shift; q.act = act; q.residual = residual; q.ldr = ldr;
@@ -749,8 +764,8 @@ int hvit_gemm_f32(const float* a, int lda, const float* w, const float* scale, c
   return launch_igemm_f32(q, a, lda, w, reinterpret_cast<cudaStream_t>(stream));
 }
 
-int hvit_conv3x3_bf16(const void* x, const void* w, const float* scale, const float* shift, int relu, int pool,
-                      int up2, void* out, int B, int H, int W, int Cin, int Cout, void* stream) {
+int hvit_conv3x3_16(const void* x, const void* w, const float* scale, const float* shift, int relu, int pool,
+                    int up2, void* out, int B, int H, int W, int Cin, int Cout, int f16, void* stream) {
   int r = require_sm100();
   if (r) return r;
   if (pool && up2) {
@@ -758,7 +773,7 @@ int hvit_conv3x3_bf16(const void* x, const void* w, const float* scale, const fl
     return HVIT_E_SHAPE;
   }
   hvit_plan tmp;
-  tmp.cfg.precision = HVIT_PREC_BF16;
+  tmp.cfg.precision = f16 ? HVIT_PREC_FP16 : HVIT_PREC_BF16;
   const int Ho = pool ? H / 2 : (up2 ? 2 * H : H);
   r = add_conv(&tmp, x, B, H, W, Cin, w, scale, shift, relu, pool, up2, out, Cout, Ho, Cout, nullptr);
   if (r) return r;
@@ -782,13 +797,14 @@ int hvit_conv3x3_f32(const float* x, const float* w, const float* scale, const f
   return tmp.steps[0](c);
 }
 
-int hvit_attention_bf16(const void* qkv, void* out, int B, int N, int heads, void* stream) {
+int hvit_attention_16(const void* qkv, void* out, int B, int N, int heads, int f16, void* stream) {
   int r = require_sm100();
   if (r) return r;
+  g_tmap_f16 = f16 ? 1 : 0;
   CUtensorMap tq;
   r = tmap_qkv(&tq, qkv, B, N, heads * 64);
   if (r) return r;
-  return launch_attn_tc(tq, out, B, N, heads, heads * 64, 0.125f, reinterpret_cast<cudaStream_t>(stream));
+  return launch_attn_tc(tq, out, f16 ? 1 : 0, B, N, heads, heads * 64, 0.125f, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int hvit_attention_f32(const float* qkv, float* out, float* probs, int B, int N, int heads, void* stream) {
@@ -797,11 +813,15 @@ int hvit_attention_f32(const float* qkv, float* out, float* probs, int B, int N,
   return launch_attn_f32(qkv, out, probs, B, N, heads, heads * 64, 0.125f, reinterpret_cast<cudaStream_t>(stream));
 }
 
-int hvit_layernorm(const float* x, const float* g, const float* b, void* out, int out_bf16, int rows, int D, float eps,
+int hvit_layernorm(const float* x, const float* g, const float* b, void* out, int out_dtype, int rows, int D, float eps,
                    void* stream) {
   int r = require_sm100();
   if (r) return r;
-  return launch_layernorm(x, g, b, out, out_bf16, rows, D, eps, reinterpret_cast<cudaStream_t>(stream));
+  if (out_dtype < 0 || out_dtype > 2) {
+    set_error("layernorm: out_dtype must be 0 (fp32), 1 (bf16) or 2 (fp16)");
+    return HVIT_E_ARG;
+  }
+  return launch_layernorm(x, g, b, out, out_dtype, rows, D, eps, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int hvit_stft(const float* wave, int B, int n, int normalize, void* max_val, void* spec, float* mag, void* mag_max,

@@ -26,7 +26,8 @@ constexpr int AT_SMEM = OFF_BAR + 256;
 constexpr int TMEM_COLS = 256;             // S: cols [0,128), O_blk: cols [128,192)
 
 __global__ void __launch_bounds__(AT_THREADS, 2)
-attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, bf16* __restrict__ out, int N, int D, float scale_log2) {
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, bf16* __restrict__ out, int N, int D, float scale_log2,
+               int f16) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B swizzle needs 1024-byte aligned tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -81,8 +82,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, bf16* __restrict__ 
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // Q (K-major) x K (K-major)
-      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);   // P (K-major) x V (MN-major)
+      const uint32_t idesc_s = make_idesc_16(128, 128, 0, 0, f16);   // Q (K-major) x K (K-major)
+      const uint32_t idesc_pv = make_idesc_16(128, 64, 0, 1, f16);   // P (K-major) x V (MN-major)
       const uint32_t q_addr = smem_u32(smem + OFF_Q);
       const uint32_t p_addr = smem_u32(smem + OFF_P);
       auto issue_s = [&](int j) {
@@ -156,10 +157,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, bf16* __restrict__ 
         for (int q = 0; q < 4; ++q) {
           const int cidx = c * 4 + q;  // 16-byte chunk index along the 128 keys
           uint4 pk;
-          pk.x = pack_bf16x2(pv[q * 8 + 0], pv[q * 8 + 1]);
-          pk.y = pack_bf16x2(pv[q * 8 + 2], pv[q * 8 + 3]);
-          pk.z = pack_bf16x2(pv[q * 8 + 4], pv[q * 8 + 5]);
-          pk.w = pack_bf16x2(pv[q * 8 + 6], pv[q * 8 + 7]);
+          pk.x = pack_16x2(pv[q * 8 + 0], pv[q * 8 + 1], f16);
+          pk.y = pack_16x2(pv[q * 8 + 2], pv[q * 8 + 3], f16);
+          pk.z = pack_16x2(pv[q * 8 + 4], pv[q * 8 + 5], f16);
+          pk.w = pack_16x2(pv[q * 8 + 6], pv[q * 8 + 7], f16);
           *reinterpret_cast<uint4*>(p_row + (cidx >> 3) * TILE_BYTES + (((cidx & 7) ^ sw) << 4)) = pk;
         }
       }
@@ -186,10 +187,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, bf16* __restrict__ 
 #pragma unroll
       for (int i = 0; i < 64; i += 8) {
         uint4 pk;
-        pk.x = pack_bf16x2(o[i] * inv, o[i + 1] * inv);
-        pk.y = pack_bf16x2(o[i + 2] * inv, o[i + 3] * inv);
-        pk.z = pack_bf16x2(o[i + 4] * inv, o[i + 5] * inv);
-        pk.w = pack_bf16x2(o[i + 6] * inv, o[i + 7] * inv);
+        pk.x = pack_16x2(o[i] * inv, o[i + 1] * inv, f16);
+        pk.y = pack_16x2(o[i + 2] * inv, o[i + 3] * inv, f16);
+        pk.z = pack_16x2(o[i + 4] * inv, o[i + 5] * inv, f16);
+        pk.w = pack_16x2(o[i + 6] * inv, o[i + 7] * inv, f16);
         *reinterpret_cast<uint4*>(dst + i) = pk;
       }
     }
@@ -202,7 +203,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, bf16* __restrict__ 
 
 }  // namespace
 
-int launch_attn_tc(const CUtensorMap& tmap_qkv, void* out_bf16, int B, int N, int heads, int D, float scale,
+int launch_attn_tc(const CUtensorMap& tmap_qkv, void* out16, int f16, int B, int N, int heads, int D, float scale,
                    cudaStream_t stream) {
   if (D != heads * 64) {
     set_error("attention: head_dim must be 64 (D=%d heads=%d)", D, heads);
@@ -221,8 +222,8 @@ int launch_attn_tc(const CUtensorMap& tmap_qkv, void* out_bf16, int B, int N, in
     configured = true;
   }
   dim3 grid((N + 127) / 128, heads, B);
-  attn_tc_kernel<<<grid, AT_THREADS, AT_SMEM, stream>>>(tmap_qkv, reinterpret_cast<bf16*>(out_bf16), N, D,
-                                                         scale * 1.4426950408889634f);
+  attn_tc_kernel<<<grid, AT_THREADS, AT_SMEM, stream>>>(tmap_qkv, reinterpret_cast<bf16*>(out16), N, D,
+                                                         scale * 1.4426950408889634f, f16);
   return check_launch("attn_tc");
 }
 

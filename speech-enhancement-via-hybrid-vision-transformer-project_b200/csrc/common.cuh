@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -150,9 +151,10 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
   return d;
 }
 
-// Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+// Instruction descriptor for kind::f16: A/B both bf16 (f16 = 0) or both fp16 (f16 = 1), fp32 D.
+__host__ __device__ constexpr uint32_t make_idesc_16(int M, int N, int a_mn_major, int b_mn_major, int f16) {
+  const uint32_t fmt = f16 ? 0u : 1u;  // F16F32Format: F16 = 0, BF16 = 1
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
@@ -177,6 +179,16 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// fp16 pair, round-to-nearest, saturating to the largest finite value instead of overflowing to inf
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// runtime-selected 16-bit storage type of the tensor-core path: f16 = 1 -> fp16, 0 -> bf16
+__device__ __forceinline__ uint32_t pack_16x2(float lo, float hi, int f16) {
+  return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
 }
 
 }  // namespace hvit

@@ -1,4 +1,4 @@
-// tcgen05 implicit-GEMM for sm_100a: bf16 operands staged by TMA (128B swizzle), fp32 accumulation in TMEM,
+// tcgen05 implicit-GEMM for sm_100a: 16-bit (bf16 or fp16) operands staged by TMA (128B swizzle), fp32 accumulation in TMEM,
 // persistent tiles, warp-specialised (1 TMA warp, 1 MMA warp, 4 epilogue warps), double-buffered accumulator so
 // the epilogue of tile i overlaps the main loop of tile i+1.
 //
@@ -139,7 +139,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (one thread)
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+      const uint32_t idesc = make_idesc_16(BLOCK_M, BLOCK_N, 0, 0, p.f16);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -269,10 +269,10 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               uint4 q;
-              q.x = pack_bf16x2(v[j], v[j + 1]);
-              q.y = pack_bf16x2(v[j + 2], v[j + 3]);
-              q.z = pack_bf16x2(v[j + 4], v[j + 5]);
-              q.w = pack_bf16x2(v[j + 6], v[j + 7]);
+              q.x = pack_16x2(v[j], v[j + 1], p.f16);
+              q.y = pack_16x2(v[j + 2], v[j + 3], p.f16);
+              q.z = pack_16x2(v[j + 4], v[j + 5], p.f16);
+              q.w = pack_16x2(v[j + 6], v[j + 7], p.f16);
               *reinterpret_cast<uint4*>(o + j) = q;
             }
           }

@@ -197,6 +197,19 @@ __device__ __forceinline__ void store16<bf16>(bf16* dst, const float* v) {
   }
 }
 
+template <>
+__device__ __forceinline__ void store16<__half>(__half* dst, const float* v) {
+#pragma unroll
+  for (int j = 0; j < 16; j += 8) {
+    uint4 q;
+    q.x = pack_f16x2(v[j], v[j + 1]);
+    q.y = pack_f16x2(v[j + 2], v[j + 3]);
+    q.z = pack_f16x2(v[j + 4], v[j + 5]);
+    q.w = pack_f16x2(v[j + 6], v[j + 7]);
+    *reinterpret_cast<uint4*>(dst + j) = q;
+  }
+}
+
 template <typename T, int POOL>
 __global__ void stem_kernel(const float* __restrict__ x, const unsigned* __restrict__ mag_max_bits,
                             const float* __restrict__ w9c, const float* __restrict__ scale,
@@ -266,6 +279,48 @@ __global__ void stem_kernel(const float* __restrict__ x, const unsigned* __restr
   store16<T>(out + ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * C + cbase, res);
 }
 
+template <typename T>
+__device__ __forceinline__ void ld4(const T* p, float* v);
+template <typename T>
+__device__ __forceinline__ void st4(T* p, const float* v);
+template <>
+__device__ __forceinline__ void ld4<float>(const float* p, float* v) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+template <>
+__device__ __forceinline__ void ld4<bf16>(const bf16* p, float* v) {
+  const uint2 a = *reinterpret_cast<const uint2*>(p);
+  const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&a.x));
+  const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&a.y));
+  v[0] = x.x; v[1] = x.y; v[2] = y.x; v[3] = y.y;
+}
+template <>
+__device__ __forceinline__ void ld4<__half>(const __half* p, float* v) {
+  const uint2 a = *reinterpret_cast<const uint2*>(p);
+  const float2 x = __half22float2(*reinterpret_cast<const __half2*>(&a.x));
+  const float2 y = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
+  v[0] = x.x; v[1] = x.y; v[2] = y.x; v[3] = y.y;
+}
+template <>
+__device__ __forceinline__ void st4<float>(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <>
+__device__ __forceinline__ void st4<bf16>(bf16* p, const float* v) {
+  uint2 pk;
+  pk.x = pack_bf16x2(v[0], v[1]);
+  pk.y = pack_bf16x2(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = pk;
+}
+template <>
+__device__ __forceinline__ void st4<__half>(__half* p, const float* v) {
+  uint2 pk;
+  pk.x = pack_f16x2(v[0], v[1]);
+  pk.y = pack_f16x2(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = pk;
+}
+
 // ------------------------------------------------------------------ LayerNorm (warp per row)
 template <typename T>
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ bb,
@@ -294,14 +349,8 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
     const float4 be = __ldg(reinterpret_cast<const float4*>(bb + i));
     const float y0 = (v.x - mean) * rstd * gg.x + be.x, y1 = (v.y - mean) * rstd * gg.y + be.y;
     const float y2 = (v.z - mean) * rstd * gg.z + be.z, y3 = (v.w - mean) * rstd * gg.w + be.w;
-    if (sizeof(T) == 4) {
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(orow) + i) = make_float4(y0, y1, y2, y3);
-    } else {
-      uint2 pk;
-      pk.x = pack_bf16x2(y0, y1);
-      pk.y = pack_bf16x2(y2, y3);
-      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(orow) + i) = pk;
-    }
+    const float yv[4] = {y0, y1, y2, y3};
+    st4<T>(orow + i, yv);
   }
 }
 
@@ -321,34 +370,6 @@ __device__ __forceinline__ Lerp make_lerp(int dst, int in_size, int out_size) {
   r.l1 = src - static_cast<float>(r.i0);
   r.l0 = 1.0f - r.l1;
   return r;
-}
-
-template <typename T>
-__device__ __forceinline__ void ld4(const T* p, float* v);
-template <>
-__device__ __forceinline__ void ld4<float>(const float* p, float* v) {
-  const float4 a = *reinterpret_cast<const float4*>(p);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-}
-template <>
-__device__ __forceinline__ void ld4<bf16>(const bf16* p, float* v) {
-  const uint2 a = *reinterpret_cast<const uint2*>(p);
-  const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&a.x));
-  const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&a.y));
-  v[0] = x.x; v[1] = x.y; v[2] = y.x; v[3] = y.y;
-}
-template <typename T>
-__device__ __forceinline__ void st4(T* p, const float* v);
-template <>
-__device__ __forceinline__ void st4<float>(float* p, const float* v) {
-  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-}
-template <>
-__device__ __forceinline__ void st4<bf16>(bf16* p, const float* v) {
-  uint2 pk;
-  pk.x = pack_bf16x2(v[0], v[1]);
-  pk.y = pack_bf16x2(v[2], v[3]);
-  *reinterpret_cast<uint2*>(p) = pk;
 }
 
 // skip feature [B, Hs(pitch), Ws, C] -> bilinear sample at decoder resolution [B*Hd*Wd, C]
@@ -503,8 +524,18 @@ int launch_istft(const float* model_out, const float2* spec, const unsigned* mag
   return check_launch("istft");
 }
 
+template <typename T>
+static void stem_dispatch(const float* x, const unsigned* mm, const float* w, const float* scale, const float* shift,
+                          void* out, int H, int W, int C, int pool, dim3 grid, dim3 block, int smem, cudaStream_t s) {
+  const int Ho = H / pool, Wo = W / pool;
+  if (pool == 2)
+    stem_kernel<T, 2><<<grid, block, smem, s>>>(x, mm, w, scale, shift, reinterpret_cast<T*>(out), H, W, C, Ho, Wo);
+  else
+    stem_kernel<T, 1><<<grid, block, smem, s>>>(x, mm, w, scale, shift, reinterpret_cast<T*>(out), H, W, C, Ho, Wo);
+}
+
 int launch_stem(const float* x, const unsigned* mag_max_bits, const float* w, const float* scale, const float* shift,
-                void* out, int act_bf16, int B, int H, int W, int C, int pool, cudaStream_t s) {
+                void* out, int dt, int B, int H, int W, int C, int pool, cudaStream_t s) {
   if (C % 16 != 0 || C > 512 || (pool != 1 && pool != 2)) {
     set_error("stem: unsupported C=%d pool=%d", C, pool);
     return -1;
@@ -512,52 +543,45 @@ int launch_stem(const float* x, const unsigned* mag_max_bits, const float* w, co
   const int Ho = H / pool, Wo = W / pool;
   dim3 block(32, C / 16), grid((Wo + 31) / 32, Ho, B);
   const int smem = ((pool + 2) * (32 * pool + 2) + 11 * C) * sizeof(float);
-  if (pool == 2) {
-    if (act_bf16)
-      stem_kernel<bf16, 2><<<grid, block, smem, s>>>(x, mag_max_bits, w, scale, shift, reinterpret_cast<bf16*>(out), H,
-                                                     W, C, Ho, Wo);
-    else
-      stem_kernel<float, 2><<<grid, block, smem, s>>>(x, mag_max_bits, w, scale, shift, reinterpret_cast<float*>(out),
-                                                      H, W, C, Ho, Wo);
-  } else {
-    if (act_bf16)
-      stem_kernel<bf16, 1><<<grid, block, smem, s>>>(x, mag_max_bits, w, scale, shift, reinterpret_cast<bf16*>(out), H,
-                                                     W, C, Ho, Wo);
-    else
-      stem_kernel<float, 1><<<grid, block, smem, s>>>(x, mag_max_bits, w, scale, shift, reinterpret_cast<float*>(out),
-                                                      H, W, C, Ho, Wo);
-  }
+  if (dt == DT_BF16) stem_dispatch<bf16>(x, mag_max_bits, w, scale, shift, out, H, W, C, pool, grid, block, smem, s);
+  else if (dt == DT_F16) stem_dispatch<__half>(x, mag_max_bits, w, scale, shift, out, H, W, C, pool, grid, block, smem, s);
+  else stem_dispatch<float>(x, mag_max_bits, w, scale, shift, out, H, W, C, pool, grid, block, smem, s);
   return check_launch("stem");
 }
 
-int launch_layernorm(const float* x, const float* g, const float* b, void* out, int act_bf16, int rows, int D,
+int launch_layernorm(const float* x, const float* g, const float* b, void* out, int dt, int rows, int D,
                      float eps, cudaStream_t s) {
   if (D % 4 != 0) {
     set_error("layernorm: D %% 4 != 0");
     return -1;
   }
   const int grid = (rows + 7) / 8;
-  if (act_bf16)
+  if (dt == DT_BF16)
     layernorm_kernel<bf16><<<grid, 256, 0, s>>>(x, g, b, reinterpret_cast<bf16*>(out), rows, D, eps);
+  else if (dt == DT_F16)
+    layernorm_kernel<__half><<<grid, 256, 0, s>>>(x, g, b, reinterpret_cast<__half*>(out), rows, D, eps);
   else
     layernorm_kernel<float><<<grid, 256, 0, s>>>(x, g, b, reinterpret_cast<float*>(out), rows, D, eps);
   return check_launch("layernorm");
 }
 
-int launch_skip_sample(const void* src, int act_bf16, int B, int Hs, int HsPitch, int Ws, int C, int Hd, int Wd,
+int launch_skip_sample(const void* src, int dt, int B, int Hs, int HsPitch, int Ws, int C, int Hd, int Wd,
                        void* dst, cudaStream_t s) {
   const long long total = static_cast<long long>(B) * Hd * Wd * (C / 4);
   const unsigned grid = static_cast<unsigned>((total + 255) / 256);
-  if (act_bf16)
+  if (dt == DT_BF16)
     skip_sample_kernel<bf16><<<grid, 256, 0, s>>>(reinterpret_cast<const bf16*>(src), Hs, HsPitch, Ws, C, Hd, Wd,
                                                   reinterpret_cast<bf16*>(dst), total);
+  else if (dt == DT_F16)
+    skip_sample_kernel<__half><<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(src), Hs, HsPitch, Ws, C, Hd, Wd,
+                                                    reinterpret_cast<__half*>(dst), total);
   else
     skip_sample_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(src), Hs, HsPitch, Ws, C, Hd, Wd,
                                                    reinterpret_cast<float*>(dst), total);
   return check_launch("skip_sample");
 }
 
-int launch_head(const void* x, int act_bf16, const float* w, int B, int H, int W, int C, float* logits,
+int launch_head(const void* x, int dt, const float* w, int B, int H, int W, int C, float* logits,
                 float* out_tanh, cudaStream_t s) {
   if (C % 4 != 0) {
     set_error("head: C %% 4 != 0");
@@ -565,8 +589,10 @@ int launch_head(const void* x, int act_bf16, const float* w, int B, int H, int W
   }
   const long long threads = static_cast<long long>(B) * H * W * 8;
   const unsigned grid = static_cast<unsigned>((threads + 255) / 256);
-  if (act_bf16)
+  if (dt == DT_BF16)
     head_kernel<bf16><<<grid, 256, 0, s>>>(reinterpret_cast<const bf16*>(x), w, B, H, W, C, logits, out_tanh);
+  else if (dt == DT_F16)
+    head_kernel<__half><<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(x), w, B, H, W, C, logits, out_tanh);
   else
     head_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(x), w, B, H, W, C, logits, out_tanh);
   return check_launch("head");

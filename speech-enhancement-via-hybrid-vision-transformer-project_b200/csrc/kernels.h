@@ -19,6 +19,8 @@ namespace hvit {
 // ---------------------------------------------------------------------------------------------
 enum { IG_PLAIN = 0, IG_CONV3 = 1, IG_UP2 = 2, IG_PATCH = 3 };
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+// activation storage type of a plan: fp32 (CUDA-core mode) or one of the two 16-bit tensor-core operand types
+enum { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
 
 struct IgemmParams {
   int mode;
@@ -40,7 +42,8 @@ struct IgemmParams {
   int pool;             // 1: fused 2x2 max-pool (IG_CONV3 only)
   void* out;
   int ldc;              // elements between consecutive output rows
-  int out_f32;          // 1: fp32 output, 0: bf16 output
+  int out_f32;          // 1: fp32 output, 0: 16-bit output
+  int f16;              // tcgen05 path: 1 = fp16 operands / outputs, 0 = bf16
   int Ho, Wo;           // valid output image dims (conv modes)
   int HoPitch;          // image row pitch of the output buffer in pixel rows (>= Ho)
 };
@@ -56,16 +59,16 @@ int launch_igemm_f32(const IgemmParams& p, const float* A, int lda, const float*
 // ---------------------------------------------------------------------------------------------
 // Attention. qkv: [B*N, 3*D] (q | k | v, head h at columns h*64 .. h*64+63 of each third), out: [B*N, D].
 // ---------------------------------------------------------------------------------------------
-int launch_attn_tc(const CUtensorMap& tmap_qkv, void* out_bf16, int B, int N, int heads, int D, float scale,
+int launch_attn_tc(const CUtensorMap& tmap_qkv, void* out16, int f16, int B, int N, int heads, int D, float scale,
                    cudaStream_t stream);
 int launch_attn_f32(const float* qkv, float* out, float* probs /*nullable [B,h,N,N]*/, int B, int N, int heads, int D,
                     float scale, cudaStream_t stream);
 // probabilities only (return_attentions=True slow path) from bf16 qkv
-int launch_attn_probs_bf16(const void* qkv_bf16, float* probs, int B, int N, int heads, int D, float scale,
-                           cudaStream_t stream);
+int launch_attn_probs_16(const void* qkv16, int f16, float* probs, int B, int N, int heads, int D, float scale,
+                         cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------
-// Bandwidth-bound glue kernels.  `T` is selected by `act_bf16` (1: bf16 activations, 0: fp32).
+// Bandwidth-bound glue kernels.  The activation type is selected by `dt` (DT_F32 / DT_BF16 / DT_F16).
 // ---------------------------------------------------------------------------------------------
 int launch_peak(const float* wave, int B, int n, float* max_val /*[B]*/, int normalize, cudaStream_t s);
 int launch_stft(const float* wave, int B, int n, int T, const float* max_val, float2* spec /*[B,257,T]*/,
@@ -74,13 +77,13 @@ int launch_istft(const float* model_out /*[B,257,T] in [-1,1]*/, const float2* s
                  const float* max_val, float* frames /*[B,T,512] scratch*/, float* wave_out, int B, int n, int T,
                  cudaStream_t s);
 int launch_stem(const float* x /*[B,H,W]*/, const unsigned* mag_max_bits /*nullable*/, const float* w /*[9][C]*/,
-                const float* scale, const float* shift, void* out, int act_bf16, int B, int H, int W, int C, int pool,
+                const float* scale, const float* shift, void* out, int dt, int B, int H, int W, int C, int pool,
                 cudaStream_t s);
-int launch_layernorm(const float* x, const float* g, const float* b, void* out, int act_bf16, int rows, int D,
+int launch_layernorm(const float* x, const float* g, const float* b, void* out, int dt, int rows, int D,
                      float eps, cudaStream_t s);
-int launch_skip_sample(const void* src, int act_bf16, int B, int Hs, int HsPitch, int Ws, int C, int Hd, int Wd,
+int launch_skip_sample(const void* src, int dt, int B, int Hs, int HsPitch, int Ws, int C, int Hd, int Wd,
                        void* dst, cudaStream_t s);
-int launch_head(const void* x, int act_bf16, const float* w /*[9][C]*/, int B, int H, int W, int C, float* logits,
+int launch_head(const void* x, int dt, const float* w /*[9][C]*/, int B, int H, int W, int C, float* logits,
                 float* out_tanh, cudaStream_t s);
 int launch_resize(const float* src, int B, int Hs, int Ws, float* dst, int Hd, int Wd, cudaStream_t s);
 int launch_maxpool2(const float* src, float* dst, int B, int H, int W, int C, cudaStream_t s);

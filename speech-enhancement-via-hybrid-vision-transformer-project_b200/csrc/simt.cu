@@ -143,6 +143,13 @@ template <>
 __device__ __forceinline__ float2 ld2<bf16>(const bf16* p) {
   return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
 }
+template <>
+__device__ __forceinline__ float2 ld2<__half>(const __half* p) {
+  return __half22float2(*reinterpret_cast<const __half2*>(p));
+}
+__device__ __forceinline__ void st2(__half* p, float a, float b) {
+  *reinterpret_cast<uint32_t*>(p) = pack_f16x2(a, b);
+}
 __device__ __forceinline__ void st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
 __device__ __forceinline__ void st2(bf16* p, float a, float b) {
   *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
@@ -226,16 +233,21 @@ int launch_attn_f32(const float* qkv, float* out, float* probs, int B, int N, in
   return check_launch("attn_f32");
 }
 
-int launch_attn_probs_bf16(const void* qkv, float* probs, int B, int N, int heads, int D, float scale,
-                           cudaStream_t stream) {
+int launch_attn_probs_16(const void* qkv, int f16, float* probs, int B, int N, int heads, int D, float scale,
+                         cudaStream_t stream) {
   if (D != heads * 64) {
     set_error("attention: head_dim must be 64 (D=%d heads=%d)", D, heads);
     return -1;
   }
   const long long warps = static_cast<long long>(B) * heads * N;
-  attn_simt_kernel<bf16, false><<<static_cast<unsigned>((warps + 7) / 8), 256, 0, stream>>>(
-      reinterpret_cast<const bf16*>(qkv), nullptr, probs, B, N, heads, D, scale);
-  return check_launch("attn_probs_bf16");
+  const unsigned grid = static_cast<unsigned>((warps + 7) / 8);
+  if (f16)
+    attn_simt_kernel<__half, false><<<grid, 256, 0, stream>>>(reinterpret_cast<const __half*>(qkv), nullptr, probs, B,
+                                                              N, heads, D, scale);
+  else
+    attn_simt_kernel<bf16, false><<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(qkv), nullptr, probs, B, N,
+                                                            heads, D, scale);
+  return check_launch("attn_probs_16");
 }
 
 }  // namespace hvit

@@ -44,7 +44,7 @@ class PackedWeights:
     def __init__(self, model, precision: int):
         dev = next(model.parameters()).device
         sd = {k: v.detach() for k, v in model.state_dict().items()}
-        act = torch.bfloat16 if precision == _lib.PREC_BF16 else torch.float32
+        act = {_lib.PREC_BF16: torch.bfloat16, _lib.PREC_FP16: torch.float16, _lib.PREC_FP32: torch.float32}[precision]
         self.keep: List[torch.Tensor] = []
         self.c = _lib.Weights()
         c = self.c
@@ -88,7 +88,7 @@ class PackedWeights:
             if i == n_dec - 1:
                 c.head_w = hold(w[0].permute(1, 2, 0))              # [3,3,C]
                 continue
-            if up > 1 and precision == _lib.PREC_BF16:
+            if up > 1 and precision != _lib.PREC_FP32:
                 c.dec_w[i] = hold(up2_parity_kernels(w), act)
             else:
                 c.dec_w[i] = hold(conv_khwc(w), act)

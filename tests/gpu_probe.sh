@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 groups=("$@")
 if [ ${#groups[@]} -eq 0 ]; then
-  groups=("gemm_f32" "gemm_bf16" "conv3x3_f32 or up2_parity" "conv3x3_bf16" "attention_f32" "attention_bf16" "layernorm or stft")
+  groups=("gemm_f32" "gemm_16 or fp16_conv" "conv3x3_f32 or up2_parity" "conv3x3_16" "attention_f32" "attention_16" "layernorm or stft")
 fi
 i=0
 for g in "${groups[@]}"; do

@@ -26,14 +26,17 @@ def rel_err(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
-def gemm_bf16(a, w, scale=None, shift=None, act=0, residual=None, out_f32=False, out=None, ldc=None):
+def gemm_16(a, w, scale=None, shift=None, act=0, residual=None, out_f32=False, out=None, ldc=None):
+    """tcgen05 GEMM; the 16-bit operand type (bf16 / fp16) follows a.dtype."""
     M, K = a.shape
     N = w.shape[0]
+    assert a.dtype == w.dtype and a.dtype in (torch.bfloat16, torch.float16)
     if out is None:
-        out = torch.empty((M, N), dtype=torch.float32 if out_f32 else torch.bfloat16, device=a.device)
-    _lib.check(lib().hvit_gemm_bf16(P(a), a.stride(0), P(w), P(scale), P(shift), act, P(residual),
-                                    0 if residual is None else residual.stride(0), P(out), ldc or out.stride(0),
-                                    1 if out_f32 else 0, M, N, K, stream()), "hvit_gemm_bf16")
+        out = torch.empty((M, N), dtype=torch.float32 if out_f32 else a.dtype, device=a.device)
+    _lib.check(lib().hvit_gemm_16(P(a), a.stride(0), P(w), P(scale), P(shift), act, P(residual),
+                                  0 if residual is None else residual.stride(0), P(out), ldc or out.stride(0),
+                                  1 if out_f32 else 0, M, N, K, 1 if a.dtype == torch.float16 else 0, stream()),
+               "hvit_gemm_16")
     return out
 
 

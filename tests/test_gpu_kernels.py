@@ -15,6 +15,8 @@ if torch.cuda.is_available():
     from hvit_b200.models.packing import conv_khwc, up2_parity_kernels
 
 DEV = "cuda"
+DT16 = {"bf16": torch.bfloat16, "fp16": torch.float16}
+OUT_TOL = {"bf16": 6e-3, "fp16": 8e-4}   # rounding of a 16-bit output (2^-8 / 2^-11) with margin
 
 
 def _rand(*shape, seed=0, scale=1.0):
@@ -40,43 +42,55 @@ def test_gemm_f32(M, N, K):
 
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (128, 256, 64), (200, 128, 128), (496, 1536, 512),
                                    (1000, 512, 2048), (64 * 48, 384, 128), (37, 256, 512), (31744, 512, 512)])
-def test_gemm_bf16_tcgen05(M, N, K):
-    a = _rand(M, K, seed=1).bfloat16()
-    w = _rand(N, K, seed=2, scale=0.05).bfloat16()
-    out = U.gemm_bf16(a, w, out_f32=True)
+@pytest.mark.parametrize("kind", ["bf16", "fp16"])
+def test_gemm_16_tcgen05(M, N, K, kind):
+    a = _rand(M, K, seed=1).to(DT16[kind])
+    w = _rand(N, K, seed=2, scale=0.05).to(DT16[kind])
+    out = U.gemm_16(a, w, out_f32=True)
     ref = a.double() @ w.double().t()
-    assert U.rel_err(out, ref) < 2e-5          # fp32 accumulation of exact bf16 products
-    out16 = U.gemm_bf16(a, w, out_f32=False)
-    assert U.rel_err(out16.float(), ref) < 6e-3  # bf16 output rounding (2^-8)
+    assert U.rel_err(out, ref) < 2e-5          # fp32 accumulation of exact 16-bit products
+    out16 = U.gemm_16(a, w, out_f32=False)
+    assert out16.dtype == DT16[kind]
+    assert U.rel_err(out16.float(), ref) < OUT_TOL[kind]
 
 
-def test_gemm_bf16_epilogues():
+@pytest.mark.parametrize("kind", ["bf16", "fp16"])
+def test_gemm_16_epilogues(kind):
     M, N, K = 300, 512, 256
-    a = _rand(M, K, seed=4).bfloat16()
-    w = _rand(N, K, seed=5, scale=0.05).bfloat16()
+    a = _rand(M, K, seed=4).to(DT16[kind])
+    w = _rand(N, K, seed=5, scale=0.05).to(DT16[kind])
     scale, shift, res = _rand(N, seed=6), _rand(N, seed=7), _rand(M, N, seed=8)
     base = a.double() @ w.double().t()
-    out = U.gemm_bf16(a, w, scale=scale, shift=shift, act=_lib.ACT_RELU, out_f32=True)
+    out = U.gemm_16(a, w, scale=scale, shift=shift, act=_lib.ACT_RELU, out_f32=True)
     assert U.rel_err(out, torch.relu(base * scale.double() + shift.double())) < 2e-5
-    out = U.gemm_bf16(a, w, shift=shift, act=_lib.ACT_GELU, out_f32=True)
+    out = U.gemm_16(a, w, shift=shift, act=_lib.ACT_GELU, out_f32=True)
     assert U.rel_err(out, F.gelu(base + shift.double())) < 2e-5
     # residual add, in place on the fp32 residual stream (x += proj(attn))
     x = res.clone()
-    U.gemm_bf16(a, w, shift=shift, residual=x, out_f32=True, out=x)
+    U.gemm_16(a, w, shift=shift, residual=x, out_f32=True, out=x)
     assert U.rel_err(x, base + shift.double() + res.double()) < 2e-5
     # strided output: write a channel slice of a wider (concat) buffer
-    wide = torch.zeros((M, N + 128), dtype=torch.bfloat16, device=DEV)
-    U.gemm_bf16(a, w, shift=shift, out=wide[:, 128:], ldc=N + 128)
+    wide = torch.zeros((M, N + 128), dtype=DT16[kind], device=DEV)
+    U.gemm_16(a, w, shift=shift, out=wide[:, 128:], ldc=N + 128)
     U.sync()
-    assert U.rel_err(wide[:, 128:].float(), base + shift.double()) < 6e-3
+    assert U.rel_err(wide[:, 128:].float(), base + shift.double()) < OUT_TOL[kind]
     assert float(wide[:, :128].abs().max()) == 0.0
 
 
-def test_gemm_bf16_matches_simt_fp32():
+def test_fp16_conversion_saturates():
+    """fp16 outputs saturate to the largest finite value instead of overflowing to inf."""
+    a = torch.full((128, 64), 200.0, dtype=torch.float16, device=DEV)
+    w = torch.full((64, 64), 200.0, dtype=torch.float16, device=DEV)
+    out = U.gemm_16(a, w)          # 64 * 4e4 = 2.56e6 > 65504
+    U.sync()
+    assert torch.isfinite(out.float()).all() and float(out.float().max()) == 65504.0
+
+
+def test_gemm_16_matches_simt_fp32():
     M, N, K = 512, 256, 1152
     a = _rand(M, K, seed=9).bfloat16()
     w = _rand(N, K, seed=10, scale=0.03).bfloat16()
-    tc = U.gemm_bf16(a, w, out_f32=True)
+    tc = U.gemm_16(a, w, out_f32=True)
     simt = U.gemm_f32(a.float(), w.float())
     assert U.rel_err(tc, simt) < 2e-5
 
@@ -97,18 +111,20 @@ def _conv_ref(x_nhwc, w, scale, shift, relu, pool, up2):
 @pytest.mark.parametrize("B,H,W,Cin,Cout,pool,up2", [
     (2, 16, 31, 128, 64, 0, 0), (1, 64, 125, 128, 256, 0, 0), (2, 37, 50, 64, 128, 1, 0), (1, 128, 250, 64, 128, 1, 0),
     (2, 16, 31, 384, 128, 0, 1), (1, 32, 62, 192, 64, 0, 1), (3, 5, 7, 64, 64, 0, 0), (2, 9, 3, 64, 64, 0, 1)])
-def test_conv3x3_bf16_tcgen05(B, H, W, Cin, Cout, pool, up2):
-    x = _rand(B, H, W, Cin, seed=11).bfloat16()
+@pytest.mark.parametrize("kind", ["bf16", "fp16"])
+def test_conv3x3_16_tcgen05(B, H, W, Cin, Cout, pool, up2, kind):
+    dt = DT16[kind]
+    x = _rand(B, H, W, Cin, seed=11).to(dt)
     w = _rand(Cout, Cin, 3, 3, seed=12, scale=(2.0 / (9 * Cin)) ** 0.5)
     scale, shift = _rand(Cout, seed=13).abs() + 0.5, _rand(Cout, seed=14, scale=0.1)
     if up2:
-        wp = up2_parity_kernels(w).bfloat16()
+        wp = up2_parity_kernels(w).to(dt)
     else:
-        wp = conv_khwc(w).bfloat16()
+        wp = conv_khwc(w).to(dt)
     Ho, Wo = (H // 2, W // 2) if pool else ((2 * H, 2 * W) if up2 else (H, W))
-    out = torch.full((B, Ho, Wo, Cout), float("nan"), dtype=torch.bfloat16, device=DEV)
-    _lib.check(U.lib().hvit_conv3x3_bf16(U.P(x), U.P(wp), U.P(scale), U.P(shift), 1, pool, up2, U.P(out), B, H, W, Cin,
-                                         Cout, U.stream()), "hvit_conv3x3_bf16")
+    out = torch.full((B, Ho, Wo, Cout), float("nan"), dtype=dt, device=DEV)
+    _lib.check(U.lib().hvit_conv3x3_16(U.P(x), U.P(wp), U.P(scale), U.P(shift), 1, pool, up2, U.P(out), B, H, W, Cin,
+                                       Cout, 1 if kind == "fp16" else 0, U.stream()), "hvit_conv3x3_16")
     U.sync()
     if up2:   # reference assembled from the same bf16-rounded parity kernels
         ref = _up2_from_parity(x.float().permute(0, 3, 1, 2).double(), wp.double())
@@ -117,7 +133,7 @@ def test_conv3x3_bf16_tcgen05(B, H, W, Cin, Cout, pool, up2):
     else:
         ref = _conv_ref(x.float(), wp.float().permute(0, 3, 1, 2), scale, shift, True, pool, up2)
     assert torch.isfinite(out.float()).all()
-    assert U.rel_err(out.float(), ref) < 6e-3
+    assert U.rel_err(out.float(), ref) < OUT_TOL[kind]
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,up2", [(2, 16, 31, 64, 64, 0), (1, 9, 14, 32, 48, 1)])
@@ -176,15 +192,17 @@ def test_attention_f32(B, N, h):
 
 
 @pytest.mark.parametrize("B,N,h", [(2, 48, 2), (1, 112, 8), (2, 496, 8), (1, 640, 2), (1, 1248, 1), (64, 496, 8)])
-def test_attention_bf16_tcgen05(B, N, h):
-    qkv = _rand(B * N, 3 * h * 64, seed=22).bfloat16()
-    out = torch.full((B * N, h * 64), float("nan"), dtype=torch.bfloat16, device=DEV)
-    _lib.check(U.lib().hvit_attention_bf16(U.P(qkv), U.P(out), B, N, h, U.stream()), "attention_bf16")
+@pytest.mark.parametrize("kind", ["bf16", "fp16"])
+def test_attention_16_tcgen05(B, N, h, kind):
+    qkv = _rand(B * N, 3 * h * 64, seed=22).to(DT16[kind])
+    out = torch.full((B * N, h * 64), float("nan"), dtype=DT16[kind], device=DEV)
+    _lib.check(U.lib().hvit_attention_16(U.P(qkv), U.P(out), B, N, h, 1 if kind == "fp16" else 0, U.stream()),
+               "attention_16")
     U.sync()
     sl = slice(0, min(B, 2) * N)
     ref, _ = _attn_ref(qkv[sl].float(), min(B, 2), N, h)
     assert torch.isfinite(out.float()).all()
-    assert U.rel_err(out[sl].float(), ref) < 1.5e-2   # P and the output are rounded to bf16
+    assert U.rel_err(out[sl].float(), ref) < (1.5e-2 if kind == "bf16" else 2e-3)   # P and the output are 16-bit
 
 
 # ------------------------------------------------------------------------------------------------ glue
@@ -195,9 +213,10 @@ def test_layernorm(rows, D):
     _lib.check(U.lib().hvit_layernorm(U.P(x), U.P(g), U.P(b), U.P(out), 0, rows, D, 1e-5, U.stream()), "layernorm")
     ref = F.layer_norm(x.double(), (D,), g.double(), b.double(), 1e-5)
     assert U.rel_err(out, ref) < 1e-5
-    out16 = torch.empty((rows, D), dtype=torch.bfloat16, device=DEV)
-    _lib.check(U.lib().hvit_layernorm(U.P(x), U.P(g), U.P(b), U.P(out16), 1, rows, D, 1e-5, U.stream()), "layernorm")
-    assert U.rel_err(out16.float(), ref) < 6e-3
+    for code, kind in ((1, "bf16"), (2, "fp16")):
+        out16 = torch.empty((rows, D), dtype=DT16[kind], device=DEV)
+        _lib.check(U.lib().hvit_layernorm(U.P(x), U.P(g), U.P(b), U.P(out16), code, rows, D, 1e-5, U.stream()), "layernorm")
+        assert U.rel_err(out16.float(), ref) < OUT_TOL[kind]
 
 
 @pytest.mark.parametrize("n", [64000, 16000, 9001, 2048])
