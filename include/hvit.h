@@ -129,6 +129,15 @@ int hvit_enhance(hvit_plan* plan, const float* wave_in_dev, float* wave_out_dev,
 int hvit_plan_buffer(const hvit_plan* plan, const char* name, size_t* offset, int* dims, int* elem_bytes);
 /* Number of kernels one hvit_forward / hvit_enhance call launches. */
 int hvit_plan_launch_count(const hvit_plan* plan, int enhance);
+/* Measurement hooks (bench.py): the plan as a list of steps (enhance=1 includes peak/STFT/iSTFT), each with its
+ * layer name, kernel family, algorithmic / executed FLOPs, compulsory HBM bytes and launch count; and one enhance
+ * call with a CUDA event recorded on `stream` after every step (synchronises the stream, writes per-step
+ * milliseconds to host memory). */
+int hvit_plan_num_steps(const hvit_plan* plan, int enhance);
+int hvit_plan_step_info(const hvit_plan* plan, int enhance, int i, char* name, int name_len, char* kernel,
+                        int kernel_len, double* algo_flops, double* exec_flops, double* algo_bytes, int* launches);
+int hvit_enhance_profiled(hvit_plan* plan, const float* wave_in_dev, float* wave_out_dev, int normalize, void* stream,
+                          float* step_ms_host, int n_steps);
 /* Token count N and patch grid of the plan. */
 int hvit_plan_tokens(const hvit_plan* plan, int* hp, int* wp);
 

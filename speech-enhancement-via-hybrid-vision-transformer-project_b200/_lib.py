@@ -59,6 +59,10 @@ SYMBOLS = {
     "hvit_plan_buffer": (_I, [_VP, C.c_char_p, C.POINTER(_SZ), C.POINTER(_I * 4), C.POINTER(_I)]),
     "hvit_plan_launch_count": (_I, [_VP, _I]),
     "hvit_plan_tokens": (_I, [_VP, C.POINTER(_I), C.POINTER(_I)]),
+    "hvit_plan_num_steps": (_I, [_VP, _I]),
+    "hvit_plan_step_info": (_I, [_VP, _I, _I, C.c_char_p, _I, C.c_char_p, _I, C.POINTER(C.c_double),
+                                 C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I)]),
+    "hvit_enhance_profiled": (_I, [_VP, _VP, _VP, _I, _VP, C.POINTER(C.c_float), _I]),
     "hvit_gemm_16": (_I, [_VP, _I, _VP, _VP, _VP, _I, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, _VP]),
     "hvit_gemm_f32": (_I, [_VP, _I, _VP, _VP, _VP, _I, _VP, _I, _VP, _I, _I, _I, _I, _VP]),
     "hvit_conv3x3_16": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP, _I, _I, _I, _I, _I, _I, _VP]),

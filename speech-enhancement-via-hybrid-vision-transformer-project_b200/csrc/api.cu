@@ -148,9 +148,22 @@ struct Ctx {
   float* y;                  // model output [B,F,T]
   float* probs;              // optional attention maps
   const unsigned* mag_max;   // per-clip magnitude max (enhance) or null
+  const float* wave_in;      // enhance only
+  float* wave_out;           // enhance only
+  int normalize;             // enhance only
   cudaStream_t stream;
 };
 typedef std::function<int(const Ctx&)> Step;
+
+// Book-keeping for measurement (bench.py roofline): what each step is and how much work it represents.
+struct StepMeta {
+  std::string name;      // layer name, e.g. "blocks.3.fc1"
+  std::string kernel;    // kernel family, e.g. "igemm_tc"
+  double algo_flops;     // multiply-add FLOPs of the reference graph for this op (torch FlopCounter convention)
+  double exec_flops;     // FLOPs actually executed (differs when an exact algebraic shortcut is used)
+  double algo_bytes;     // compulsory HBM traffic (inputs read once + outputs written once)
+  int launches;
+};
 
 struct Buf {
   size_t off;
@@ -182,8 +195,18 @@ struct hvit_plan {
   hvit_weights w;
   hvit::Geometry g;
   uint8_t* ws;
-  std::vector<hvit::Step> steps;
+  std::vector<hvit::Step> steps;      // HybridViT.forward
+  std::vector<hvit::StepMeta> meta;
+  std::vector<hvit::Step> pre, post;  // enhance: peak/STFT before, iSTFT after
+  std::vector<hvit::StepMeta> pre_meta, post_meta;
   int launches_forward;
+  // tag the most recently pushed step(s)
+  void tag(const std::string& name, const char* kernel, double aflops, double eflops, double bytes, int launches = 1) {
+    while (meta.size() < steps.size()) meta.push_back(hvit::StepMeta{name, kernel, 0.0, 0.0, 0.0, 1});
+    hvit::StepMeta& m = meta.back();
+    m.name = name; m.kernel = kernel; m.algo_flops = aflops; m.exec_flops = eflops; m.algo_bytes = bytes;
+    m.launches = launches;
+  }
 };
 
 namespace hvit {
@@ -351,9 +374,13 @@ static IgemmParams ig_zero() {
 }
 
 // plain GEMM step (both precisions)
-static int add_linear(hvit_plan* p, const void* A, int lda, const void* W, const float* shift, int act,
-                      const float* residual, int ldr, int res_mod, void* out, int ldc, int out_f32, int M, int N,
-                      int K) {
+static int add_linear(hvit_plan* p, const std::string& name, const void* A, int lda, const void* W,
+                      const float* shift, int act, const float* residual, int ldr, int res_mod, void* out, int ldc,
+                      int out_f32, int M, int N, int K, double algo_flops = -1.0) {
+  const double fl = 2.0 * M * N * K;
+  const int es_ = p->cfg.precision == HVIT_PREC_FP32 ? 4 : 2;
+  const double by = (static_cast<double>(M) * K + static_cast<double>(N) * K) * es_ +
+                    static_cast<double>(M) * N * (out_f32 ? 4 : es_) * (residual != nullptr && res_mod == 0 ? 2 : 1);
   IgemmParams q = ig_zero();
   q.mode = IG_PLAIN;
   q.M = M; q.N = N; q.K = K;
@@ -370,17 +397,20 @@ static int add_linear(hvit_plan* p, const void* A, int lda, const void* W, const
     if (r) return r;
     const int sms = num_sms();
     p->steps.push_back([=](const Ctx& c) { return launch_igemm_tc(q, ta, tb, bn, sms, c.stream); });
+    p->tag(name, "igemm_tc", algo_flops >= 0 ? algo_flops : fl, fl, by);
   } else {
     q.out_f32 = 1;
     const float* Af = reinterpret_cast<const float*>(A);
     const float* Wf = reinterpret_cast<const float*>(W);
     p->steps.push_back([=](const Ctx& c) { return launch_igemm_f32(q, Af, lda, Wf, c.stream); });
+    p->tag(name, "igemm_f32", algo_flops >= 0 ? algo_flops : fl, fl, by);
   }
   return HVIT_OK;
 }
 
 // 3x3 conv (+ optional fused pool / x2 upsample) step
-static int add_conv(hvit_plan* p, const void* in, int B, int H, int W, int Cin, const void* Wt, const float* scale,
+static int add_conv(hvit_plan* p, const std::string& name, const void* in, int B, int H, int W, int Cin,
+                    const void* Wt, const float* scale,
                     const float* shift, int relu, int pool, int up2, void* out, int ldc, int HoPitch, int Cout,
                     float* conv_tmp) {
   IgemmParams q = ig_zero();
@@ -390,6 +420,10 @@ static int add_conv(hvit_plan* p, const void* in, int B, int H, int W, int Cin, 
   q.scale = scale; q.shift = shift; q.act = relu ? ACT_RELU : ACT_NONE;
   q.out = out; q.ldc = ldc;
   const int Hfull = up2 ? 2 * H : H, Wfull = up2 ? 2 * W : W;
+  const double algo_fl = 2.0 * B * Hfull * Wfull * Cout * 9.0 * Cin;
+  const int es_ = p->cfg.precision == HVIT_PREC_FP32 ? 4 : 2;
+  const double by = (static_cast<double>(B) * H * W * Cin + static_cast<double>(B) * Hfull * Wfull * Cout / (pool ? 4 : 1) +
+                     9.0 * Cin * Cout) * es_;
   q.f16 = p->cfg.precision == HVIT_PREC_FP16;
   if (p->cfg.precision != HVIT_PREC_FP32) {
     g_tmap_f16 = q.f16;
@@ -414,6 +448,7 @@ static int add_conv(hvit_plan* p, const void* in, int B, int H, int W, int Cin, 
     if (r) return r;
     const int sms = num_sms();
     p->steps.push_back([=](const Ctx& c) { return launch_igemm_tc(q, ta, tb, bn, sms, c.stream); });
+    p->tag(name, "igemm_tc", algo_fl, up2 ? algo_fl * 4.0 / 9.0 : algo_fl, by);
   } else {
     q.K = 9 * Cin;
     q.out_f32 = 1;
@@ -424,10 +459,13 @@ static int add_conv(hvit_plan* p, const void* in, int B, int H, int W, int Cin, 
       q.out = conv_tmp; q.ldc = Cout; q.HoPitch = Hfull;
       float* dst = reinterpret_cast<float*>(out);
       p->steps.push_back([=](const Ctx& c) { return launch_igemm_f32(q, inf, Cin, wf, c.stream); });
+      p->tag(name, "igemm_f32", algo_fl, algo_fl, by);
       p->steps.push_back([=](const Ctx& c) { return launch_maxpool2(conv_tmp, dst, B, H, W, Cout, c.stream); });
+      p->tag(name + ".pool", "maxpool2", 0, 0, 1.25 * B * H * W * Cout * 4.0);
     } else {
       q.HoPitch = HoPitch;
       p->steps.push_back([=](const Ctx& c) { return launch_igemm_f32(q, inf, Cin, wf, c.stream); });
+      p->tag(name, "igemm_f32", algo_fl, algo_fl, by);
     }
   }
   return HVIT_OK;
@@ -451,6 +489,10 @@ static int build_steps(hvit_plan* p) {
     const int C0 = c.enc_channels[0], pool = c.enc_pool[0], F = g.F, T = g.T;
     const float *sw = w.stem_w, *ss = w.stem_scale, *sh = w.stem_shift;
     p->steps.push_back([=](const Ctx& k) { return launch_stem(k.x, k.mag_max, sw, ss, sh, out, dt, B, F, T, C0, pool, k.stream); });
+    {
+      const double fl = 2.0 * B * F * T * C0 * 9.0;
+      p->tag("encoder.0", "stem", fl, fl, static_cast<double>(B) * F * T * 4 + static_cast<double>(B) * g.enc[0].H * g.enc[0].W * C0 * g.es);
+    }
   }
   // 2. encoder blocks 1.. : implicit-GEMM 3x3 conv + folded BN + ReLU (+ fused 2x2 max-pool)
   float* conv_tmp = g.bufs.count("conv_tmp") ? at<float>(p, "conv_tmp") : nullptr;
@@ -459,7 +501,7 @@ static int build_steps(hvit_plan* p) {
     snprintf(nm2, sizeof(nm2), "enc%d", i);
     const EncGeo& s = g.enc[i - 1];
     const EncGeo& d = g.enc[i];
-    r = add_conv(p, at<void>(p, nm), B, s.H, s.W, s.C, w.enc_w[i], w.enc_scale[i], w.enc_shift[i], 1,
+    r = add_conv(p, std::string("encoder.") + std::to_string(i), at<void>(p, nm), B, s.H, s.W, s.C, w.enc_w[i], w.enc_scale[i], w.enc_shift[i], 1,
                  c.enc_pool[i] == 2, 0, at<void>(p, nm2), d.C, d.pitch, d.C, conv_tmp);
     if (r) return r;
   }
@@ -494,6 +536,11 @@ static int build_steps(hvit_plan* p) {
       const int lda = e.C;
       p->steps.push_back([=](const Ctx& k) { return launch_igemm_f32(q, inf, lda, wf, k.stream); });
     }
+    {
+      const double fl = 2.0 * g.M * D * q.K;
+      p->tag("patch_embed", bf ? "igemm_tc" : "igemm_f32", fl, fl,
+             (static_cast<double>(g.M) * q.K + static_cast<double>(D) * q.K) * g.es + 2.0 * g.M * D * 4);
+    }
   }
   // 4. transformer blocks (pre-norm), residual stream fp32
   float* tok = at<float>(p, "tokens");
@@ -511,8 +558,11 @@ static int build_steps(hvit_plan* p) {
   }
   for (int l = 0; l < c.num_layers; ++l) {
     const float *g1 = w.ln1_g[l], *b1 = w.ln1_b[l], *g2 = w.ln2_g[l], *b2 = w.ln2_b[l];
+    const std::string L = "blocks." + std::to_string(l);
+    const double ln_bytes = static_cast<double>(M) * D * (4 + g.es);
     p->steps.push_back([=](const Ctx& k) { return launch_layernorm(tok, g1, b1, ln, dt, M, D, eps, k.stream); });
-    r = add_linear(p, ln, D, w.qkv_w[l], w.qkv_b[l], ACT_NONE, nullptr, 0, 0, qkv, 3 * D, !bf, M, 3 * D, D);
+    p->tag(L + ".norm1", "layernorm", 0, 0, ln_bytes);
+    r = add_linear(p, L + ".qkv", ln, D, w.qkv_w[l], w.qkv_b[l], ACT_NONE, nullptr, 0, 0, qkv, 3 * D, !bf, M, 3 * D, D);
     if (r) return r;
     const size_t probs_off = static_cast<size_t>(l) * B * heads * Np * Np;
     if (bf) {
@@ -523,26 +573,32 @@ static int build_steps(hvit_plan* p) {
         }
         return launch_attn_tc(tq, att, f16, B, Np, heads, D, scale, k.stream);
       });
+      p->tag(L + ".attn", "attn_tc", 4.0 * B * heads * Np * Np * 64.0, 4.0 * B * heads * Np * Np * 64.0,
+             static_cast<double>(M) * 4 * D * g.es);
     } else {
       p->steps.push_back([=](const Ctx& k) {
         return launch_attn_f32(reinterpret_cast<const float*>(qkv), reinterpret_cast<float*>(att),
                                k.probs != nullptr ? k.probs + probs_off : nullptr, B, Np, heads, D, scale, k.stream);
       });
+      p->tag(L + ".attn", "attn_f32", 4.0 * B * heads * Np * Np * 64.0, 4.0 * B * heads * Np * Np * 64.0,
+             static_cast<double>(M) * 4 * D * g.es);
     }
-    r = add_linear(p, att, D, w.proj_w[l], w.proj_b[l], ACT_NONE, tok, D, 0, tok, D, 1, M, D, D);
+    r = add_linear(p, L + ".proj", att, D, w.proj_w[l], w.proj_b[l], ACT_NONE, tok, D, 0, tok, D, 1, M, D, D);
     if (r) return r;
     p->steps.push_back([=](const Ctx& k) { return launch_layernorm(tok, g2, b2, ln, dt, M, D, eps, k.stream); });
-    r = add_linear(p, ln, D, w.fc1_w[l], w.fc1_b[l], ACT_GELU, nullptr, 0, 0, mlp, c.mlp_hidden, !bf, M, c.mlp_hidden, D);
+    p->tag(L + ".norm2", "layernorm", 0, 0, ln_bytes);
+    r = add_linear(p, L + ".fc1", ln, D, w.fc1_w[l], w.fc1_b[l], ACT_GELU, nullptr, 0, 0, mlp, c.mlp_hidden, !bf, M, c.mlp_hidden, D);
     if (r) return r;
-    r = add_linear(p, mlp, c.mlp_hidden, w.fc2_w[l], w.fc2_b[l], ACT_NONE, tok, D, 0, tok, D, 1, M, D, c.mlp_hidden);
+    r = add_linear(p, L + ".fc2", mlp, c.mlp_hidden, w.fc2_w[l], w.fc2_b[l], ACT_NONE, tok, D, 0, tok, D, 1, M, D, c.mlp_hidden);
     if (r) return r;
   }
   // 5. final LayerNorm + to_feature_map, written straight into the first decoder concat buffer (NHWC == [B,N,C])
   {
     const float *gf = w.lnf_g, *bfp = w.lnf_b;
     p->steps.push_back([=](const Ctx& k) { return launch_layernorm(tok, gf, bfp, ln, dt, M, D, eps, k.stream); });
+    p->tag("transformer.norm", "layernorm", 0, 0, static_cast<double>(M) * D * (4 + g.es));
     const CatGeo& k0 = g.cat[0];
-    r = add_linear(p, ln, D, w.tofm_w, w.tofm_b, ACT_NONE, nullptr, 0, 0, at<void>(p, "cat0"), k0.Ccat, !bf, M, k0.Cx, D);
+    r = add_linear(p, "to_feature_map", ln, D, w.tofm_w, w.tofm_b, ACT_NONE, nullptr, 0, 0, at<void>(p, "cat0"), k0.Ccat, !bf, M, k0.Cx, D);
     if (r) return r;
   }
   // 6. decoder blocks with skip connections
@@ -561,11 +617,14 @@ static int build_steps(hvit_plan* p) {
       void* samp = at<void>(p, "samp");
       const int Hs = e.H, Hpit = e.pitch, Ws = e.W, Cs = e.C, Hd = k.H, Wd = k.W;
       p->steps.push_back([=](const Ctx& x) { return launch_skip_sample(src, dt, B, Hs, Hpit, Ws, Cs, Hd, Wd, samp, x.stream); });
-      r = add_linear(p, samp, Cs, w.skip_w[i], w.skip_b[i], ACT_NONE, nullptr, 0, 0, cat + static_cast<size_t>(k.Cx) * g.es,
-                     k.Ccat, !bf, B * Hd * Wd, c.dec_channels[i], Cs);
+      p->tag("skip." + std::to_string(i) + ".sample", "skip_sample", 0, 0, 5.0 * B * Hd * Wd * Cs * g.es);
+      // reference graph: 1x1 conv on the full-resolution skip feature, then bilinear resize (hybrid_vit.py:377-386)
+      r = add_linear(p, "skip." + std::to_string(i) + ".proj", samp, Cs, w.skip_w[i], w.skip_b[i], ACT_NONE, nullptr, 0,
+                     0, cat + static_cast<size_t>(k.Cx) * g.es, k.Ccat, !bf, B * Hd * Wd, c.dec_channels[i], Cs,
+                     2.0 * B * Hs * Ws * c.dec_channels[i] * Cs);
       if (r) return r;
     }
-    r = add_conv(p, cat, B, k.H, k.W, k.Ccat, w.dec_w[i], w.dec_scale[i], w.dec_shift[i], 1, 0, c.dec_up[i] == 2,
+    r = add_conv(p, std::string("decoder.") + std::to_string(i), cat, B, k.H, k.W, k.Ccat, w.dec_w[i], w.dec_scale[i], w.dec_shift[i], 1, 0, c.dec_up[i] == 2,
                  at<void>(p, nm2), kn.Ccat, kn.H, c.dec_channels[i], nullptr);
     if (r) return r;
   }
@@ -579,9 +638,33 @@ static int build_steps(hvit_plan* p) {
     const float* hw = w.head_w;
     const int H = k.H, W = k.W, C = k.Ccat, F = g.F, T = g.T;
     p->steps.push_back([=](const Ctx& x) { return launch_head(in, dt, hw, B, H, W, C, logits, th, x.stream); });
+    p->tag("decoder." + std::to_string(c.n_dec - 1), "head", 2.0 * B * H * W * C * 9.0, 2.0 * B * H * W * C * 9.0,
+           static_cast<double>(B) * H * W * (C * g.es + 8));
     p->steps.push_back([=](const Ctx& x) { return launch_resize(th, B, H, W, x.y, F, T, x.stream); });
+    p->tag("resize", "resize", 0, 0, static_cast<double>(B) * (H * W + F * T) * 4);
   }
-  p->launches_forward = static_cast<int>(p->steps.size());
+  // enhance-only stages around the model
+  if (g.n_samples > 0) {
+    const int n = g.n_samples, T = g.T;
+    float* max_val = at<float>(p, "max_val");
+    unsigned* mag_max = at<unsigned>(p, "mag_max");
+    float2* spec = at<float2>(p, "spec");
+    float* mag = at<float>(p, "mag");
+    float* mo = at<float>(p, "model_out");
+    float* frames = at<float>(p, "frames");
+    const double ft = static_cast<double>(B) * 257 * T;
+    p->pre.push_back([=](const Ctx& x) { return launch_peak(x.wave_in, B, n, max_val, x.normalize, x.stream); });
+    p->pre_meta.push_back(StepMeta{"peak_norm", "peak", 0, 0, static_cast<double>(B) * n * 4, 2});
+    p->pre.push_back([=](const Ctx& x) { return launch_stft(x.wave_in, B, n, T, max_val, spec, mag, mag_max, x.stream); });
+    p->pre_meta.push_back(StepMeta{"stft", "stft", 0, 0, static_cast<double>(B) * n * 4 + ft * 12, 2});
+    p->post.push_back([=](const Ctx& x) { return launch_istft_frames(mo, spec, mag_max, frames, B, T, x.stream); });
+    p->post_meta.push_back(StepMeta{"istft.frames", "istft_frames", 0, 0, ft * 12 + static_cast<double>(B) * T * 512 * 4, 1});
+    p->post.push_back([=](const Ctx& x) { return launch_istft_ola(frames, max_val, x.wave_out, B, n, T, x.stream); });
+    p->post_meta.push_back(StepMeta{"istft.ola", "istft_ola", 0, 0, static_cast<double>(B) * T * 512 * 4 + static_cast<double>(B) * n * 4, 1});
+  }
+  while (p->meta.size() < p->steps.size()) p->meta.push_back(StepMeta{"op", "op", 0, 0, 0, 1});
+  p->launches_forward = 0;
+  for (const StepMeta& m : p->meta) p->launches_forward += m.launches;
   return HVIT_OK;
 }
 
@@ -647,6 +730,17 @@ int hvit_plan_create(const hvit_model_cfg* cfg, const hvit_weights* weights, int
 
 void hvit_plan_destroy(hvit_plan* plan) { delete plan; }
 
+static Ctx enhance_ctx(hvit_plan* plan, const float* wave_in, float* wave_out, int normalize, void* stream) {
+  Ctx c;
+  memset(&c, 0, sizeof(c));
+  c.x = at<float>(plan, "mag");
+  c.y = at<float>(plan, "model_out");
+  c.mag_max = at<unsigned>(plan, "mag_max");
+  c.wave_in = wave_in; c.wave_out = wave_out; c.normalize = normalize;
+  c.stream = reinterpret_cast<cudaStream_t>(stream);
+  return c;
+}
+
 static int run_steps(hvit_plan* p, const Ctx& c) {
   for (size_t i = 0; i < p->steps.size(); ++i) {
     const int r = p->steps[i](c);
@@ -661,6 +755,7 @@ int hvit_forward(hvit_plan* plan, const float* x_dev, float* y_dev, float* attn_
     return HVIT_E_ARG;
   }
   Ctx c;
+  memset(&c, 0, sizeof(c));
   c.x = x_dev; c.y = y_dev; c.probs = attn_probs_dev; c.mag_max = nullptr;
   c.stream = reinterpret_cast<cudaStream_t>(stream);
   return run_steps(plan, c);
@@ -675,22 +770,84 @@ int hvit_enhance(hvit_plan* plan, const float* wave_in_dev, float* wave_out_dev,
     set_error("hvit_enhance: plan was created without n_samples");
     return HVIT_E_ARG;
   }
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const Geometry& g = plan->g;
-  float* max_val = at<float>(plan, "max_val");
-  unsigned* mag_max = at<unsigned>(plan, "mag_max");
-  float2* spec = at<float2>(plan, "spec");
-  float* mag = at<float>(plan, "mag");
-  float* mo = at<float>(plan, "model_out");
-  int r = launch_peak(wave_in_dev, g.B, g.n_samples, max_val, normalize, s);
+  const Ctx c = enhance_ctx(plan, wave_in_dev, wave_out_dev, normalize, stream);
+  for (const Step& st : plan->pre) {
+    const int r = st(c);
+    if (r) return r;
+  }
+  int r = run_steps(plan, c);
   if (r) return r;
-  r = launch_stft(wave_in_dev, g.B, g.n_samples, g.T, max_val, spec, mag, mag_max, s);
-  if (r) return r;
-  Ctx c;
-  c.x = mag; c.y = mo; c.probs = nullptr; c.mag_max = mag_max; c.stream = s;
-  r = run_steps(plan, c);
-  if (r) return r;
-  return launch_istft(mo, spec, mag_max, max_val, at<float>(plan, "frames"), wave_out_dev, g.B, g.n_samples, g.T, s);
+  for (const Step& st : plan->post) {
+    r = st(c);
+    if (r) return r;
+  }
+  return HVIT_OK;
+}
+
+int hvit_plan_num_steps(const hvit_plan* plan, int enhance) {
+  if (plan == nullptr) return HVIT_E_ARG;
+  return static_cast<int>(plan->steps.size() + (enhance ? plan->pre.size() + plan->post.size() : 0));
+}
+
+static const StepMeta* step_meta(const hvit_plan* plan, int enhance, int i) {
+  const int npre = enhance ? static_cast<int>(plan->pre.size()) : 0;
+  const int nmid = static_cast<int>(plan->steps.size());
+  if (i < 0) return nullptr;
+  if (i < npre) return &plan->pre_meta[i];
+  if (i < npre + nmid) return &plan->meta[i - npre];
+  if (enhance && i < npre + nmid + static_cast<int>(plan->post.size())) return &plan->post_meta[i - npre - nmid];
+  return nullptr;
+}
+
+int hvit_plan_step_info(const hvit_plan* plan, int enhance, int i, char* name, int name_len, char* kernel,
+                        int kernel_len, double* algo_flops, double* exec_flops, double* algo_bytes, int* launches) {
+  if (plan == nullptr) return HVIT_E_ARG;
+  const StepMeta* m = step_meta(plan, enhance, i);
+  if (m == nullptr) {
+    set_error("step index %d out of range", i);
+    return HVIT_E_ARG;
+  }
+  if (name != nullptr && name_len > 0) snprintf(name, name_len, "%s", m->name.c_str());
+  if (kernel != nullptr && kernel_len > 0) snprintf(kernel, kernel_len, "%s", m->kernel.c_str());
+  if (algo_flops) *algo_flops = m->algo_flops;
+  if (exec_flops) *exec_flops = m->exec_flops;
+  if (algo_bytes) *algo_bytes = m->algo_bytes;
+  if (launches) *launches = m->launches;
+  return HVIT_OK;
+}
+
+int hvit_enhance_profiled(hvit_plan* plan, const float* wave_in_dev, float* wave_out_dev, int normalize, void* stream,
+                          float* step_ms_host, int n_steps) {
+  if (plan == nullptr || wave_in_dev == nullptr || wave_out_dev == nullptr || step_ms_host == nullptr) {
+    set_error("hvit_enhance_profiled: null argument");
+    return HVIT_E_ARG;
+  }
+  if (plan->g.n_samples <= 0 || n_steps != hvit_plan_num_steps(plan, 1)) {
+    set_error("hvit_enhance_profiled: plan has no enhance stages or n_steps mismatch");
+    return HVIT_E_ARG;
+  }
+  const Ctx c = enhance_ctx(plan, wave_in_dev, wave_out_dev, normalize, stream);
+  std::vector<cudaEvent_t> ev(n_steps + 1);
+  for (auto& e : ev) cudaEventCreate(&e);
+  int r = HVIT_OK, i = 0;
+  cudaEventRecord(ev[0], c.stream);
+  auto run = [&](const std::vector<Step>& v) {
+    for (const Step& st : v) {
+      if (r == HVIT_OK) r = st(c);
+      cudaEventRecord(ev[++i], c.stream);
+    }
+  };
+  run(plan->pre);
+  run(plan->steps);
+  run(plan->post);
+  if (cudaStreamSynchronize(c.stream) != cudaSuccess && r == HVIT_OK) r = check_launch("hvit_enhance_profiled");
+  for (int k = 0; k < n_steps; ++k) {
+    float ms = 0.f;
+    if (r == HVIT_OK) cudaEventElapsedTime(&ms, ev[k], ev[k + 1]);
+    step_ms_host[k] = ms;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return r;
 }
 
 int hvit_plan_buffer(const hvit_plan* plan, const char* name, size_t* offset, int* dims, int* elem_bytes) {
@@ -709,7 +866,10 @@ int hvit_plan_buffer(const hvit_plan* plan, const char* name, size_t* offset, in
 int hvit_plan_launch_count(const hvit_plan* plan, int enhance) {
   if (plan == nullptr) return HVIT_E_ARG;
   int n = plan->launches_forward;
-  if (enhance) n += 2 /*peak*/ + 2 /*stft*/ + 2 /*istft*/;
+  if (enhance) {
+    for (const StepMeta& m : plan->pre_meta) n += m.launches;
+    for (const StepMeta& m : plan->post_meta) n += m.launches;
+  }
   return n;
 }
 
@@ -775,7 +935,7 @@ int hvit_conv3x3_16(const void* x, const void* w, const float* scale, const floa
   hvit_plan tmp;
   tmp.cfg.precision = f16 ? HVIT_PREC_FP16 : HVIT_PREC_BF16;
   const int Ho = pool ? H / 2 : (up2 ? 2 * H : H);
-  r = add_conv(&tmp, x, B, H, W, Cin, w, scale, shift, relu, pool, up2, out, Cout, Ho, Cout, nullptr);
+  r = add_conv(&tmp, "conv", x, B, H, W, Cin, w, scale, shift, relu, pool, up2, out, Cout, Ho, Cout, nullptr);
   if (r) return r;
   Ctx c;
   memset(&c, 0, sizeof(c));
@@ -789,7 +949,7 @@ int hvit_conv3x3_f32(const float* x, const float* w, const float* scale, const f
   if (r) return r;
   hvit_plan tmp;
   tmp.cfg.precision = HVIT_PREC_FP32;
-  r = add_conv(&tmp, x, B, H, W, Cin, w, scale, shift, relu, 0, up2, out, Cout, up2 ? 2 * H : H, Cout, nullptr);
+  r = add_conv(&tmp, "conv", x, B, H, W, Cin, w, scale, shift, relu, 0, up2, out, Cout, up2 ? 2 * H : H, Cout, nullptr);
   if (r) return r;
   Ctx c;
   memset(&c, 0, sizeof(c));
@@ -839,9 +999,11 @@ int hvit_istft(const float* mag_norm, const void* spec, const void* mag_max, con
                float* wave_out, int B, int n, void* stream) {
   int r = require_sm100();
   if (r) return r;
-  return launch_istft(mag_norm, reinterpret_cast<const float2*>(spec), reinterpret_cast<const unsigned*>(mag_max),
-                      reinterpret_cast<const float*>(max_val), frames, wave_out, B, n, 1 + n / 128,
-                      reinterpret_cast<cudaStream_t>(stream));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  r = launch_istft_frames(mag_norm, reinterpret_cast<const float2*>(spec), reinterpret_cast<const unsigned*>(mag_max),
+                          frames, B, 1 + n / 128, st);
+  if (r) return r;
+  return launch_istft_ola(frames, reinterpret_cast<const float*>(max_val), wave_out, B, n, 1 + n / 128, st);
 }
 
 }  // extern "C"

@@ -507,21 +507,28 @@ int launch_stft(const float* wave, int B, int n, int T, const float* max_val, fl
   return check_launch("stft");
 }
 
-int launch_istft(const float* model_out, const float2* spec, const unsigned* mag_max_bits, const float* max_val,
-                 float* frames, float* wave_out, int B, int n, int T, cudaStream_t s) {
+static void fft_smem_config() {
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FFT_SMEM);
     cudaFuncSetAttribute(istft_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FFT_SMEM);
     configured = true;
   }
+}
+
+int launch_istft_frames(const float* model_out, const float2* spec, const unsigned* mag_max_bits, float* frames, int B,
+                        int T, cudaStream_t s) {
+  fft_smem_config();
   dim3 grid((T + FR - 1) / FR, B);
   istft_frames_kernel<<<grid, FR * 32, FFT_SMEM, s>>>(model_out, spec, mag_max_bits, T, frames);
-  if (n > 0) {
-    dim3 g2((n + 255) / 256, B);
-    istft_ola_kernel<<<g2, 256, 0, s>>>(frames, reinterpret_cast<const unsigned*>(max_val), n, T, wave_out);
-  }
-  return check_launch("istft");
+  return check_launch("istft_frames");
+}
+
+int launch_istft_ola(const float* frames, const float* max_val, float* wave_out, int B, int n, int T, cudaStream_t s) {
+  if (n <= 0) return 0;
+  dim3 g2((n + 255) / 256, B);
+  istft_ola_kernel<<<g2, 256, 0, s>>>(frames, reinterpret_cast<const unsigned*>(max_val), n, T, wave_out);
+  return check_launch("istft_ola");
 }
 
 template <typename T>

@@ -73,9 +73,9 @@ int launch_attn_probs_16(const void* qkv16, int f16, float* probs, int B, int N,
 int launch_peak(const float* wave, int B, int n, float* max_val /*[B]*/, int normalize, cudaStream_t s);
 int launch_stft(const float* wave, int B, int n, int T, const float* max_val, float2* spec /*[B,257,T]*/,
                 float* mag /*[B,257,T]*/, unsigned* mag_max_bits /*[B]*/, cudaStream_t s);
-int launch_istft(const float* model_out /*[B,257,T] in [-1,1]*/, const float2* spec, const unsigned* mag_max_bits,
-                 const float* max_val, float* frames /*[B,T,512] scratch*/, float* wave_out, int B, int n, int T,
-                 cudaStream_t s);
+int launch_istft_frames(const float* model_out /*[B,257,T] in [-1,1]*/, const float2* spec,
+                        const unsigned* mag_max_bits, float* frames /*[B,T,512]*/, int B, int T, cudaStream_t s);
+int launch_istft_ola(const float* frames, const float* max_val, float* wave_out, int B, int n, int T, cudaStream_t s);
 int launch_stem(const float* x /*[B,H,W]*/, const unsigned* mag_max_bits /*nullable*/, const float* w /*[9][C]*/,
                 const float* scale, const float* shift, void* out, int dt, int B, int H, int W, int C, int pool,
                 cudaStream_t s);

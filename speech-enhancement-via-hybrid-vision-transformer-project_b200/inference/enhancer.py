@@ -74,6 +74,20 @@ class AudioEnhancer:
                                              _lib.current_stream_ptr()), "hvit_enhance")
         return out
 
+    def enhance_pinned(self, pinned_in: torch.Tensor, pinned_out: torch.Tensor, normalize: bool = True,
+                       synchronize: bool = True) -> torch.Tensor:
+        """Host-to-host batch API on caller-owned pinned buffers [B, n] fp32: async H2D, enhance, async D2H on the
+        current stream (what ``enhance_batch`` does after staging the numpy input)."""
+        B, n = pinned_in.shape
+        _, _, d_in, d_out = self._staging(B, n)
+        with torch.cuda.device(self._dev):
+            d_in.copy_(pinned_in, non_blocking=True)
+            self.enhance_device(d_in, normalize=normalize, out=d_out)
+            pinned_out.copy_(d_out, non_blocking=True)
+            if synchronize:
+                torch.cuda.current_stream().synchronize()
+        return pinned_out
+
     @torch.no_grad()
     def enhance_batch(self, noisy_audio: Union[np.ndarray, Sequence[np.ndarray]], normalize: bool = True) -> np.ndarray:
         """Batched extension of :meth:`enhance`: equal-length clips [B, n] (numpy) -> [B, n] float32."""
@@ -83,11 +97,7 @@ class AudioEnhancer:
         B, n = x.shape
         pin_in, pin_out, d_in, d_out = self._staging(B, n)
         pin_in.numpy()[...] = x
-        with torch.cuda.device(self._dev):
-            d_in.copy_(pin_in, non_blocking=True)
-            self.enhance_device(d_in, normalize=normalize, out=d_out)
-            pin_out.copy_(d_out, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+        self.enhance_pinned(pin_in, pin_out, normalize=normalize, synchronize=True)
         return pin_out.numpy().copy()
 
     # ------------------------------------------------------------------ reference API

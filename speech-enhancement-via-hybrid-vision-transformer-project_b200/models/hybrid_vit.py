@@ -64,6 +64,28 @@ class _Plan:
     def launch_count(self, enhance: bool) -> int:
         return self.lib.hvit_plan_launch_count(self.handle, 1 if enhance else 0)
 
+    def steps(self, enhance: bool = True):
+        """[{name, kernel, algo_flops, exec_flops, algo_bytes, launches}] for measurement (bench.py)."""
+        e = 1 if enhance else 0
+        out = []
+        for i in range(self.lib.hvit_plan_num_steps(self.handle, e)):
+            name, kern = C.create_string_buffer(64), C.create_string_buffer(32)
+            af, ef, ab, nl = C.c_double(), C.c_double(), C.c_double(), C.c_int()
+            _lib.check(self.lib.hvit_plan_step_info(self.handle, e, i, name, 64, kern, 32, C.byref(af), C.byref(ef),
+                                                    C.byref(ab), C.byref(nl)), "hvit_plan_step_info")
+            out.append(dict(name=name.value.decode(), kernel=kern.value.decode(), algo_flops=af.value,
+                            exec_flops=ef.value, algo_bytes=ab.value, launches=nl.value))
+        return out
+
+    def enhance_profiled(self, wave_in: torch.Tensor, wave_out: torch.Tensor, normalize: bool = True):
+        """One enhance call with a CUDA event after every step; returns per-step milliseconds (synchronises)."""
+        n = self.lib.hvit_plan_num_steps(self.handle, 1)
+        ms = (C.c_float * n)()
+        _lib.check(self.lib.hvit_enhance_profiled(self.handle, wave_in.data_ptr(), wave_out.data_ptr(),
+                                                  1 if normalize else 0, _lib.current_stream_ptr(), ms, n),
+                   "hvit_enhance_profiled")
+        return list(ms)
+
     def __del__(self):
         try:
             if self.handle:
