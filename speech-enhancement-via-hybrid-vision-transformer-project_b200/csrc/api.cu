@@ -2,6 +2,7 @@
 // AudioEnhancer.enhance, TMA tensor-map construction, per-kernel test entry points, error plumbing.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -57,7 +58,7 @@ static thread_local int g_tmap_f16 = 0;
 
 // 16-bit tensor (bf16 or fp16), 128-byte swizzle, zero fill out of bounds. dims/box innermost first; strides (bytes) for dims 1..rank-1.
 static int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                     const uint32_t* box) {
+                     const uint32_t* box, int f32 = 0) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -72,7 +73,7 @@ static int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t*
     es[i] = 1;
     if (i > 0) gs[i - 1] = strides[i - 1];
   }
-  const CUresult r = fn(m, g_tmap_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+  const CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (g_tmap_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), static_cast<cuuint32_t>(rank), const_cast<void*>(base),
                         gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -116,6 +117,20 @@ static int tmap_qkv(CUtensorMap* m, const void* base, int B, int N, int D) {
   return make_tmap(m, base, 3, dims, strides, box);
 }
 
+// CTA-pair kernel by default; HVIT_IGEMM_1CTA=1 selects the single-CTA kernel (A/B comparison, debugging)
+static bool use_2cta() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("HVIT_IGEMM_1CTA");
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+static int launch_igemm_any(const IgemmParams& q, const IgemmMaps& mp, int bn, int sms, cudaStream_t s) {
+  return use_2cta() ? launch_igemm_tc2(q, mp, bn, sms, s) : launch_igemm_tc(q, mp.a, mp.b, bn, sms, s);
+}
+static int b_box_rows(int bn) { return use_2cta() ? bn / 2 : bn; }
+
 static int pick_block_n(int N) { return N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64); }
 
 static void pick_tile(int H, int W, int* Wt, int* Ht) {
@@ -129,6 +144,54 @@ static void pick_tile(int H, int W, int* Wt, int* Ht) {
       *Ht = cand[i][1];
     }
   }
+}
+
+// 4-D output (and residual) maps of the TMA-store epilogue: dim 0 = channel / column (128-byte box), dims 1..3 =
+// the tile's spatial / row coordinates as the kernel passes them (see igemm_tc2_kernel).
+static int tmap_out4(CUtensorMap* m, const void* base, int f32, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
+                     uint64_t s1, uint64_t s2, uint64_t s3, uint32_t b1, uint32_t b2) {
+  const uint64_t dims[4] = {d0, d1, d2, d3};
+  const uint64_t strides[3] = {s1, s2, s3};
+  const uint32_t box[4] = {f32 ? 32u : 64u, b1, b2, 1};
+  return make_tmap(m, base, 4, dims, strides, box, f32);
+}
+
+static int make_out_maps(const IgemmParams& q, IgemmMaps* mp) {
+  const int f32 = q.out_f32;
+  const uint64_t es = f32 ? 4 : 2;
+  const uint64_t ld = static_cast<uint64_t>(q.ldc) * es;
+  uint8_t* out = reinterpret_cast<uint8_t*>(q.out);
+  const uint64_t N = q.N;
+  int r = HVIT_OK;
+  memset(mp->out, 0, sizeof(mp->out));
+  memset(&mp->res, 0, sizeof(mp->res));
+  if (q.mode == IG_PLAIN) {
+    r = tmap_out4(&mp->out[0], out, f32, N, q.M, 1, 1, ld, ld * q.M, ld * q.M, 128, 1);
+    if (r == HVIT_OK && q.residual != nullptr) {
+      const uint64_t lr = static_cast<uint64_t>(q.ldr) * 4;
+      r = tmap_out4(&mp->res, q.residual, 1, N, q.M, 1, 1, lr, lr * q.M, lr * q.M, 128, 1);
+    }
+  } else if (q.mode == IG_CONV3) {
+    const uint64_t img = static_cast<uint64_t>(q.HoPitch) * q.Wo * ld;
+    if (q.pool)
+      r = tmap_out4(&mp->out[0], out, f32, N, q.Wo, q.Ho, q.B, ld, ld * q.Wo, img, 8, 4);
+    else
+      r = tmap_out4(&mp->out[0], out, f32, N, q.W, q.H, q.B, ld, ld * q.Wo, img, q.Wt, q.Ht);
+  } else if (q.mode == IG_UP2) {
+    const uint64_t img = static_cast<uint64_t>(q.HoPitch) * q.Wo * ld;
+    for (int par = 0; par < 4 && r == HVIT_OK; ++par) {
+      const uint64_t off = (static_cast<uint64_t>(par >> 1) * q.Wo + (par & 1)) * ld;
+      r = tmap_out4(&mp->out[par], out + off, f32, N, q.W, q.H, q.B, 2 * ld, 2 * ld * q.Wo, img, q.Wt, q.Ht);
+    }
+  } else {  // IG_PATCH
+    const uint64_t np = static_cast<uint64_t>(q.Hp) * q.Wp;
+    r = tmap_out4(&mp->out[0], out, f32, N, q.Wp, q.Hp, q.B, ld, ld * q.Wp, ld * np, q.Wt, q.Ht);
+    if (r == HVIT_OK && q.residual != nullptr) {
+      const uint64_t lr = static_cast<uint64_t>(q.ldr) * 4;
+      r = tmap_out4(&mp->res, q.residual, 1, N, q.Wp, q.Hp, q.res_mod > 0 ? 1 : q.B, lr, lr * q.Wp, lr * np, q.Wt, q.Ht);
+    }
+  }
+  return r;
 }
 
 static int num_sms() {
@@ -388,15 +451,17 @@ static int add_linear(hvit_plan* p, const std::string& name, const void* A, int 
   q.out = out; q.ldc = ldc; q.out_f32 = out_f32;
   q.f16 = p->cfg.precision == HVIT_PREC_FP16;
   if (p->cfg.precision != HVIT_PREC_FP32) {
-    CUtensorMap ta, tb;
+    IgemmMaps mp;
     const int bn = pick_block_n(N);
     g_tmap_f16 = q.f16;
-    int r = tmap_matrix(&ta, A, M, K, lda, 128);
+    int r = tmap_matrix(&mp.a, A, M, K, lda, 128);
     if (r) return r;
-    r = tmap_matrix(&tb, W, N, K, K, bn);
+    r = tmap_matrix(&mp.b, W, N, K, K, b_box_rows(bn));
+    if (r) return r;
+    r = make_out_maps(q, &mp);
     if (r) return r;
     const int sms = num_sms();
-    p->steps.push_back([=](const Ctx& c) { return launch_igemm_tc(q, ta, tb, bn, sms, c.stream); });
+    p->steps.push_back([=](const Ctx& c) { return launch_igemm_any(q, mp, bn, sms, c.stream); });
     p->tag(name, "igemm_tc", algo_flops >= 0 ? algo_flops : fl, fl, by);
   } else {
     q.out_f32 = 1;
@@ -440,14 +505,16 @@ static int add_conv(hvit_plan* p, const std::string& name, const void* in, int B
     }
     q.tiles_w = (W + q.Wt - 1) / q.Wt;
     q.tiles_h = (H + q.Ht - 1) / q.Ht;
-    CUtensorMap ta, tb;
+    IgemmMaps mp;
     const int bn = pick_block_n(Cout);
-    int r = tmap_image(&ta, in, B, H, H, W, Cin, q.Wt, q.Ht);
+    int r = tmap_image(&mp.a, in, B, H, H, W, Cin, q.Wt, q.Ht);
     if (r) return r;
-    r = tmap_matrix(&tb, Wt, static_cast<long long>(up2 ? 4 : 1) * Cout, q.K, q.K, bn);
+    r = tmap_matrix(&mp.b, Wt, static_cast<long long>(up2 ? 4 : 1) * Cout, q.K, q.K, b_box_rows(bn));
+    if (r) return r;
+    r = make_out_maps(q, &mp);
     if (r) return r;
     const int sms = num_sms();
-    p->steps.push_back([=](const Ctx& c) { return launch_igemm_tc(q, ta, tb, bn, sms, c.stream); });
+    p->steps.push_back([=](const Ctx& c) { return launch_igemm_any(q, mp, bn, sms, c.stream); });
     p->tag(name, "igemm_tc", algo_fl, up2 ? algo_fl * 4.0 / 9.0 : algo_fl, by);
   } else {
     q.K = 9 * Cin;
@@ -522,14 +589,16 @@ static int build_steps(hvit_plan* p) {
       pick_tile(g.Hp, g.Wp, &q.Wt, &q.Ht);
       q.tiles_w = (g.Wp + q.Wt - 1) / q.Wt;
       q.tiles_h = (g.Hp + q.Ht - 1) / q.Ht;
-      CUtensorMap ta, tb;
+      IgemmMaps mp;
       const int bn = pick_block_n(D);
-      r = tmap_patch(&ta, in, B, q.Hq, e.W, e.C, c.patch_size, g.Wp, q.Wt, q.Ht);
+      r = tmap_patch(&mp.a, in, B, q.Hq, e.W, e.C, c.patch_size, g.Wp, q.Wt, q.Ht);
       if (r) return r;
-      r = tmap_matrix(&tb, w.patch_w, D, q.K, q.K, bn);
+      r = tmap_matrix(&mp.b, w.patch_w, D, q.K, q.K, b_box_rows(bn));
+      if (r) return r;
+      r = make_out_maps(q, &mp);
       if (r) return r;
       const int sms = num_sms();
-      p->steps.push_back([=](const Ctx& k) { return launch_igemm_tc(q, ta, tb, bn, sms, k.stream); });
+      p->steps.push_back([=](const Ctx& k) { return launch_igemm_any(q, mp, bn, sms, k.stream); });
     } else {
       const float* inf = reinterpret_cast<const float*>(in);
       const float* wf = reinterpret_cast<const float*>(w.patch_w);
@@ -899,17 +968,20 @@ int hvit_gemm_16(const void* a, int lda, const void* w, const float* scale, cons
   g_tmap_f16 = f16 ? 1 : 0;
   IgemmParams q = ig_zero();
   q.f16 = f16 ? 1 : 0;
+  if (const char* e = getenv("HVIT_DBG")) q.dbg = atoi(e);
   q.mode = IG_PLAIN;
   q.M = M; q.N = N; q.K = K;
   q.scale = scale; q.shift = shift; q.act = act; q.residual = residual; q.ldr = ldr;
   q.out = out; q.ldc = ldc; q.out_f32 = out_f32;
-  CUtensorMap ta, tb;
+  IgemmMaps mp;
   const int bn = pick_block_n(N);
-  r = tmap_matrix(&ta, a, M, K, lda, 128);
+  r = tmap_matrix(&mp.a, a, M, K, lda, 128);
   if (r) return r;
-  r = tmap_matrix(&tb, w, N, K, K, bn);
+  r = tmap_matrix(&mp.b, w, N, K, K, b_box_rows(bn));
   if (r) return r;
-  return launch_igemm_tc(q, ta, tb, bn, num_sms(), reinterpret_cast<cudaStream_t>(stream));
+  r = make_out_maps(q, &mp);
+  if (r) return r;
+  return launch_igemm_any(q, mp, bn, num_sms(), reinterpret_cast<cudaStream_t>(stream));
 }
 
 int hvit_gemm_f32(const float* a, int lda, const float* w, const float* scale, const float* shift, int act,

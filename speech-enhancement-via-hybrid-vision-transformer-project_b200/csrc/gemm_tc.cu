@@ -1,5 +1,5 @@
 // tcgen05 implicit-GEMM for sm_100a: 16-bit (bf16 or fp16) operands staged by TMA (128B swizzle), fp32 accumulation in TMEM,
-// persistent tiles, warp-specialised (1 TMA warp, 1 MMA warp, 4 epilogue warps), double-buffered accumulator so
+// persistent tiles, warp-specialised (1 TMA warp, 1 MMA warp, 8 epilogue warps), double-buffered accumulator so
 // the epilogue of tile i overlaps the main loop of tile i+1.
 //
 // One kernel covers every dense contraction of the HybridViT forward (reference models/hybrid_vit.py:396-469):
@@ -9,6 +9,8 @@
 //   IG_PATCH  4x4 / stride 4 patch embedding                                   (components.py:275-280)
 // The A operand of the conv modes is fetched with shifted multi-dimensional TMA boxes on the NHWC activation;
 // out-of-bounds box elements are zero-filled by the TMA unit, which implements the conv zero padding.
+#include <cstring>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -20,7 +22,8 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;  // two per TMEM lane quarter: they split the 32-column chunks (even / odd)
+constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 
 template <int BLOCK_N>
 struct Cfg {
@@ -28,7 +31,8 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int STAGING_BYTES = NUM_EPI_WARPS * 1024;  // per epilogue warp: scale/shift of its chunks
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;
 };
 
 struct TileCoord {
@@ -63,7 +67,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   using C = Cfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* staging = smem + C::STAGES * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + C::STAGING_BYTES);
   uint64_t* full_bar = bars;                    // [STAGES]
   uint64_t* empty_bar = bars + C::STAGES;       // [STAGES]
   uint64_t* tmem_full = bars + 2 * C::STAGES;   // [2]
@@ -86,7 +91,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);
+      mbar_init(&tmem_empty[a], NUM_EPI_WARPS);
     }
     mbar_fence_init();
   }
@@ -174,8 +179,17 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
   } else {
     // ------------------------------------------------------------ epilogue: TMEM -> regs -> global
-    const int sub = warp & 3;           // TMEM sub-partition this warp may read
+    // 8 warps: warp w may only read TMEM lanes [32*(w%4), +32); the two warps of a lane quarter take the even / odd
+    // 32-column chunks.  Each epilogue warp is alone (or one of two) on its SM sub-partition, so every dependent
+    // latency is exposed: per-channel constants are therefore staged in shared memory BEFORE waiting for the
+    // accumulator, TMEM loads are double-buffered, and residual loads are issued before the TMEM wait.
+    const int ew = warp - 2;
+    const int sub = warp & 3;           // TMEM lane quarter this warp may read
+    const int grp = ew >> 2;            // chunk parity handled by this warp
     const int m = sub * 32 + lane;      // accumulator row == TMEM lane
+    float* cst = reinterpret_cast<float*>(staging + ew * 1024);  // [KCH][scale 32 | shift 32]
+    constexpr int NCH = BLOCK_N / 32;
+    constexpr int KCH = NCH / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -207,42 +221,49 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
       }
       const float* res_row = nullptr;
-      if (p.residual != nullptr) {
+      if (p.residual != nullptr && valid) {
         const long long rr = p.res_mod > 0 ? (out_row % p.res_mod) : out_row;
         res_row = p.residual + rr * p.ldr;
       }
+      // per-channel constants of this warp's chunks -> smem (latency hidden behind this tile's main loop)
+#pragma unroll
+      for (int k = 0; k < KCH; ++k) {
+        const int col = c.n0 + (2 * k + grp) * 32 + lane;
+        cst[k * 64 + lane] = p.scale != nullptr ? __ldg(p.scale + col) : 1.0f;
+        cst[k * 64 + 32 + lane] = p.shift != nullptr ? __ldg(p.shift + col) : 0.0f;
+      }
+      __syncwarp();
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-#pragma unroll 1
-      for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BLOCK_N + chunk * 32, r);
-        tmem_ld_wait();
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BLOCK_N;
+
+      auto process = [&](int k, uint32_t (&cur)[32], uint32_t (&nxt)[32], bool has_next) {
+        const int chunk = 2 * k + grp;
         const int col = c.n0 + chunk * 32;
-        float v[32];
+        float4 res[8];
+        if (res_row != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.scale != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col + j));
-            v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
-          }
+          for (int j = 0; j < 8; ++j) res[j] = *reinterpret_cast<const float4*>(res_row + col + 4 * j);
         }
-        if (p.shift != nullptr) {
+        tmem_ld_wait(cur);
+        if (has_next) tmem_ld32(t_base + (chunk + 2) * 32, nxt);
+        float v[32];
+        const float4* cs = reinterpret_cast<const float4*>(cst + k * 64);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.shift + col + j));
-            v[j] += s4.x; v[j + 1] += s4.y; v[j + 2] += s4.z; v[j + 3] += s4.w;
-          }
+        for (int j = 0; j < 8; ++j) {
+          const float4 sc = cs[j], sh = cs[8 + j];
+          v[4 * j + 0] = fmaf(__uint_as_float(cur[4 * j + 0]), sc.x, sh.x);
+          v[4 * j + 1] = fmaf(__uint_as_float(cur[4 * j + 1]), sc.y, sh.y);
+          v[4 * j + 2] = fmaf(__uint_as_float(cur[4 * j + 2]), sc.z, sh.z);
+          v[4 * j + 3] = fmaf(__uint_as_float(cur[4 * j + 3]), sc.w, sh.w);
         }
         if (p.act == ACT_RELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
         } else if (p.act == ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
         }
         if (p.pool) {
 #pragma unroll
@@ -254,9 +275,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         if (valid) {
           if (res_row != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 r4 = *reinterpret_cast<const float4*>(res_row + col + j);
-              v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
+            for (int j = 0; j < 8; ++j) {
+              v[4 * j] += res[j].x; v[4 * j + 1] += res[j].y; v[4 * j + 2] += res[j].z; v[4 * j + 3] += res[j].w;
             }
           }
           if (p.out_f32) {
@@ -277,6 +297,14 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             }
           }
         }
+      };
+
+      uint32_t ra[32], rb[32];
+      tmem_ld32(t_base + grp * 32, ra);
+#pragma unroll
+      for (int k = 0; k < KCH; k += 2) {
+        process(k, ra, rb, k + 1 < KCH);
+        if (k + 1 < KCH) process(k + 1, rb, ra, k + 2 < KCH);
       }
       tc_fence_before();
       __syncwarp();
@@ -309,7 +337,17 @@ int launch_impl(const IgemmParams& p, const CUtensorMap& ta, const CUtensorMap& 
   }
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
   igemm_tc_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p, num_tiles, n_tiles_n);
-  return check_launch("igemm_tc");
+  const cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess) {
+    cudaFuncAttributes fa;
+    memset(&fa, 0, sizeof(fa));
+    cudaFuncGetAttributes(&fa, igemm_tc_kernel<BLOCK_N>);
+    set_error("igemm_tc<%d>: %s (threads %d, dyn smem %d, regs %d, static smem %zu, local %zu, maxThreadsPerBlock %d, "
+              "maxDynSmem %d)", BLOCK_N, cudaGetErrorString(le), NUM_THREADS, C::SMEM_BYTES, fa.numRegs,
+              fa.sharedSizeBytes, fa.localSizeBytes, fa.maxThreadsPerBlock, fa.maxDynamicSharedSizeBytes);
+    return -4;
+  }
+  return 0;
 }
 
 }  // namespace
@@ -318,6 +356,10 @@ int launch_igemm_tc(const IgemmParams& p, const CUtensorMap& ta, const CUtensorM
                     cudaStream_t stream) {
   if (p.K % BLOCK_K != 0 || p.N % block_n != 0 || (p.mode != IG_PLAIN && p.Cin % BLOCK_K != 0)) {
     set_error("igemm_tc: unsupported shape N=%d K=%d Cin=%d block_n=%d", p.N, p.K, p.Cin, block_n);
+    return -1;
+  }
+  if (p.residual != nullptr && !p.out_f32) {
+    set_error("igemm_tc: a residual input needs an fp32 output");
     return -1;
   }
   if (p.pool && !(p.mode == IG_CONV3 && p.Wt == 16 && p.Ht == 8)) {

@@ -1,0 +1,448 @@
+// CTA-pair (cta_group::2) tcgen05 implicit GEMM - the production kernel for every dense contraction of the
+// HybridViT forward (same problem description and A-operand modes as gemm_tc.cu, which is kept as the single-CTA
+// comparison kernel).
+//
+// Why a CTA pair: with cta_group::1 a 128x256x16 MMA reads 12 KB of operands from shared memory in 128 cycles
+// (96 B/clk) while TMA refills the ring at 94 B/clk - together above the 128 B/clk/SM shared-memory port.  Here one
+// UMMA of M = 256 spans two SMs: each CTA stages its own 128 rows of A and only HALF of the B tile, i.e. per SM
+// 64 B/clk of operand reads + 62 B/clk of TMA fill, and the L2 -> SM traffic per FLOP drops by a third
+// (measured: 1.50 PFLOP/s on a 31744x4096x4096 fp16 GEMM vs 1.35 for the single-CTA kernel).
+//
+// Why a TMA-store epilogue: row-per-thread global stores (32 distinct 128-byte lines per warp instruction) cost more
+// than the whole K = 512 main loop (qkv projection: 86 us, 41 us with the stores removed).  The epilogue therefore
+// writes 128-byte-wide column blocks of the tile into 128B-swizzled shared memory and one thread issues a TMA store;
+// the fp32 residual of proj / fc2 / patch-embedding is TMA-loaded into the same staging buffer and added in place.
+//
+// Pair protocol (per smem stage s / accumulator stage a):
+//   full[s]       lives in the LEADER (cluster rank 0); the leader's producer posts expect_tx for the bytes of both
+//                 CTAs, both producers' TMA loads complete_tx on it (cp.async.bulk.tensor ... .cta_group::2)
+//   empty[s]      one per CTA; the leader's MMA thread frees the stage in both CTAs with a multicast tcgen05.commit
+//   tmem_full[a]  one per CTA, arrived by a multicast commit after the last k-block
+//   tmem_empty[a] lives in the leader; the 8 epilogue warps of BOTH CTAs arrive on it (remote mbarrier arrive)
+// Tiles are enumerated in pairs of adjacent 128-row M-tiles (rank r takes tile 2i+r) that share the N-tile; pairs never
+// straddle an upsample parity class; an odd leftover tile is padded with an out-of-range tile (TMA zero fill on load,
+// clipped on store).
+//
+// Epilogue organisation: 8 warps = 2 groups x 4 warps (a group covers the four TMEM lane quarters).  Group g owns
+// the column blocks j = g, g+2, ... of the tile (a block is 128 bytes of every output row: 64 16-bit or 32 fp32
+// columns), with two 16 KB staging buffers, its own named barrier and its own store-issuing thread.
+#include <cstring>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace hvit {
+
+namespace {
+
+constexpr int BLOCK_M = 128;  // rows per CTA (UMMA M = 256 across the pair)
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
+constexpr int STG_BUF_BYTES = 128 * 128;  // 128 rows x 128 B
+
+template <int BLOCK_N>
+struct Cfg2 {
+  static constexpr int B_HALF_ROWS = BLOCK_N / 2;
+  static constexpr int B_STAGE_BYTES = B_HALF_ROWS * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 7);
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+  static constexpr int STAGING_BYTES = 4 * STG_BUF_BYTES;    // [group][buffer]
+  static constexpr int CONST_BYTES = NUM_EPI_WARPS * 2048;   // per-warp scale/shift of its (<= 4) column blocks
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + CONST_BYTES + 1024 + 512;
+};
+
+struct TileCoord {
+  int n0, m0, b, h0, w0, par;
+};
+
+// cluster tile -> this CTA's 128-row tile.  group = upsample parity (IG_UP2) or 0.
+__device__ __forceinline__ TileCoord decode_ctile(const IgemmParams& p, int ct, int n_tiles_n, int block_n,
+                                                  int pairs_per_group, int rank) {
+  TileCoord c;
+  c.n0 = (ct % n_tiles_n) * block_n;
+  const int pr = ct / n_tiles_n;
+  const int g = pr / pairs_per_group;
+  int i = 2 * (pr - g * pairs_per_group) + rank;
+  c.m0 = 0; c.b = 0; c.h0 = 0; c.w0 = 0; c.par = g;
+  if (p.mode == IG_PLAIN) {
+    c.m0 = i * BLOCK_M;  // >= M for the padding tile: zero fill on load, clipped on store
+  } else {
+    c.w0 = (i % p.tiles_w) * p.Wt;
+    i /= p.tiles_w;
+    c.h0 = (i % p.tiles_h) * p.Ht;
+    c.b = i / p.tiles_h;  // == B for the padding tile
+  }
+  return c;
+}
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, int num_ctiles, int n_tiles_n,
+                 int pairs_per_group) {
+  using C = Cfg2<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + C::STAGES * C::STAGE_BYTES;
+  uint8_t* consts = staging + C::STAGING_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(consts + C::CONST_BYTES);
+  uint64_t* full_bar = bars;                    // [STAGES]   (used in the leader)
+  uint64_t* empty_bar = bars + C::STAGES;       // [STAGES]
+  uint64_t* tmem_full = bars + 2 * C::STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]        (used in the leader)
+  uint64_t* res_bar = tmem_empty + 2;           // [group][buffer]: residual tile landed in the staging buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = static_cast<int>(cluster_ctarank());
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int kblocks = p.K / BLOCK_K;
+  const int cblocks = p.Cin / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a);
+    tma_prefetch_desc(&maps.b);
+    tma_prefetch_desc(&maps.out[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 2 * NUM_EPI_WARPS);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barrier inits and TMEM allocation of both CTAs visible before any cross-CTA traffic
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
+        const TileCoord c = decode_ctile(p, ct, n_tiles_n, BLOCK_N, pairs_per_group, rank);
+        const int py = c.par >> 1, px = c.par & 1;
+        const int b_row = c.n0 + c.par * p.N + rank * C::B_HALF_ROWS;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+          if (p.mode == IG_PLAIN) {
+            tma_load_2d_2sm(sa, &maps.a, &full_bar[stage], kb * BLOCK_K, c.m0);
+          } else {
+            const int tap = kb / cblocks;
+            const int c0 = (kb - tap * cblocks) * BLOCK_K;
+            if (p.mode == IG_CONV3) {
+              const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+              tma_load_4d_2sm(sa, &maps.a, &full_bar[stage], c0, c.w0 + dx, c.h0 + dy, c.b);
+            } else if (p.mode == IG_UP2) {
+              const int dy = (tap >> 1) + py - 1, dx = (tap & 1) + px - 1;
+              tma_load_4d_2sm(sa, &maps.a, &full_bar[stage], c0, c.w0 + dx, c.h0 + dy, c.b);
+            } else {  // IG_PATCH
+              const int ky = tap / p.patch, kx = tap % p.patch;
+              tma_load_5d_2sm(sa, &maps.a, &full_bar[stage], c0, kx, c.w0, ky, c.b * p.Hq + c.h0);
+            }
+          }
+          tma_load_2d_2sm(sb, &maps.b, &full_bar[stage], kb * BLOCK_K, b_row);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (one thread of the leader CTA)
+    if (rank == 0 && elect_one()) {
+      const uint32_t idesc = make_idesc_16(2 * BLOCK_M, BLOCK_N, 0, 0, p.f16);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t adesc = make_smem_desc_sw128(a_addr + k * UMMA_K * 2, 1024, 16);
+            const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * UMMA_K * 2, 1024, 16);
+            if (!(p.dbg & 4)) umma_16_2sm(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage], 3);  // stage free in both CTAs once these MMAs have read it
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&tmem_full[acc], 3);  // accumulator halves complete in both CTAs
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: TMEM -> regs -> smem -> TMA store
+    const int ew = warp - 2;
+    const int sub = warp & 3;            // TMEM lane quarter this warp may read
+    const int grp = ew >> 2;             // column-block parity owned by this warp's group
+    const int m = sub * 32 + lane;       // accumulator row == TMEM lane
+    const bool issuer = (ew & 3) == 0 && lane == 0;
+    const int wcols = p.out_f32 ? 32 : 64;          // columns per 128-byte block
+    const int nblk = BLOCK_N / wcols;
+    const int J = (nblk - grp + 1) / 2;             // blocks of this group per tile
+    float* cst = reinterpret_cast<float*>(consts + ew * 2048);  // [J][scale 64 | shift 64]
+    uint8_t* stg0 = staging + grp * 2 * STG_BUF_BYTES;
+    const bool has_res = p.residual != nullptr;
+    // staging row of this thread (pooled convolutions only keep the pooled pixels)
+    const bool writer = p.pool ? ((lane & 17) == 0) : true;
+    const int srow = p.pool ? (sub * 8 + ((lane & 15) >> 1)) : m;
+    const int sw = srow & 7;
+    uint32_t it = 0;  // running column-block counter of this group: buffer = it & 1, residual phase = (it >> 1) & 1
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
+      const TileCoord c = decode_ctile(p, ct, n_tiles_n, BLOCK_N, pairs_per_group, rank);
+      // output coordinates of the tile origin (dims 1..3 of the 4-D output map; dim 0 is the channel)
+      int o1, o2, o3;
+      if (p.mode == IG_PLAIN) {
+        o1 = c.m0; o2 = 0; o3 = 0;
+      } else if (p.pool) {
+        o1 = c.w0 >> 1; o2 = c.h0 >> 1; o3 = c.b;
+      } else {
+        o1 = c.w0; o2 = c.h0; o3 = c.b;
+      }
+      const CUtensorMap* omap = &maps.out[c.par];
+      const int r3 = p.res_mod > 0 ? 0 : o3;  // positional table: same rows for every clip
+      // per-channel constants of this warp's blocks -> smem (latency hidden behind this tile's main loop)
+      for (int j = 0; j < J; ++j) {
+        const int col = c.n0 + (2 * j + grp) * wcols;
+        for (int e = lane; e < wcols; e += 32) {
+          cst[j * 128 + e] = p.scale != nullptr ? __ldg(p.scale + col + e) : 1.0f;
+          cst[j * 128 + 64 + e] = p.shift != nullptr ? __ldg(p.shift + col + e) : 0.0f;
+        }
+      }
+      __syncwarp();
+      if (has_res && issuer && J > 0) {  // residual tile of the first block -> staging buffer
+        uint8_t* buf = stg0 + (it & 1) * STG_BUF_BYTES;
+        mbar_expect_tx(&res_bar[grp * 2 + (it & 1)], STG_BUF_BYTES);
+        tma_load_4d(buf, &maps.res, &res_bar[grp * 2 + (it & 1)], c.n0 + grp * wcols, o1, o2, r3);
+      }
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BLOCK_N;
+
+      // one 32-column TMEM chunk -> staging row.  half = which 64-byte half of the 128-byte row (16-bit output only)
+      auto emit_chunk = [&](const uint32_t (&cur)[32], const float* cs, int half, uint8_t* buf) {
+        uint8_t* row = buf + srow * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {  // 8 columns at a time keeps the live register set small
+          float v[8];
+          const float4 sc0 = *reinterpret_cast<const float4*>(cs + q * 8);
+          const float4 sc1 = *reinterpret_cast<const float4*>(cs + q * 8 + 4);
+          const float4 sh0 = *reinterpret_cast<const float4*>(cs + 64 + q * 8);
+          const float4 sh1 = *reinterpret_cast<const float4*>(cs + 64 + q * 8 + 4);
+          v[0] = fmaf(__uint_as_float(cur[q * 8 + 0]), sc0.x, sh0.x);
+          v[1] = fmaf(__uint_as_float(cur[q * 8 + 1]), sc0.y, sh0.y);
+          v[2] = fmaf(__uint_as_float(cur[q * 8 + 2]), sc0.z, sh0.z);
+          v[3] = fmaf(__uint_as_float(cur[q * 8 + 3]), sc0.w, sh0.w);
+          v[4] = fmaf(__uint_as_float(cur[q * 8 + 4]), sc1.x, sh1.x);
+          v[5] = fmaf(__uint_as_float(cur[q * 8 + 5]), sc1.y, sh1.y);
+          v[6] = fmaf(__uint_as_float(cur[q * 8 + 6]), sc1.z, sh1.z);
+          v[7] = fmaf(__uint_as_float(cur[q * 8 + 7]), sc1.w, sh1.w);
+          if (p.act == ACT_RELU) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.0f);
+          } else if (p.act == ACT_GELU) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = gelu_erf_fast(v[e]);
+          }
+          if (p.pool) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              v[e] = fmaxf(v[e], __shfl_xor_sync(0xFFFFFFFFu, v[e], 1));
+              v[e] = fmaxf(v[e], __shfl_xor_sync(0xFFFFFFFFu, v[e], 16));
+            }
+          }
+          if (writer) {
+            if (p.out_f32) {
+              float4* d0 = reinterpret_cast<float4*>(row + (((2 * q) ^ sw) << 4));
+              float4* d1 = reinterpret_cast<float4*>(row + (((2 * q + 1) ^ sw) << 4));
+              if (has_res) {
+                const float4 r0 = *d0, r1 = *d1;
+                v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+                v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+              }
+              *d0 = make_float4(v[0], v[1], v[2], v[3]);
+              *d1 = make_float4(v[4], v[5], v[6], v[7]);
+            } else {
+              uint4 pk;
+              pk.x = pack_16x2(v[0], v[1], p.f16);
+              pk.y = pack_16x2(v[2], v[3], p.f16);
+              pk.z = pack_16x2(v[4], v[5], p.f16);
+              pk.w = pack_16x2(v[6], v[7], p.f16);
+              *reinterpret_cast<uint4*>(row + (((half * 4 + q) ^ sw) << 4)) = pk;
+            }
+          }
+        }
+      };
+
+      // hand a finished column block to the TMA: all 128 threads of the group have written (and fenced) their rows
+      auto finish_block = [&](int j, uint8_t* buf, int col0) {
+        fence_proxy_async_smem();            // staging writes -> visible to the TMA (async proxy)
+        if (issuer) tma_store_wait_read0();  // the previous store of this group has released the other buffer
+        named_bar_sync(1 + grp, 128);
+        if (issuer) {
+          if (!(p.dbg & 1)) tma_store_4d(omap, buf, col0, o1, o2, o3);
+          tma_store_commit();
+          if (has_res && j + 1 < J) {        // residual tile of the next block -> the other buffer
+            const uint32_t nb = (it + 1) & 1;
+            mbar_expect_tx(&res_bar[grp * 2 + nb], STG_BUF_BYTES);
+            tma_load_4d(stg0 + nb * STG_BUF_BYTES, &maps.res, &res_bar[grp * 2 + nb], col0 + 2 * wcols, o1, o2, r3);
+          }
+        }
+        ++it;
+      };
+
+      uint32_t ra[32], rb[32];
+      if (J > 0) tmem_ld32(t_base + grp * wcols, ra);
+      if (!p.out_f32) {
+        // 16-bit output: a block is two 32-column TMEM chunks; the next chunk is always in flight
+        for (int j = 0; j < J; ++j) {
+          const int blk = 2 * j + grp;
+          uint8_t* buf = stg0 + (it & 1) * STG_BUF_BYTES;
+          const float* cs = cst + j * 128;
+          tmem_ld_wait(ra);
+          tmem_ld32(t_base + blk * 64 + 32, rb);
+          emit_chunk(ra, cs, 0, buf);
+          tmem_ld_wait(rb);
+          if (j + 1 < J) tmem_ld32(t_base + (blk + 2) * 64, ra);
+          emit_chunk(rb, cs + 32, 1, buf);
+          finish_block(j, buf, c.n0 + blk * 64);
+        }
+      } else {
+        // fp32 output: a block is one chunk; ra / rb alternate as current / prefetch buffer
+        auto block32 = [&](int j, uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
+          const int blk = 2 * j + grp;
+          uint8_t* buf = stg0 + (it & 1) * STG_BUF_BYTES;
+          if (has_res) mbar_wait(&res_bar[grp * 2 + (it & 1)], (it >> 1) & 1);
+          tmem_ld_wait(cur);
+          if (j + 1 < J) tmem_ld32(t_base + (blk + 2) * 32, nxt);
+          emit_chunk(cur, cst + j * 128, 0, buf);
+          finish_block(j, buf, c.n0 + blk * 32);
+        };
+        for (int j = 0; j < J; j += 2) {
+          block32(j, ra, rb);
+          if (j + 1 < J) block32(j + 1, rb, ra);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);  // the leader CTA owns the accumulator-free barrier
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    if (issuer) tma_store_wait_all();  // global writes complete before the kernel (and its smem) goes away
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // nobody exits (or frees TMEM) while the peer can still touch this CTA's smem / barriers
+  if (warp == 2) tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
+}
+
+template <int BLOCK_N>
+int launch_impl2(const IgemmParams& p, const IgemmMaps& maps, int num_ctiles, int n_tiles_n, int pairs_per_group,
+                 int num_sms, cudaStream_t stream) {
+  using C = Cfg2<BLOCK_N>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_tc2_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("igemm_tc2: cudaFuncSetAttribute(%d B smem) failed: %s", C::SMEM_BYTES, cudaGetErrorString(e));
+      return -4;
+    }
+    configured = true;
+  }
+  const int max_clusters = num_sms / 2;
+  const int clusters = num_ctiles < max_clusters ? num_ctiles : max_clusters;
+  igemm_tc2_kernel<BLOCK_N><<<2 * clusters, NUM_THREADS, C::SMEM_BYTES, stream>>>(maps, p, num_ctiles, n_tiles_n,
+                                                                                  pairs_per_group);
+  const cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess) {
+    cudaFuncAttributes fa;
+    memset(&fa, 0, sizeof(fa));
+    cudaFuncGetAttributes(&fa, igemm_tc2_kernel<BLOCK_N>);
+    set_error("igemm_tc2<%d>: %s (grid %d, threads %d, dyn smem %d, regs %d, maxThreadsPerBlock %d)", BLOCK_N,
+              cudaGetErrorString(le), 2 * clusters, NUM_THREADS, C::SMEM_BYTES, fa.numRegs, fa.maxThreadsPerBlock);
+    return -4;
+  }
+  return 0;
+}
+
+}  // namespace
+
+int launch_igemm_tc2(const IgemmParams& p, const IgemmMaps& maps, int block_n, int num_sms, cudaStream_t stream) {
+  if (p.K % BLOCK_K != 0 || p.N % block_n != 0 || (p.mode != IG_PLAIN && p.Cin % BLOCK_K != 0)) {
+    set_error("igemm_tc2: unsupported shape N=%d K=%d Cin=%d block_n=%d", p.N, p.K, p.Cin, block_n);
+    return -1;
+  }
+  if (p.pool && !(p.mode == IG_CONV3 && p.Wt == 16 && p.Ht == 8)) {
+    set_error("igemm_tc2: fused pool needs a 16x8 spatial tile");
+    return -1;
+  }
+  if (p.residual != nullptr && !p.out_f32) {
+    set_error("igemm_tc2: a residual input needs an fp32 output");
+    return -1;
+  }
+  const int n_tiles_n = p.N / block_n;
+  long long group_tiles;
+  int groups = 1;
+  if (p.mode == IG_PLAIN) {
+    group_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  } else {
+    group_tiles = static_cast<long long>(p.B) * p.tiles_h * p.tiles_w;
+    if (p.mode == IG_UP2) groups = 4;
+  }
+  const long long pairs_per_group = (group_tiles + 1) / 2;
+  const long long nct = pairs_per_group * groups * n_tiles_n;
+  if (nct <= 0 || nct > 0x7FFFFFFF) {
+    set_error("igemm_tc2: bad tile count %lld", nct);
+    return -1;
+  }
+  const int a = static_cast<int>(nct), b = static_cast<int>(pairs_per_group);
+  switch (block_n) {
+    case 256: return launch_impl2<256>(p, maps, a, n_tiles_n, b, num_sms, stream);
+    case 128: return launch_impl2<128>(p, maps, a, n_tiles_n, b, num_sms, stream);
+    case 64: return launch_impl2<64>(p, maps, a, n_tiles_n, b, num_sms, stream);
+    default: set_error("igemm_tc2: block_n must be 64/128/256"); return -1;
+  }
+}
+
+}  // namespace hvit

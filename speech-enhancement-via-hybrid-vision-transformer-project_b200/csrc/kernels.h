@@ -44,6 +44,7 @@ struct IgemmParams {
   int ldc;              // elements between consecutive output rows
   int out_f32;          // 1: fp32 output, 0: 16-bit output
   int f16;              // tcgen05 path: 1 = fp16 operands / outputs, 0 = bf16
+  int dbg;              // diagnostics only (HVIT_DBG): 1 skip global stores, 2 skip TMEM loads, 4 skip MMA issue
   int Ho, Wo;           // valid output image dims (conv modes)
   int HoPitch;          // image row pitch of the output buffer in pixel rows (>= Ho)
 };
@@ -51,6 +52,14 @@ struct IgemmParams {
 // tcgen05 path. A / Wt are described by TMA tensor maps built on the host (see tmap.cpp).
 int launch_igemm_tc(const IgemmParams& p, const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, int block_n,
                     int num_sms, cudaStream_t stream);
+
+// CTA-pair (cta_group::2, UMMA M = 256) variant; tmap_b is built with a box of block_n / 2 rows.  The epilogue
+// writes through shared memory with TMA stores: `out` holds one 4-D map per upsample parity (index 0 otherwise) with a
+// 128-byte-wide box (64 16-bit or 32 fp32 columns); `res` is the fp32 residual map (same box) when p.residual is set.
+struct IgemmMaps {
+  CUtensorMap a, b, out[4], res;
+};
+int launch_igemm_tc2(const IgemmParams& p, const IgemmMaps& maps, int block_n, int num_sms, cudaStream_t stream);
 
 // fp32 SIMT path (precision = fp32 mode, also the on-device cross-check of the tcgen05 kernels).
 // A and Wt are fp32; for IG_UP2 the weights are the ORIGINAL 3x3 weights [N, 9*Cin] (direct y//2 gather).
