@@ -214,6 +214,7 @@ struct Ctx {
   const float* wave_in;      // enhance only
   float* wave_out;           // enhance only
   int normalize;             // enhance only
+  int fused_resize;          // enhance: the final bilinear resize is fused into the iSTFT frame kernel
   cudaStream_t stream;
 };
 typedef std::function<int(const Ctx&)> Step;
@@ -709,7 +710,7 @@ static int build_steps(hvit_plan* p) {
     p->steps.push_back([=](const Ctx& x) { return launch_head(in, dt, hw, B, H, W, C, logits, th, x.stream); });
     p->tag("decoder." + std::to_string(c.n_dec - 1), "head", 2.0 * B * H * W * C * 9.0, 2.0 * B * H * W * C * 9.0,
            static_cast<double>(B) * H * W * (C * g.es + 8));
-    p->steps.push_back([=](const Ctx& x) { return launch_resize(th, B, H, W, x.y, F, T, x.stream); });
+    p->steps.push_back([=](const Ctx& x) { return x.fused_resize ? 0 : launch_resize(th, B, H, W, x.y, F, T, x.stream); });
     p->tag("resize", "resize", 0, 0, static_cast<double>(B) * (H * W + F * T) * 4);
   }
   // enhance-only stages around the model
@@ -726,7 +727,10 @@ static int build_steps(hvit_plan* p) {
     p->pre_meta.push_back(StepMeta{"peak_norm", "peak", 0, 0, static_cast<double>(B) * n * 4, 2});
     p->pre.push_back([=](const Ctx& x) { return launch_stft(x.wave_in, B, n, T, max_val, spec, mag, mag_max, x.stream); });
     p->pre_meta.push_back(StepMeta{"stft", "stft", 0, 0, static_cast<double>(B) * n * 4 + ft * 12, 2});
-    p->post.push_back([=](const Ctx& x) { return launch_istft_frames(mo, spec, mag_max, frames, B, T, x.stream); });
+    const CatGeo& hl = g.cat[c.n_dec - 1];
+    const float* th = at<float>(p, "tanh");
+    const int Hs = hl.H, Ws = hl.W;
+    p->post.push_back([=](const Ctx& x) { return launch_istft_frames(mo, th, Hs, Ws, spec, mag_max, frames, B, T, x.stream); });
     p->post_meta.push_back(StepMeta{"istft.frames", "istft_frames", 0, 0, ft * 12 + static_cast<double>(B) * T * 512 * 4, 1});
     p->post.push_back([=](const Ctx& x) { return launch_istft_ola(frames, max_val, x.wave_out, B, n, T, x.stream); });
     p->post_meta.push_back(StepMeta{"istft.ola", "istft_ola", 0, 0, static_cast<double>(B) * T * 512 * 4 + static_cast<double>(B) * n * 4, 1});
@@ -788,6 +792,7 @@ int hvit_plan_create(const hvit_model_cfg* cfg, const hvit_weights* weights, int
     set_error("workspace too small or not 1024-byte aligned: need %zu bytes, got %zu", p->g.total, workspace_bytes);
     r = HVIT_E_ALLOC;
   }
+  if (r == HVIT_OK && n_samples > 0) r = ensure_fft_tables(nullptr);
   if (r == HVIT_OK) r = build_steps(p);
   if (r != HVIT_OK) {
     delete p;
@@ -806,6 +811,7 @@ static Ctx enhance_ctx(hvit_plan* plan, const float* wave_in, float* wave_out, i
   c.y = at<float>(plan, "model_out");
   c.mag_max = at<unsigned>(plan, "mag_max");
   c.wave_in = wave_in; c.wave_out = wave_out; c.normalize = normalize;
+  c.fused_resize = 1;
   c.stream = reinterpret_cast<cudaStream_t>(stream);
   return c;
 }
@@ -938,6 +944,7 @@ int hvit_plan_launch_count(const hvit_plan* plan, int enhance) {
   if (enhance) {
     for (const StepMeta& m : plan->pre_meta) n += m.launches;
     for (const StepMeta& m : plan->post_meta) n += m.launches;
+    n -= 1;  // the stand-alone resize kernel is fused into the iSTFT frame kernel
   }
   return n;
 }
@@ -1061,6 +1068,8 @@ int hvit_stft(const float* wave, int B, int n, int normalize, void* max_val, voi
   int r = require_sm100();
   if (r) return r;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  r = ensure_fft_tables(s);
+  if (r) return r;
   r = launch_peak(wave, B, n, reinterpret_cast<float*>(max_val), normalize, s);
   if (r) return r;
   return launch_stft(wave, B, n, 1 + n / 128, reinterpret_cast<const float*>(max_val), reinterpret_cast<float2*>(spec),
@@ -1072,8 +1081,10 @@ int hvit_istft(const float* mag_norm, const void* spec, const void* mag_max, con
   int r = require_sm100();
   if (r) return r;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  r = launch_istft_frames(mag_norm, reinterpret_cast<const float2*>(spec), reinterpret_cast<const unsigned*>(mag_max),
-                          frames, B, 1 + n / 128, st);
+  r = ensure_fft_tables(st);
+  if (r) return r;
+  r = launch_istft_frames(const_cast<float*>(mag_norm), nullptr, 0, 0, reinterpret_cast<const float2*>(spec),
+                          reinterpret_cast<const unsigned*>(mag_max), frames, B, 1 + n / 128, st);
   if (r) return r;
   return launch_istft_ola(frames, reinterpret_cast<const float*>(max_val), wave_out, B, n, 1 + n / 128, st);
 }

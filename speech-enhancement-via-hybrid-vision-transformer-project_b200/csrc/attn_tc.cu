@@ -25,6 +25,12 @@ constexpr int OFF_BAR = 7 * TILE_BYTES;
 constexpr int AT_SMEM = OFF_BAR + 256;
 constexpr int TMEM_COLS = 256;             // S: cols [0,128), O_blk: cols [128,192)
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, bf16* __restrict__ out, int N, int D, float scale_log2,
                int f16) {
@@ -129,38 +135,48 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, bf16* __restrict__ 
       const int nvalid = min(128, N - j * 128);
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      float mx = m_run;
+      // Instruction diet (ncu: this kernel is issue-bound): the row maximum is taken on the raw scores (one FMNMX
+      // per element, scaled once), exp2 is a bare MUFU.EX2 fed by one FFMA, and key masking only exists in the code
+      // path of a partial last block.
+      const bool full = nvalid == 128;
+      float mraw = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t r[32];
         tmem_ld32(tmem_s + lane_addr + c * 32, r);
-        tmem_ld_wait();
+        tmem_ld_wait(r);
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(r[i]) * scale_log2);
+          for (int i = 0; i < 32; ++i) mraw = fmaxf(mraw, __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < nvalid) mraw = fmaxf(mraw, __uint_as_float(r[i]));
+        }
       }
-      const float alpha = exp2f(m_run - mx);
+      const float mx = fmaxf(m_run, mraw * scale_log2);
+      const float alpha = ex2_approx(m_run - mx);
       float rowsum = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t r[32];
         tmem_ld32(tmem_s + lane_addr + c * 32, r);
-        tmem_ld_wait();
-        float pv[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e = exp2f(__uint_as_float(r[i]) * scale_log2 - mx);
-          pv[i] = (c * 32 + i < nvalid) ? e : 0.f;
-          rowsum += pv[i];
-        }
+        tmem_ld_wait(r);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
+          float pv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            pv[i] = ex2_approx(fmaf(__uint_as_float(r[q * 8 + i]), scale_log2, -mx));
+            if (!full && c * 32 + q * 8 + i >= nvalid) pv[i] = 0.f;
+          }
+          rowsum += ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7]));
           const int cidx = c * 4 + q;  // 16-byte chunk index along the 128 keys
           uint4 pk;
-          pk.x = pack_16x2(pv[q * 8 + 0], pv[q * 8 + 1], f16);
-          pk.y = pack_16x2(pv[q * 8 + 2], pv[q * 8 + 3], f16);
-          pk.z = pack_16x2(pv[q * 8 + 4], pv[q * 8 + 5], f16);
-          pk.w = pack_16x2(pv[q * 8 + 6], pv[q * 8 + 7], f16);
+          pk.x = pack_16x2(pv[0], pv[1], f16);
+          pk.y = pack_16x2(pv[2], pv[3], f16);
+          pk.z = pack_16x2(pv[4], pv[5], f16);
+          pk.w = pack_16x2(pv[6], pv[7], f16);
           *reinterpret_cast<uint4*>(p_row + (cidx >> 3) * TILE_BYTES + (((cidx & 7) ^ sw) << 4)) = pk;
         }
       }
@@ -176,9 +192,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, bf16* __restrict__ 
       for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
         tmem_ld32(tmem_o + lane_addr + c * 32, r);
-        tmem_ld_wait();
+        tmem_ld_wait(r);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * alpha + __uint_as_float(r[i]);
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha, __uint_as_float(r[i]));
       }
     }
     if (q0 + row < N) {

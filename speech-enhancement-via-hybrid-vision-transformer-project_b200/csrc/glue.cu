@@ -11,8 +11,10 @@ namespace {
 constexpr int NFFT = 512;
 constexpr int HOP = 128;
 constexpr int NBIN = NFFT / 2 + 1;  // 257
-constexpr int FR = 16;              // frames per block (one warp each)
-constexpr int XS = NFFT + 1;        // padded frame stride in float2 (bank-conflict-free transposes)
+constexpr int FR = 8;               // frames per block (one warp each)
+constexpr int XS = 545;             // frame stride in float2: 512 + 32 in-frame padding + 1 (odd mod 16 -> the
+                                    // 16-frame transposes are bank-conflict free)
+__device__ __forceinline__ int fpad(int i) { return i + (i >> 4); }  // in-frame padding against Stockham store conflicts
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
@@ -28,36 +30,90 @@ __device__ __forceinline__ float guard_scalar(unsigned bits) {  // "if > 1e-8 us
   const float v = __uint_as_float(bits);
   return v > 1e-8f ? v : 1.0f;
 }
-__device__ __forceinline__ float hann512(int i) { return 0.5f - 0.5f * cospif(static_cast<float>(i) * (1.0f / 256.0f)); }
-__device__ __forceinline__ int brev9(int i) { return static_cast<int>(__brev(static_cast<unsigned>(i)) >> 23); }
-
-// In-place radix-2 DIT FFT of one 512-point frame held (bit-reversed) in shared memory, executed by one warp.
-// tw[k] = exp(-2*pi*i*k/512), k < 256.
-__device__ __forceinline__ void fft512_warp(float2* x, const float2* tw, int lane, bool inverse) {
-#pragma unroll 1
-  for (int s = 1; s <= 9; ++s) {
-    const int half = 1 << (s - 1);
-    const int tstep = NFFT >> s;
-#pragma unroll
-    for (int j = lane; j < NFFT / 2; j += 32) {
-      const int grp = j >> (s - 1), pos = j & (half - 1);
-      const int i0 = (grp << s) + pos, i1 = i0 + half;
-      float2 w = tw[pos * tstep];
-      if (inverse) w.y = -w.y;
-      const float2 a = x[i0], b = x[i1];
-      const float2 t = make_float2(b.x * w.x - b.y * w.y, b.x * w.y + b.y * w.x);
-      x[i0] = make_float2(a.x + t.x, a.y + t.y);
-      x[i1] = make_float2(a.x - t.x, a.y - t.y);
-    }
-    __syncwarp();
+// Tables shared by the STFT / iSTFT kernels, filled once per process by fft_tables_kernel (read through L1):
+//   g_tw512[n] = exp(-2*pi*i*n/512), g_hann512[n] = periodic Hann window (scipy.signal.get_window('hann', 512)).
+__device__ float2 g_tw512[NFFT];
+__device__ float g_hann512[NFFT];
+__global__ void fft_tables_kernel() {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < NFFT) {
+    float sn, cs;
+    sincospif(-static_cast<float>(k) * (1.0f / 256.0f), &sn, &cs);
+    g_tw512[k] = make_float2(cs, sn);
+    g_hann512[k] = 0.5f - 0.5f * cospif(static_cast<float>(k) * (1.0f / 256.0f));
   }
 }
+__device__ __forceinline__ float hann512(int i) { return __ldg(&g_hann512[i]); }
+__device__ __forceinline__ int brev9(int i) { return static_cast<int>(__brev(static_cast<unsigned>(i)) >> 23); }
 
-__device__ __forceinline__ void fill_twiddles(float2* tw) {
-  for (int k = threadIdx.x; k < NFFT / 2; k += blockDim.x) {
-    float s, c;
-    sincospif(-static_cast<float>(k) * (1.0f / 256.0f), &s, &c);
-    tw[k] = make_float2(c, s);
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// 8-point DFT in registers (three radix-2 levels).  INV selects the conjugate twiddles.
+template <bool INV>
+__device__ __forceinline__ void dft8(float2 (&v)[8]) {
+  constexpr float S = INV ? 1.0f : -1.0f;   // exp(S * i * theta)
+  constexpr float H = 0.70710678118654752440f;
+  float2 a[8];
+  a[0] = make_float2(v[0].x + v[4].x, v[0].y + v[4].y); a[1] = make_float2(v[0].x - v[4].x, v[0].y - v[4].y);
+  a[2] = make_float2(v[2].x + v[6].x, v[2].y + v[6].y); a[3] = make_float2(v[2].x - v[6].x, v[2].y - v[6].y);
+  a[4] = make_float2(v[1].x + v[5].x, v[1].y + v[5].y); a[5] = make_float2(v[1].x - v[5].x, v[1].y - v[5].y);
+  a[6] = make_float2(v[3].x + v[7].x, v[3].y + v[7].y); a[7] = make_float2(v[3].x - v[7].x, v[3].y - v[7].y);
+  // (S*i) * z = (-S*z.y, S*z.x)
+  const float2 ja3 = make_float2(-S * a[3].y, S * a[3].x), ja7 = make_float2(-S * a[7].y, S * a[7].x);
+  const float2 b0 = make_float2(a[0].x + a[2].x, a[0].y + a[2].y), b2 = make_float2(a[0].x - a[2].x, a[0].y - a[2].y);
+  const float2 b1 = make_float2(a[1].x + ja3.x, a[1].y + ja3.y), b3 = make_float2(a[1].x - ja3.x, a[1].y - ja3.y);
+  const float2 c0 = make_float2(a[4].x + a[6].x, a[4].y + a[6].y);
+  float2 c2 = make_float2(a[4].x - a[6].x, a[4].y - a[6].y);
+  float2 c1 = make_float2(a[5].x + ja7.x, a[5].y + ja7.y), c3 = make_float2(a[5].x - ja7.x, a[5].y - ja7.y);
+  c1 = make_float2(H * (c1.x - S * c1.y), H * (S * c1.x + c1.y));     // * exp(S*i*pi/4)
+  c2 = make_float2(-S * c2.y, S * c2.x);                                // * exp(S*i*pi/2)
+  c3 = make_float2(H * (-c3.x - S * c3.y), H * (S * c3.x - c3.y));    // * exp(S*i*3pi/4)
+  v[0] = make_float2(b0.x + c0.x, b0.y + c0.y); v[4] = make_float2(b0.x - c0.x, b0.y - c0.y);
+  v[1] = make_float2(b1.x + c1.x, b1.y + c1.y); v[5] = make_float2(b1.x - c1.x, b1.y - c1.y);
+  v[2] = make_float2(b2.x + c2.x, b2.y + c2.y); v[6] = make_float2(b2.x - c2.x, b2.y - c2.y);
+  v[3] = make_float2(b3.x + c3.x, b3.y + c3.y); v[7] = make_float2(b3.x - c3.x, b3.y - c3.y);
+}
+
+// 512-point complex FFT of one frame in shared memory by ONE warp: radix-8 Stockham, 3 passes, natural order in and
+// out (indices through fpad()).  Each lane does two 8-point butterflies per pass (64 per pass); all 16 inputs are
+// read into registers before any output is written, so the transform is in place with only __syncwarp().
+// tw[n] = exp(-2*pi*i*n/512), n < 512.  (Indexing verified against numpy.fft in a host prototype, DESIGN.md.)
+template <bool INV>
+__device__ __forceinline__ void fft512_warp(float2* x, int lane) {
+  const float2* tw = g_tw512;
+#pragma unroll
+  for (int stage = 0; stage < 3; ++stage) {
+    const int Ns = stage == 0 ? 1 : (stage == 1 ? 8 : 64);
+    const int tmul = 64 / Ns;  // 512 / (Ns * 8)
+    float2 v[2][8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = lane + 32 * h;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v[h][r] = x[fpad(j + r * 64)];
+      if (stage > 0) {
+        const int k = j & (Ns - 1);
+#pragma unroll
+        for (int r = 1; r < 8; ++r) {
+          float2 w = __ldg(&tw[r * k * tmul]);
+          if (INV) w.y = -w.y;
+          v[h][r] = cmul(v[h][r], w);
+        }
+      }
+      dft8<INV>(v[h]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = lane + 32 * h;
+      const int k = j & (Ns - 1);
+      const int base = (j - k) * 8 + k;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) x[fpad(base + r * Ns)] = v[h][r];
+    }
+    __syncwarp();
   }
 }
 
@@ -76,17 +132,15 @@ __global__ void fill_u32_kernel(unsigned* p, int n, unsigned v) {
 }
 
 // ------------------------------------------------------------------ STFT + |.| + per-clip max (enhancer.py:82-101)
-__global__ void __launch_bounds__(FR * 32) stft_kernel(const float* __restrict__ wave, int n, int T,
+__global__ void __launch_bounds__(FR * 32, 5) stft_kernel(const float* __restrict__ wave, int n, int T,
                                                        const unsigned* __restrict__ max_bits,
                                                        float2* __restrict__ spec, float* __restrict__ mag,
                                                        unsigned* __restrict__ mag_max_bits) {
   extern __shared__ float2 sm[];
   float2* xs = sm;                // [FR][XS]
-  float2* tw = sm + FR * XS;      // [256]
   const int b = blockIdx.y, t0 = blockIdx.x * FR;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  fill_twiddles(tw);
-  const float mv = guard_scalar(max_bits[b]);
+  const float inv_mv = 1.0f / guard_scalar(max_bits[b]);
   const int t = t0 + warp;
   float2* x = xs + warp * XS;
   if (t < T) {
@@ -94,21 +148,21 @@ __global__ void __launch_bounds__(FR * 32) stft_kernel(const float* __restrict__
     for (int i = lane; i < NFFT; i += 32) {
       const int src = t * HOP - NFFT / 2 + i;  // centred frame, zero padding
       float v = 0.f;
-      if (src >= 0 && src < n) v = (w[src] / mv) * hann512(i);
-      x[brev9(i)] = make_float2(v, 0.f);
+      if (src >= 0 && src < n) v = (w[src] * inv_mv) * hann512(i);
+      x[fpad(i)] = make_float2(v, 0.f);
     }
   }
-  __syncthreads();  // twiddles + frames visible
-  if (t < T) fft512_warp(x, tw, lane, false);
+  __syncwarp();
+  if (t < T) fft512_warp<false>(x, lane);
   __syncthreads();
   float lmax = 0.f;
   for (int idx = threadIdx.x; idx < NBIN * FR; idx += blockDim.x) {
     const int tl = idx & (FR - 1), f = idx / FR;
     if (t0 + tl < T) {
-      const float2 z = xs[tl * XS + f];
+      const float2 z = xs[tl * XS + fpad(f)];
       const long long o = (static_cast<long long>(b) * NBIN + f) * T + t0 + tl;
       spec[o] = z;
-      const float m = hypotf(z.x, z.y);
+      const float m = sqrtf(z.x * z.x + z.y * z.y);
       mag[o] = m;
       lmax = fmaxf(lmax, m);
     }
@@ -117,40 +171,71 @@ __global__ void __launch_bounds__(FR * 32) stft_kernel(const float* __restrict__
   if (lane == 0) atomicMax(mag_max_bits + b, __float_as_uint(lmax));
 }
 
+// ------------------------------------------------------------------ bilinear helpers (torch align_corners=False)
+struct Lerp {
+  int i0, i1;
+  float l0, l1;
+};
+__device__ __forceinline__ Lerp make_lerp(int dst, int in_size, int out_size) {
+  const float scale = static_cast<float>(in_size) / static_cast<float>(out_size);
+  float src = scale * (static_cast<float>(dst) + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  Lerp r;
+  r.i0 = static_cast<int>(src);
+  if (r.i0 > in_size - 1) r.i0 = in_size - 1;
+  r.i1 = r.i0 + (r.i0 < in_size - 1 ? 1 : 0);
+  r.l1 = src - static_cast<float>(r.i0);
+  r.l0 = 1.0f - r.l1;
+  return r;
+}
+
 // ------------------------------------------------------------------ iSTFT part 1: spectrum -> windowed frames
 // E = (model_out * mag_max) * S/|S|  (== mag * exp(1j*angle(S)), enhancer.py:115-119), irfft-512, * Hann.
-__global__ void __launch_bounds__(FR * 32) istft_frames_kernel(const float* __restrict__ model_out,
+// When `lowres` is given the model output is bilinearly sampled from the decoder's [B,Hs,Ws] tanh map on the fly
+// (HybridViT's final F.interpolate, hybrid_vit.py:458-465, fused here) and also written to model_out.
+__global__ void __launch_bounds__(FR * 32, 5) istft_frames_kernel(float* __restrict__ model_out,
+                                                               const float* __restrict__ lowres, int Hs, int Ws,
                                                                const float2* __restrict__ spec,
                                                                const unsigned* __restrict__ mag_max_bits, int T,
                                                                float* __restrict__ frames) {
   extern __shared__ float2 sm[];
   float2* xs = sm;
-  float2* tw = sm + FR * XS;
   const int b = blockIdx.y, t0 = blockIdx.x * FR;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  fill_twiddles(tw);
   const float mm = guard_scalar(mag_max_bits[b]);
   for (int idx = threadIdx.x; idx < NBIN * FR; idx += blockDim.x) {
     const int tl = idx & (FR - 1), f = idx / FR;
     if (t0 + tl < T) {
       const long long o = (static_cast<long long>(b) * NBIN + f) * T + t0 + tl;
       const float2 z = spec[o];
-      const float a = hypotf(z.x, z.y);
-      const float e = model_out[o] * mm;
-      float2 E = a > 0.f ? make_float2(e * (z.x / a), e * (z.y / a)) : make_float2(e, 0.f);
+      const float a = sqrtf(z.x * z.x + z.y * z.y);
+      float mo;
+      if (lowres != nullptr) {
+        const Lerp ly = make_lerp(f, Hs, NBIN), lx = make_lerp(t0 + tl, Ws, T);
+        const float* src = lowres + static_cast<long long>(b) * Hs * Ws;
+        const float v00 = src[ly.i0 * Ws + lx.i0], v01 = src[ly.i0 * Ws + lx.i1];
+        const float v10 = src[ly.i1 * Ws + lx.i0], v11 = src[ly.i1 * Ws + lx.i1];
+        mo = ly.l0 * (lx.l0 * v00 + lx.l1 * v01) + ly.l1 * (lx.l0 * v10 + lx.l1 * v11);
+        model_out[o] = mo;
+      } else {
+        mo = model_out[o];
+      }
+      const float e = mo * mm;
+      const float ea = a > 0.f ? e / a : 0.f;
+      float2 E = a > 0.f ? make_float2(ea * z.x, ea * z.y) : make_float2(e, 0.f);
       if (f == 0 || f == NFFT / 2) E.y = 0.f;  // c2r transforms ignore the imaginary part of DC / Nyquist
       float2* x = xs + tl * XS;
-      x[brev9(f)] = E;
-      if (f > 0 && f < NFFT / 2) x[brev9(NFFT - f)] = make_float2(E.x, -E.y);
+      x[fpad(f)] = E;
+      if (f > 0 && f < NFFT / 2) x[fpad(NFFT - f)] = make_float2(E.x, -E.y);
     }
   }
   __syncthreads();
   const int t = t0 + warp;
   if (t < T) {
     float2* x = xs + warp * XS;
-    fft512_warp(x, tw, lane, true);
+    fft512_warp<true>(x, lane);
     float* fr = frames + (static_cast<long long>(b) * T + t) * NFFT;
-    for (int i = lane; i < NFFT; i += 32) fr[i] = x[i].x * (1.0f / NFFT) * hann512(i);
+    for (int i = lane; i < NFFT; i += 32) fr[i] = x[fpad(i)].x * (1.0f / NFFT) * hann512(i);
   }
 }
 
@@ -322,13 +407,43 @@ __device__ __forceinline__ void st4<__half>(__half* p, const float* v) {
 }
 
 // ------------------------------------------------------------------ LayerNorm (warp per row)
-template <typename T>
+// V float4 per lane (D = 128 * V): the row is read once into registers; mean / centred variance in fp32 via warp
+// shuffles (same two-pass arithmetic as torch), gamma/beta through the read-only path.  V == 0: generic D.
+template <typename T, int V>
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ bb,
                                  T* __restrict__ out, int rows, int D, float eps) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float* xr = x + static_cast<long long>(row) * D;
+  T* orow = out + static_cast<long long>(row) * D;
+  if (V > 0) {
+    float4 v[V > 0 ? V : 1];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      v[k] = *reinterpret_cast<const float4*>(xr + k * 128 + lane * 4);
+      s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+    const float mean = warp_sum(s) / D;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      v[k].x -= mean; v[k].y -= mean; v[k].z -= mean; v[k].w -= mean;
+      q += (v[k].x * v[k].x + v[k].y * v[k].y) + (v[k].z * v[k].z + v[k].w * v[k].w);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / D + eps);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const int i = k * 128 + lane * 4;
+      const float4 gg = __ldg(reinterpret_cast<const float4*>(g + i));
+      const float4 be = __ldg(reinterpret_cast<const float4*>(bb + i));
+      const float yv[4] = {fmaf(v[k].x * rstd, gg.x, be.x), fmaf(v[k].y * rstd, gg.y, be.y),
+                           fmaf(v[k].z * rstd, gg.z, be.z), fmaf(v[k].w * rstd, gg.w, be.w)};
+      st4<T>(orow + i, yv);
+    }
+    return;
+  }
   float s = 0.f;
   for (int i = lane * 4; i < D; i += 128) {
     const float4 v = *reinterpret_cast<const float4*>(xr + i);
@@ -342,34 +457,14 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
     q += (a * a + b * b) + (c * c + d * d);
   }
   const float rstd = rsqrtf(warp_sum(q) / D + eps);
-  T* orow = out + static_cast<long long>(row) * D;
   for (int i = lane * 4; i < D; i += 128) {
     const float4 v = *reinterpret_cast<const float4*>(xr + i);
     const float4 gg = __ldg(reinterpret_cast<const float4*>(g + i));
     const float4 be = __ldg(reinterpret_cast<const float4*>(bb + i));
-    const float y0 = (v.x - mean) * rstd * gg.x + be.x, y1 = (v.y - mean) * rstd * gg.y + be.y;
-    const float y2 = (v.z - mean) * rstd * gg.z + be.z, y3 = (v.w - mean) * rstd * gg.w + be.w;
-    const float yv[4] = {y0, y1, y2, y3};
+    const float yv[4] = {(v.x - mean) * rstd * gg.x + be.x, (v.y - mean) * rstd * gg.y + be.y,
+                         (v.z - mean) * rstd * gg.z + be.z, (v.w - mean) * rstd * gg.w + be.w};
     st4<T>(orow + i, yv);
   }
-}
-
-// ------------------------------------------------------------------ bilinear helpers (torch align_corners=False)
-struct Lerp {
-  int i0, i1;
-  float l0, l1;
-};
-__device__ __forceinline__ Lerp make_lerp(int dst, int in_size, int out_size) {
-  const float scale = static_cast<float>(in_size) / static_cast<float>(out_size);
-  float src = scale * (static_cast<float>(dst) + 0.5f) - 0.5f;
-  if (src < 0.f) src = 0.f;
-  Lerp r;
-  r.i0 = static_cast<int>(src);
-  if (r.i0 > in_size - 1) r.i0 = in_size - 1;
-  r.i1 = r.i0 + (r.i0 < in_size - 1 ? 1 : 0);
-  r.l1 = src - static_cast<float>(r.i0);
-  r.l0 = 1.0f - r.l1;
-  return r;
 }
 
 // skip feature [B, Hs(pitch), Ws, C] -> bilinear sample at decoder resolution [B*Hd*Wd, C]
@@ -400,37 +495,74 @@ __global__ void skip_sample_kernel(const T* __restrict__ src, int Hs, int HsPitc
 }
 
 // ------------------------------------------------------------------ head: Conv3x3(C->1, no bias) + tanh, fp32 accumulate
+// One thread per output pixel, 32x8 pixel tiles per block (neighbouring threads re-read the same input pixels
+// through L1), 16-byte loads, weights broadcast from shared memory.
 template <typename T>
-__global__ void head_kernel(const T* __restrict__ x, const float* __restrict__ w9c, int B, int H, int W, int C,
-                            float* __restrict__ logits, float* __restrict__ out_tanh) {
-  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long pix = gid >> 3;
-  const int sub = static_cast<int>(gid & 7);
+__device__ __forceinline__ void ld8(const T* p, float* v);
+template <>
+__device__ __forceinline__ void ld8<float>(const float* p, float* v) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void ld8<bf16>(const bf16* p, float* v) {
+  const uint4 a = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+template <>
+__device__ __forceinline__ void ld8<__half>(const __half* p, float* v) {
+  const uint4 a = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+
+// 8 lanes per output pixel, each lane owns 8 channels (one 16-byte load per tap): a warp instruction reads 4 whole
+// 128-byte pixel vectors (4 L1 wavefronts instead of 32 with a pixel-per-lane mapping - ncu showed that version
+// L1-bound at 84 %).  The lane's 72 weights live in registers; the partial sums meet with three shuffles.
+template <typename T>
+__global__ void __launch_bounds__(256) head_kernel(const T* __restrict__ x, const float* __restrict__ w9c, int B, int H,
+                                                   int W, int C, float* __restrict__ logits,
+                                                   float* __restrict__ out_tanh) {
+  const int lane8 = threadIdx.x & 7;
   const long long npix = static_cast<long long>(B) * H * W;
-  const bool live = pix < npix;
-  float acc = 0.f;
-  if (live) {
+  const long long stride = static_cast<long long>(gridDim.x) * 32;  // pixels per grid sweep (32 per block)
+  for (long long pix0 = static_cast<long long>(blockIdx.x) * 32 + (threadIdx.x >> 3); pix0 - (threadIdx.x >> 3) < npix;
+       pix0 += stride) {
+    const bool live = pix0 < npix;
+    const long long pix = live ? pix0 : 0;
     const int w = static_cast<int>(pix % W);
     const int h = static_cast<int>((pix / W) % H);
     const int b = static_cast<int>(pix / (static_cast<long long>(W) * H));
-    for (int tap = 0; tap < 9; ++tap) {
-      const int iy = h + tap / 3 - 1, ix = w + tap % 3 - 1;
-      if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-      const T* px = x + ((static_cast<long long>(b) * H + iy) * W + ix) * C;
-      for (int c = sub * 4; c < C; c += 32) {
-        float v[4];
-        ld4<T>(px + c, v);
-        const float4 wv = __ldg(reinterpret_cast<const float4*>(w9c + tap * C + c));
-        acc = fmaf(v[0], wv.x, acc); acc = fmaf(v[1], wv.y, acc); acc = fmaf(v[2], wv.z, acc); acc = fmaf(v[3], wv.w, acc);
+    float acc = 0.f;
+    for (int c = lane8 * 8; c < C; c += 64) {  // 64 channels per pass of the 8 lanes
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int iy = h + tap / 3 - 1, ix = w + tap % 3 - 1;
+        if (!live || iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+        float v[8];
+        ld8<T>(x + ((static_cast<long long>(b) * H + iy) * W + ix) * C + c, v);
+        const float4 wa = __ldg(reinterpret_cast<const float4*>(w9c + tap * C + c));
+        const float4 wb = __ldg(reinterpret_cast<const float4*>(w9c + tap * C + c + 4));
+        acc = fmaf(v[0], wa.x, acc); acc = fmaf(v[1], wa.y, acc); acc = fmaf(v[2], wa.z, acc); acc = fmaf(v[3], wa.w, acc);
+        acc = fmaf(v[4], wb.x, acc); acc = fmaf(v[5], wb.y, acc); acc = fmaf(v[6], wb.z, acc); acc = fmaf(v[7], wb.w, acc);
       }
     }
-  }
-  acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
-  acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
-  acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 4);
-  if (live && sub == 0) {
-    if (logits != nullptr) logits[pix] = acc;
-    out_tanh[pix] = tanhf(acc);
+    acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
+    acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
+    acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 4);
+    if (live && lane8 == 0) {
+      if (logits != nullptr) logits[pix] = acc;
+      out_tanh[pix] = tanhf(acc);
+    }
   }
 }
 
@@ -473,7 +605,7 @@ __global__ void maxpool2_kernel(const float* __restrict__ src, float* __restrict
   *reinterpret_cast<float4*>(dst + ((b * Ho + oh) * Wo + ow) * C + c) = o;
 }
 
-constexpr int FFT_SMEM = (FR * XS + NFFT / 2) * sizeof(float2);
+constexpr int FFT_SMEM = FR * XS * sizeof(float2);
 
 }  // namespace
 
@@ -492,14 +624,21 @@ int launch_peak(const float* wave, int B, int n, float* max_val, int normalize, 
   return check_launch("peak");
 }
 
+// one-time table fill; called from plan creation / the stand-alone entry points (never inside a graph capture)
+int ensure_fft_tables(cudaStream_t s) {
+  static bool done = false;
+  if (!done) {
+    fft_tables_kernel<<<2, 256, 0, s>>>();
+    const int r = check_launch("fft_tables");
+    if (r) return r;
+    if (cudaStreamSynchronize(s) != cudaSuccess) return check_launch("fft_tables(sync)");
+    done = true;
+  }
+  return 0;
+}
+
 int launch_stft(const float* wave, int B, int n, int T, const float* max_val, float2* spec, float* mag,
                 unsigned* mag_max_bits, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FFT_SMEM);
-    cudaFuncSetAttribute(istft_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FFT_SMEM);
-    configured = true;
-  }
   fill_u32_kernel<<<(B + 255) / 256, 256, 0, s>>>(mag_max_bits, B, 0u);
   dim3 grid((T + FR - 1) / FR, B);
   stft_kernel<<<grid, FR * 32, FFT_SMEM, s>>>(wave, n, T, reinterpret_cast<const unsigned*>(max_val), spec, mag,
@@ -507,20 +646,13 @@ int launch_stft(const float* wave, int B, int n, int T, const float* max_val, fl
   return check_launch("stft");
 }
 
-static void fft_smem_config() {
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FFT_SMEM);
-    cudaFuncSetAttribute(istft_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FFT_SMEM);
-    configured = true;
-  }
-}
+static void fft_smem_config() {}
 
-int launch_istft_frames(const float* model_out, const float2* spec, const unsigned* mag_max_bits, float* frames, int B,
-                        int T, cudaStream_t s) {
+int launch_istft_frames(float* model_out, const float* lowres, int Hs, int Ws, const float2* spec,
+                        const unsigned* mag_max_bits, float* frames, int B, int T, cudaStream_t s) {
   fft_smem_config();
   dim3 grid((T + FR - 1) / FR, B);
-  istft_frames_kernel<<<grid, FR * 32, FFT_SMEM, s>>>(model_out, spec, mag_max_bits, T, frames);
+  istft_frames_kernel<<<grid, FR * 32, FFT_SMEM, s>>>(model_out, lowres, Hs, Ws, spec, mag_max_bits, T, frames);
   return check_launch("istft_frames");
 }
 
@@ -556,19 +688,28 @@ int launch_stem(const float* x, const unsigned* mag_max_bits, const float* w, co
   return check_launch("stem");
 }
 
+template <typename T>
+static void ln_dispatch(const float* x, const float* g, const float* b, void* out, int rows, int D, float eps,
+                        cudaStream_t s) {
+  const int grid = (rows + 7) / 8;
+  T* o = reinterpret_cast<T*>(out);
+  if (D == 512) layernorm_kernel<T, 4><<<grid, 256, 0, s>>>(x, g, b, o, rows, D, eps);
+  else if (D == 768) layernorm_kernel<T, 6><<<grid, 256, 0, s>>>(x, g, b, o, rows, D, eps);
+  else if (D == 1024) layernorm_kernel<T, 8><<<grid, 256, 0, s>>>(x, g, b, o, rows, D, eps);
+  else if (D == 256) layernorm_kernel<T, 2><<<grid, 256, 0, s>>>(x, g, b, o, rows, D, eps);
+  else if (D == 128) layernorm_kernel<T, 1><<<grid, 256, 0, s>>>(x, g, b, o, rows, D, eps);
+  else layernorm_kernel<T, 0><<<grid, 256, 0, s>>>(x, g, b, o, rows, D, eps);
+}
+
 int launch_layernorm(const float* x, const float* g, const float* b, void* out, int dt, int rows, int D,
                      float eps, cudaStream_t s) {
   if (D % 4 != 0) {
     set_error("layernorm: D %% 4 != 0");
     return -1;
   }
-  const int grid = (rows + 7) / 8;
-  if (dt == DT_BF16)
-    layernorm_kernel<bf16><<<grid, 256, 0, s>>>(x, g, b, reinterpret_cast<bf16*>(out), rows, D, eps);
-  else if (dt == DT_F16)
-    layernorm_kernel<__half><<<grid, 256, 0, s>>>(x, g, b, reinterpret_cast<__half*>(out), rows, D, eps);
-  else
-    layernorm_kernel<float><<<grid, 256, 0, s>>>(x, g, b, reinterpret_cast<float*>(out), rows, D, eps);
+  if (dt == DT_BF16) ln_dispatch<bf16>(x, g, b, out, rows, D, eps, s);
+  else if (dt == DT_F16) ln_dispatch<__half>(x, g, b, out, rows, D, eps, s);
+  else ln_dispatch<float>(x, g, b, out, rows, D, eps, s);
   return check_launch("layernorm");
 }
 
@@ -590,12 +731,14 @@ int launch_skip_sample(const void* src, int dt, int B, int Hs, int HsPitch, int 
 
 int launch_head(const void* x, int dt, const float* w, int B, int H, int W, int C, float* logits,
                 float* out_tanh, cudaStream_t s) {
-  if (C % 4 != 0) {
-    set_error("head: C %% 4 != 0");
+  if (C % 8 != 0) {
+    set_error("head: C must be a multiple of 8");
     return -1;
   }
-  const long long threads = static_cast<long long>(B) * H * W * 8;
-  const unsigned grid = static_cast<unsigned>((threads + 255) / 256);
+  const long long npix = static_cast<long long>(B) * H * W;
+  long long blocks = (npix + 31) / 32;
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  const unsigned grid = static_cast<unsigned>(blocks);
   if (dt == DT_BF16)
     head_kernel<bf16><<<grid, 256, 0, s>>>(reinterpret_cast<const bf16*>(x), w, B, H, W, C, logits, out_tanh);
   else if (dt == DT_F16)

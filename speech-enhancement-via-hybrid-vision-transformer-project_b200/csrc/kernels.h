@@ -79,10 +79,13 @@ int launch_attn_probs_16(const void* qkv16, int f16, float* probs, int B, int N,
 // ---------------------------------------------------------------------------------------------
 // Bandwidth-bound glue kernels.  The activation type is selected by `dt` (DT_F32 / DT_BF16 / DT_F16).
 // ---------------------------------------------------------------------------------------------
+int ensure_fft_tables(cudaStream_t s);
 int launch_peak(const float* wave, int B, int n, float* max_val /*[B]*/, int normalize, cudaStream_t s);
 int launch_stft(const float* wave, int B, int n, int T, const float* max_val, float2* spec /*[B,257,T]*/,
                 float* mag /*[B,257,T]*/, unsigned* mag_max_bits /*[B]*/, cudaStream_t s);
-int launch_istft_frames(const float* model_out /*[B,257,T] in [-1,1]*/, const float2* spec,
+// model_out [B,257,T] is read when lowres == nullptr, otherwise it is WRITTEN with the bilinear resize of
+// lowres [B,Hs,Ws] (fused final interpolate of HybridViT.forward).
+int launch_istft_frames(float* model_out, const float* lowres, int Hs, int Ws, const float2* spec,
                         const unsigned* mag_max_bits, float* frames /*[B,T,512]*/, int B, int T, cudaStream_t s);
 int launch_istft_ola(const float* frames, const float* max_val, float* wave_out, int B, int n, int T, cudaStream_t s);
 int launch_stem(const float* x /*[B,H,W]*/, const unsigned* mag_max_bits /*nullable*/, const float* w /*[9][C]*/,
