@@ -51,7 +51,8 @@ struct Cfg2 {
   static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 7);
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
   static constexpr int STAGING_BYTES = 4 * STG_BUF_BYTES;    // [group][buffer]
-  static constexpr int CONST_BYTES = NUM_EPI_WARPS * 2048;   // per-warp scale/shift of its (<= 4) column blocks
+  static constexpr int CONST_N = BLOCK_N == 256 ? 4096 : 2048;  // scale[N] | shift[N] of the whole problem fit up to here
+  static constexpr int CONST_BYTES = 2 * CONST_N * 4;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + CONST_BYTES + 1024 + 512;
 };
 
@@ -79,7 +80,153 @@ __device__ __forceinline__ TileCoord decode_ctile(const IgemmParams& p, int ct, 
   return c;
 }
 
-template <int BLOCK_N>
+
+// Epilogue specialisations.  The hot combinations of the HybridViT plan are compiled without run-time branches in
+// the per-element code (so the 32 columns of a TMEM chunk are scheduled together); any other parameter combination
+// takes EPI_GENERIC.
+enum {
+  EPI_GENERIC = 0,   // everything decided at run time
+  EPI_LIN16 = 1,     // + shift,            16-bit out (qkv, to_feature_map, skip projections)
+  EPI_GELU16 = 2,    // + shift, erf-GELU,  16-bit out (fc1)
+  EPI_BN16 = 3,      // * scale + shift, max(., lo), 16-bit out (3x3 convs; lo = 0 for ReLU, -inf for none)
+  EPI_BNPOOL16 = 4,  // EPI_BN16 + fused 2x2 max-pool
+  EPI_F32 = 5        // + shift (+ fp32 residual), fp32 out (proj, fc2, patch embedding)
+};
+
+// GELU(v) = relu(v) - 0.5*|v|*erfc(|v|/sqrt2), erfc(u/sqrt2) = 2^q(u) with a weighted-minimax degree-5 q on [0, 6]
+// (max |GELU error| 6.9e-7 in fp32 evaluation, verified against scipy - DESIGN.md): 10 instructions per element.
+__device__ __forceinline__ float gelu_erfc5(float v) {
+  const float u = fminf(fabsf(v), 6.0f);
+  float q = -4.837184678763151e-4f;
+  q = fmaf(q, u, 7.163475267589092e-3f);
+  q = fmaf(q, u, -5.204327404499054e-2f);
+  q = fmaf(q, u, -4.5973172783851624e-1f);
+  q = fmaf(q, u, -1.150922417640686f);
+  q = fmaf(q, u, -1.5133146916923579e-5f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));
+  return fmaf(-0.5f * u, e, fmaxf(v, 0.0f));
+}
+
+__device__ __forceinline__ void tile_out_coords(const IgemmParams& p, const TileCoord& c, bool pool, int& o1, int& o2,
+                                                int& o3) {
+  if (p.mode == IG_PLAIN) {
+    o1 = c.m0; o2 = 0; o3 = 0;
+  } else if (pool) {
+    o1 = c.w0 >> 1; o2 = c.h0 >> 1; o3 = c.b;
+  } else {
+    o1 = c.w0; o2 = c.h0; o3 = c.b;
+  }
+}
+
+// 32 accumulator columns -> 64 bytes of this thread's 128-byte staging row (16-bit output).
+// sc / sh: shared-memory per-channel constants of these 32 columns; half: which 64-byte half of the row.
+template <int EPI, bool F16>
+__device__ __forceinline__ void emit16(const uint32_t (&cur)[32], const float* sc, const float* sh,
+                                       const IgemmParams& p, float relu_lo, uint8_t* row, int half, int sw,
+                                       bool writer) {
+  float v[32];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 b = *reinterpret_cast<const float4*>(sh + 4 * q);
+    if (EPI == EPI_LIN16 || EPI == EPI_GELU16) {
+      v[4 * q + 0] = __uint_as_float(cur[4 * q + 0]) + b.x;
+      v[4 * q + 1] = __uint_as_float(cur[4 * q + 1]) + b.y;
+      v[4 * q + 2] = __uint_as_float(cur[4 * q + 2]) + b.z;
+      v[4 * q + 3] = __uint_as_float(cur[4 * q + 3]) + b.w;
+    } else {
+      const float4 a = *reinterpret_cast<const float4*>(sc + 4 * q);
+      v[4 * q + 0] = fmaf(__uint_as_float(cur[4 * q + 0]), a.x, b.x);
+      v[4 * q + 1] = fmaf(__uint_as_float(cur[4 * q + 1]), a.y, b.y);
+      v[4 * q + 2] = fmaf(__uint_as_float(cur[4 * q + 2]), a.z, b.z);
+      v[4 * q + 3] = fmaf(__uint_as_float(cur[4 * q + 3]), a.w, b.w);
+    }
+  }
+  if (EPI == EPI_GELU16) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = gelu_erfc5(v[e]);
+  } else if (EPI == EPI_BN16 || EPI == EPI_BNPOOL16) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], relu_lo);
+  } else if (EPI == EPI_GENERIC) {
+    if (p.act == ACT_RELU) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.0f);
+    } else if (p.act == ACT_GELU) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] = gelu_erfc5(v[e]);
+    }
+  }
+  if (EPI == EPI_BNPOOL16 || (EPI == EPI_GENERIC && p.pool)) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      v[e] = fmaxf(v[e], __shfl_xor_sync(0xFFFFFFFFu, v[e], 1));
+      v[e] = fmaxf(v[e], __shfl_xor_sync(0xFFFFFFFFu, v[e], 16));
+    }
+  }
+  if (writer) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 pk;
+      if (F16) {
+        pk.x = pack_f16x2(v[8 * q + 0], v[8 * q + 1]); pk.y = pack_f16x2(v[8 * q + 2], v[8 * q + 3]);
+        pk.z = pack_f16x2(v[8 * q + 4], v[8 * q + 5]); pk.w = pack_f16x2(v[8 * q + 6], v[8 * q + 7]);
+      } else {
+        pk.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]); pk.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+        pk.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]); pk.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+      }
+      *reinterpret_cast<uint4*>(row + (((half * 4 + q) ^ sw) << 4)) = pk;
+    }
+  }
+}
+
+// 32 accumulator columns -> this thread's whole 128-byte staging row (fp32 output); the residual tile, when present,
+// has been TMA-loaded into the same (swizzled) staging row and is added in place.
+template <int EPI>
+__device__ __forceinline__ void emit32(const uint32_t (&cur)[32], const float* sc, const float* sh,
+                                       const IgemmParams& p, float relu_lo, uint8_t* row, int sw, bool has_res) {
+  float v[32];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 b = *reinterpret_cast<const float4*>(sh + 4 * q);
+    if (EPI == EPI_F32) {
+      v[4 * q + 0] = __uint_as_float(cur[4 * q + 0]) + b.x;
+      v[4 * q + 1] = __uint_as_float(cur[4 * q + 1]) + b.y;
+      v[4 * q + 2] = __uint_as_float(cur[4 * q + 2]) + b.z;
+      v[4 * q + 3] = __uint_as_float(cur[4 * q + 3]) + b.w;
+    } else {
+      const float4 a = *reinterpret_cast<const float4*>(sc + 4 * q);
+      v[4 * q + 0] = fmaf(__uint_as_float(cur[4 * q + 0]), a.x, b.x);
+      v[4 * q + 1] = fmaf(__uint_as_float(cur[4 * q + 1]), a.y, b.y);
+      v[4 * q + 2] = fmaf(__uint_as_float(cur[4 * q + 2]), a.z, b.z);
+      v[4 * q + 3] = fmaf(__uint_as_float(cur[4 * q + 3]), a.w, b.w);
+    }
+  }
+  if (EPI == EPI_GENERIC) {
+    if (p.act == ACT_RELU) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.0f);
+    } else if (p.act == ACT_GELU) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] = gelu_erfc5(v[e]);
+    }
+  }
+  if (has_res) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float4* d = reinterpret_cast<float4*>(row + ((q ^ sw) << 4));
+      const float4 r = *d;
+      *d = make_float4(v[4 * q + 0] + r.x, v[4 * q + 1] + r.y, v[4 * q + 2] + r.z, v[4 * q + 3] + r.w);
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      *reinterpret_cast<float4*>(row + ((q ^ sw) << 4)) =
+          make_float4(v[4 * q + 0], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+}
+
+template <int BLOCK_N, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, int num_ctiles, int n_tiles_n,
                  int pairs_per_group) {
@@ -135,12 +282,20 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      long long pw = 0;
+      const long long pt0 = clock64();
       for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
         const TileCoord c = decode_ctile(p, ct, n_tiles_n, BLOCK_N, pairs_per_group, rank);
         const int py = c.par >> 1, px = c.par & 1;
         const int b_row = c.n0 + c.par * p.N + rank * C::B_HALF_ROWS;
         for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (p.prof) {
+            const long long t = clock64();
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            pw += clock64() - t;
+          } else {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+          }
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
@@ -167,6 +322,10 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
           }
         }
       }
+      if (p.prof) {
+        p.prof[blockIdx.x * 16 + 0] = pw;
+        p.prof[blockIdx.x * 16 + 1] = clock64() - pt0;
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (one thread of the leader CTA)
@@ -176,12 +335,26 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      long long mw_e = 0, mw_f = 0;
+      const long long mt0 = clock64();
       for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        if (p.prof) {
+          const long long t = clock64();
+          mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+          mw_e += clock64() - t;
+        } else {
+          mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          if (p.prof) {
+            const long long t = clock64();
+            mbar_wait(&full_bar[stage], phase);
+            mw_f += clock64() - t;
+          } else {
+            mbar_wait(&full_bar[stage], phase);
+          }
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_STAGE_BYTES;
@@ -203,6 +376,11 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
           acc_phase ^= 1;
         }
       }
+      if (p.prof) {
+        p.prof[blockIdx.x * 16 + 2] = mw_e;
+        p.prof[blockIdx.x * 16 + 3] = mw_f;
+        p.prof[blockIdx.x * 16 + 4] = clock64() - mt0;
+      }
     }
   } else {
     // ------------------------------------------------------------ epilogue: TMEM -> regs -> smem -> TMA store
@@ -211,105 +389,80 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
     const int grp = ew >> 2;             // column-block parity owned by this warp's group
     const int m = sub * 32 + lane;       // accumulator row == TMEM lane
     const bool issuer = (ew & 3) == 0 && lane == 0;
-    const int wcols = p.out_f32 ? 32 : 64;          // columns per 128-byte block
+    constexpr bool kF32 = EPI == EPI_F32;
+    const bool out_f32 = EPI == EPI_GENERIC ? p.out_f32 != 0 : kF32;
+    const bool pool = EPI == EPI_GENERIC ? p.pool != 0 : EPI == EPI_BNPOOL16;
+    const int wcols = out_f32 ? 32 : 64;            // columns per 128-byte block
     const int nblk = BLOCK_N / wcols;
     const int J = (nblk - grp + 1) / 2;             // blocks of this group per tile
-    float* cst = reinterpret_cast<float*>(consts + ew * 2048);  // [J][scale 64 | shift 64]
     uint8_t* stg0 = staging + grp * 2 * STG_BUF_BYTES;
-    const bool has_res = p.residual != nullptr;
+    // In-place residual (x += f(x), the transformer's proj / fc2): nothing is loaded - the block is added into
+    // global memory by a TMA reduce-add.  Otherwise the fp32 residual tile is TMA-loaded into the staging buffer.
+    const bool red_add = (EPI == EPI_GENERIC || kF32) && p.residual != nullptr && p.res_inplace != 0;
+    const bool has_res = (EPI == EPI_GENERIC || kF32) && p.residual != nullptr && !red_add;
     // staging row of this thread (pooled convolutions only keep the pooled pixels)
-    const bool writer = p.pool ? ((lane & 17) == 0) : true;
-    const int srow = p.pool ? (sub * 8 + ((lane & 15) >> 1)) : m;
+    const bool writer = pool ? ((lane & 17) == 0) : true;
+    const int srow = pool ? (sub * 8 + ((lane & 15) >> 1)) : m;
     const int sw = srow & 7;
+    const float relu_lo = p.act == ACT_RELU ? 0.0f : -INFINITY;
+
+    // Per-channel constants of the whole problem -> shared memory once per CTA: cscale[n] | cshift[n], n < N.
+    // (N <= C::CONST_N; larger N reloads the tile's BLOCK_N constants per tile.)
+    float* cscale = reinterpret_cast<float*>(consts);
+    float* cshift = cscale + C::CONST_N;
+    const bool preload = p.N <= C::CONST_N;
+    if (preload) {
+      for (int e = ew * 32 + lane; e < p.N; e += NUM_EPI_WARPS * 32) {
+        cscale[e] = p.scale != nullptr ? __ldg(p.scale + e) : 1.0f;
+        cshift[e] = p.shift != nullptr ? __ldg(p.shift + e) : 0.0f;
+      }
+      named_bar_sync(3, NUM_EPI_WARPS * 32);
+    }
+
     uint32_t it = 0;  // running column-block counter of this group: buffer = it & 1, residual phase = (it >> 1) & 1
     int acc = 0;
     uint32_t acc_phase = 0;
+    long long ew_full = 0, e_cst = 0, e_blk = 0, e_tiles = 0;
+    const long long et0 = clock64();
     for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
+      const long long tA = clock64();
       const TileCoord c = decode_ctile(p, ct, n_tiles_n, BLOCK_N, pairs_per_group, rank);
       // output coordinates of the tile origin (dims 1..3 of the 4-D output map; dim 0 is the channel)
       int o1, o2, o3;
-      if (p.mode == IG_PLAIN) {
-        o1 = c.m0; o2 = 0; o3 = 0;
-      } else if (p.pool) {
-        o1 = c.w0 >> 1; o2 = c.h0 >> 1; o3 = c.b;
-      } else {
-        o1 = c.w0; o2 = c.h0; o3 = c.b;
-      }
+      tile_out_coords(p, c, pool, o1, o2, o3);
       const CUtensorMap* omap = &maps.out[c.par];
       const int r3 = p.res_mod > 0 ? 0 : o3;  // positional table: same rows for every clip
-      // per-channel constants of this warp's blocks -> smem (latency hidden behind this tile's main loop)
-      for (int j = 0; j < J; ++j) {
-        const int col = c.n0 + (2 * j + grp) * wcols;
-        for (int e = lane; e < wcols; e += 32) {
-          cst[j * 128 + e] = p.scale != nullptr ? __ldg(p.scale + col + e) : 1.0f;
-          cst[j * 128 + 64 + e] = p.shift != nullptr ? __ldg(p.shift + col + e) : 0.0f;
+      int cbase = c.n0;
+      if (!preload) {  // rare: N > C::CONST_N
+        named_bar_sync(3, NUM_EPI_WARPS * 32);  // everyone is done with the previous tile's constants
+        for (int e = ew * 32 + lane; e < BLOCK_N; e += NUM_EPI_WARPS * 32) {
+          cscale[e] = p.scale != nullptr ? __ldg(p.scale + c.n0 + e) : 1.0f;
+          cshift[e] = p.shift != nullptr ? __ldg(p.shift + c.n0 + e) : 0.0f;
         }
+        named_bar_sync(3, NUM_EPI_WARPS * 32);
+        cbase = 0;
       }
-      __syncwarp();
-      if (has_res && issuer && J > 0) {  // residual tile of the first block -> staging buffer
+      if (has_res && issuer && J > 0) {
+        // residual tile of the first block -> staging buffer; the NEXT tile's residual blocks -> L2, so that the
+        // per-block TMA loads of the next tile are L2 hits instead of exposed HBM latency
         uint8_t* buf = stg0 + (it & 1) * STG_BUF_BYTES;
         mbar_expect_tx(&res_bar[grp * 2 + (it & 1)], STG_BUF_BYTES);
         tma_load_4d(buf, &maps.res, &res_bar[grp * 2 + (it & 1)], c.n0 + grp * wcols, o1, o2, r3);
+        const int nct = ct + num_clusters;
+        if (nct < num_ctiles) {
+          const TileCoord cn = decode_ctile(p, nct, n_tiles_n, BLOCK_N, pairs_per_group, rank);
+          int n1, n2, n3;
+          tile_out_coords(p, cn, pool, n1, n2, n3);
+          for (int j = 0; j < J; ++j)
+            tma_prefetch_4d(&maps.res, cn.n0 + (2 * j + grp) * wcols, n1, n2, p.res_mod > 0 ? 0 : n3);
+        }
       }
 
+      const long long tB = clock64();
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      const long long tC = clock64();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BLOCK_N;
-
-      // one 32-column TMEM chunk -> staging row.  half = which 64-byte half of the 128-byte row (16-bit output only)
-      auto emit_chunk = [&](const uint32_t (&cur)[32], const float* cs, int half, uint8_t* buf) {
-        uint8_t* row = buf + srow * 128;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {  // 8 columns at a time keeps the live register set small
-          float v[8];
-          const float4 sc0 = *reinterpret_cast<const float4*>(cs + q * 8);
-          const float4 sc1 = *reinterpret_cast<const float4*>(cs + q * 8 + 4);
-          const float4 sh0 = *reinterpret_cast<const float4*>(cs + 64 + q * 8);
-          const float4 sh1 = *reinterpret_cast<const float4*>(cs + 64 + q * 8 + 4);
-          v[0] = fmaf(__uint_as_float(cur[q * 8 + 0]), sc0.x, sh0.x);
-          v[1] = fmaf(__uint_as_float(cur[q * 8 + 1]), sc0.y, sh0.y);
-          v[2] = fmaf(__uint_as_float(cur[q * 8 + 2]), sc0.z, sh0.z);
-          v[3] = fmaf(__uint_as_float(cur[q * 8 + 3]), sc0.w, sh0.w);
-          v[4] = fmaf(__uint_as_float(cur[q * 8 + 4]), sc1.x, sh1.x);
-          v[5] = fmaf(__uint_as_float(cur[q * 8 + 5]), sc1.y, sh1.y);
-          v[6] = fmaf(__uint_as_float(cur[q * 8 + 6]), sc1.z, sh1.z);
-          v[7] = fmaf(__uint_as_float(cur[q * 8 + 7]), sc1.w, sh1.w);
-          if (p.act == ACT_RELU) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.0f);
-          } else if (p.act == ACT_GELU) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = gelu_erf_fast(v[e]);
-          }
-          if (p.pool) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              v[e] = fmaxf(v[e], __shfl_xor_sync(0xFFFFFFFFu, v[e], 1));
-              v[e] = fmaxf(v[e], __shfl_xor_sync(0xFFFFFFFFu, v[e], 16));
-            }
-          }
-          if (writer) {
-            if (p.out_f32) {
-              float4* d0 = reinterpret_cast<float4*>(row + (((2 * q) ^ sw) << 4));
-              float4* d1 = reinterpret_cast<float4*>(row + (((2 * q + 1) ^ sw) << 4));
-              if (has_res) {
-                const float4 r0 = *d0, r1 = *d1;
-                v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-                v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-              }
-              *d0 = make_float4(v[0], v[1], v[2], v[3]);
-              *d1 = make_float4(v[4], v[5], v[6], v[7]);
-            } else {
-              uint4 pk;
-              pk.x = pack_16x2(v[0], v[1], p.f16);
-              pk.y = pack_16x2(v[2], v[3], p.f16);
-              pk.z = pack_16x2(v[4], v[5], p.f16);
-              pk.w = pack_16x2(v[6], v[7], p.f16);
-              *reinterpret_cast<uint4*>(row + (((half * 4 + q) ^ sw) << 4)) = pk;
-            }
-          }
-        }
-      };
 
       // hand a finished column block to the TMA: all 128 threads of the group have written (and fenced) their rows
       auto finish_block = [&](int j, uint8_t* buf, int col0) {
@@ -317,7 +470,8 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
         if (issuer) tma_store_wait_read0();  // the previous store of this group has released the other buffer
         named_bar_sync(1 + grp, 128);
         if (issuer) {
-          if (!(p.dbg & 1)) tma_store_4d(omap, buf, col0, o1, o2, o3);
+          if (red_add) tma_reduce_add_4d(omap, buf, col0, o1, o2, o3);
+          else if (!(p.dbg & 1)) tma_store_4d(omap, buf, col0, o1, o2, o3);
           tma_store_commit();
           if (has_res && j + 1 < J) {        // residual tile of the next block -> the other buffer
             const uint32_t nb = (it + 1) & 1;
@@ -330,18 +484,22 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
 
       uint32_t ra[32], rb[32];
       if (J > 0) tmem_ld32(t_base + grp * wcols, ra);
-      if (!p.out_f32) {
+      if (!out_f32) {
         // 16-bit output: a block is two 32-column TMEM chunks; the next chunk is always in flight
         for (int j = 0; j < J; ++j) {
           const int blk = 2 * j + grp;
           uint8_t* buf = stg0 + (it & 1) * STG_BUF_BYTES;
-          const float* cs = cst + j * 128;
+          uint8_t* row = buf + srow * 128;
+          const float* sc = cscale + cbase + blk * 64;
+          const float* sh = cshift + cbase + blk * 64;
           tmem_ld_wait(ra);
           tmem_ld32(t_base + blk * 64 + 32, rb);
-          emit_chunk(ra, cs, 0, buf);
+          if (p.f16) emit16<EPI, true>(ra, sc, sh, p, relu_lo, row, 0, sw, writer);
+          else emit16<EPI, false>(ra, sc, sh, p, relu_lo, row, 0, sw, writer);
           tmem_ld_wait(rb);
           if (j + 1 < J) tmem_ld32(t_base + (blk + 2) * 64, ra);
-          emit_chunk(rb, cs + 32, 1, buf);
+          if (p.f16) emit16<EPI, true>(rb, sc + 32, sh + 32, p, relu_lo, row, 1, sw, writer);
+          else emit16<EPI, false>(rb, sc + 32, sh + 32, p, relu_lo, row, 1, sw, writer);
           finish_block(j, buf, c.n0 + blk * 64);
         }
       } else {
@@ -352,7 +510,8 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
           if (has_res) mbar_wait(&res_bar[grp * 2 + (it & 1)], (it >> 1) & 1);
           tmem_ld_wait(cur);
           if (j + 1 < J) tmem_ld32(t_base + (blk + 2) * 32, nxt);
-          emit_chunk(cur, cst + j * 128, 0, buf);
+          emit32<EPI>(cur, cscale + cbase + blk * 32, cshift + cbase + blk * 32, p, relu_lo, buf + srow * 128, sw,
+                      has_res);
           finish_block(j, buf, c.n0 + blk * 32);
         };
         for (int j = 0; j < J; j += 2) {
@@ -367,6 +526,14 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
         acc = 0;
         acc_phase ^= 1;
       }
+      e_cst += tB - tA; ew_full += tC - tB; e_blk += clock64() - tC; ++e_tiles;
+    }
+    if (p.prof && ew == 0 && lane == 0) {
+      p.prof[blockIdx.x * 16 + 5] = ew_full;
+      p.prof[blockIdx.x * 16 + 6] = e_cst;
+      p.prof[blockIdx.x * 16 + 7] = e_blk;
+      p.prof[blockIdx.x * 16 + 8] = clock64() - et0;
+      p.prof[blockIdx.x * 16 + 9] = e_tiles;
     }
     if (issuer) tma_store_wait_all();  // global writes complete before the kernel (and its smem) goes away
   }
@@ -376,13 +543,13 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
   if (warp == 2) tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int EPI>
 int launch_impl2(const IgemmParams& p, const IgemmMaps& maps, int num_ctiles, int n_tiles_n, int pairs_per_group,
                  int num_sms, cudaStream_t stream) {
   using C = Cfg2<BLOCK_N>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_tc2_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(igemm_tc2_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("igemm_tc2: cudaFuncSetAttribute(%d B smem) failed: %s", C::SMEM_BYTES, cudaGetErrorString(e));
@@ -392,18 +559,43 @@ int launch_impl2(const IgemmParams& p, const IgemmMaps& maps, int num_ctiles, in
   }
   const int max_clusters = num_sms / 2;
   const int clusters = num_ctiles < max_clusters ? num_ctiles : max_clusters;
-  igemm_tc2_kernel<BLOCK_N><<<2 * clusters, NUM_THREADS, C::SMEM_BYTES, stream>>>(maps, p, num_ctiles, n_tiles_n,
-                                                                                  pairs_per_group);
+  igemm_tc2_kernel<BLOCK_N, EPI><<<2 * clusters, NUM_THREADS, C::SMEM_BYTES, stream>>>(maps, p, num_ctiles, n_tiles_n,
+                                                                                       pairs_per_group);
   const cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess) {
     cudaFuncAttributes fa;
     memset(&fa, 0, sizeof(fa));
-    cudaFuncGetAttributes(&fa, igemm_tc2_kernel<BLOCK_N>);
-    set_error("igemm_tc2<%d>: %s (grid %d, threads %d, dyn smem %d, regs %d, maxThreadsPerBlock %d)", BLOCK_N,
+    cudaFuncGetAttributes(&fa, igemm_tc2_kernel<BLOCK_N, EPI>);
+    set_error("igemm_tc2<%d,%d>: %s (grid %d, threads %d, dyn smem %d, regs %d, maxThreadsPerBlock %d)", BLOCK_N, EPI,
               cudaGetErrorString(le), 2 * clusters, NUM_THREADS, C::SMEM_BYTES, fa.numRegs, fa.maxThreadsPerBlock);
     return -4;
   }
   return 0;
+}
+
+// which compiled epilogue serves this parameter combination (see the EPI_* enum)
+int pick_epi(const IgemmParams& p) {
+  if (p.dbg & 16) return EPI_GENERIC;
+  if (p.out_f32) return (p.act == ACT_NONE && p.scale == nullptr && !p.pool) ? EPI_F32 : EPI_GENERIC;
+  if (p.residual != nullptr) return EPI_GENERIC;
+  if (p.pool) return (p.act != ACT_GELU) ? EPI_BNPOOL16 : EPI_GENERIC;
+  if (p.scale != nullptr) return (p.act != ACT_GELU) ? EPI_BN16 : EPI_GENERIC;
+  if (p.act == ACT_GELU) return EPI_GELU16;
+  if (p.act == ACT_NONE) return EPI_LIN16;
+  return EPI_BN16;  // ReLU without scale: scale constants default to 1
+}
+
+template <int BLOCK_N>
+int launch_n(const IgemmParams& p, const IgemmMaps& maps, int a, int n_tiles_n, int b, int num_sms,
+             cudaStream_t stream) {
+  switch (pick_epi(p)) {
+    case EPI_LIN16: return launch_impl2<BLOCK_N, EPI_LIN16>(p, maps, a, n_tiles_n, b, num_sms, stream);
+    case EPI_GELU16: return launch_impl2<BLOCK_N, EPI_GELU16>(p, maps, a, n_tiles_n, b, num_sms, stream);
+    case EPI_BN16: return launch_impl2<BLOCK_N, EPI_BN16>(p, maps, a, n_tiles_n, b, num_sms, stream);
+    case EPI_BNPOOL16: return launch_impl2<BLOCK_N, EPI_BNPOOL16>(p, maps, a, n_tiles_n, b, num_sms, stream);
+    case EPI_F32: return launch_impl2<BLOCK_N, EPI_F32>(p, maps, a, n_tiles_n, b, num_sms, stream);
+    default: return launch_impl2<BLOCK_N, EPI_GENERIC>(p, maps, a, n_tiles_n, b, num_sms, stream);
+  }
 }
 
 }  // namespace
@@ -421,6 +613,9 @@ int launch_igemm_tc2(const IgemmParams& p, const IgemmMaps& maps, int block_n, i
     set_error("igemm_tc2: a residual input needs an fp32 output");
     return -1;
   }
+  IgemmParams pp = p;
+  pp.res_inplace = (p.residual != nullptr && p.residual == p.out && p.ldr == p.ldc && p.res_mod == 0 &&
+                    !(p.dbg & 32)) ? 1 : 0;
   const int n_tiles_n = p.N / block_n;
   long long group_tiles;
   int groups = 1;
@@ -438,9 +633,9 @@ int launch_igemm_tc2(const IgemmParams& p, const IgemmMaps& maps, int block_n, i
   }
   const int a = static_cast<int>(nct), b = static_cast<int>(pairs_per_group);
   switch (block_n) {
-    case 256: return launch_impl2<256>(p, maps, a, n_tiles_n, b, num_sms, stream);
-    case 128: return launch_impl2<128>(p, maps, a, n_tiles_n, b, num_sms, stream);
-    case 64: return launch_impl2<64>(p, maps, a, n_tiles_n, b, num_sms, stream);
+    case 256: return launch_n<256>(pp, maps, a, n_tiles_n, b, num_sms, stream);
+    case 128: return launch_n<128>(pp, maps, a, n_tiles_n, b, num_sms, stream);
+    case 64: return launch_n<64>(pp, maps, a, n_tiles_n, b, num_sms, stream);
     default: set_error("igemm_tc2: block_n must be 64/128/256"); return -1;
   }
 }

@@ -39,6 +39,8 @@ struct IgemmParams {
   const float* residual;  // fp32 [*, ldr] added after activation, or null
   int ldr;
   int res_mod;          // > 0: residual row = out_row % res_mod (positional-embedding table)
+  int res_inplace;      // set by the launcher: residual == out (same pitch) -> the epilogue adds into global memory
+                        // with a TMA reduce-add instead of loading the residual tile
   int pool;             // 1: fused 2x2 max-pool (IG_CONV3 only)
   void* out;
   int ldc;              // elements between consecutive output rows
@@ -47,6 +49,7 @@ struct IgemmParams {
   int dbg;              // diagnostics only (HVIT_DBG): 1 skip global stores, 2 skip TMEM loads, 4 skip MMA issue
   int Ho, Wo;           // valid output image dims (conv modes)
   int HoPitch;          // image row pitch of the output buffer in pixel rows (>= Ho)
+  long long* prof;      // diagnostics only (HVIT_PROF): per-CTA cycle counters [gridDim.x][16], or null
 };
 
 // tcgen05 path. A / Wt are described by TMA tensor maps built on the host (see tmap.cpp).
