@@ -117,6 +117,14 @@ static int tmap_qkv(CUtensorMap* m, const void* base, int B, int N, int D) {
   return make_tmap(m, base, 3, dims, strides, box);
 }
 
+// attention output [B*N, D] 16-bit as a (D, N, B) map: 128-row x 64-column (one head) store boxes, clipped at N
+static int tmap_attn_out(CUtensorMap* m, const void* base, int B, int N, int D) {
+  const uint64_t dims[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
+  const uint64_t strides[2] = {static_cast<uint64_t>(D) * 2, static_cast<uint64_t>(N) * D * 2};
+  const uint32_t box[3] = {64, 128, 1};
+  return make_tmap(m, base, 3, dims, strides, box);
+}
+
 // CTA-pair kernel by default; HVIT_IGEMM_1CTA=1 selects the single-CTA kernel (A/B comparison, debugging)
 static bool use_2cta() {
   static int v = -1;
@@ -621,9 +629,11 @@ static int build_steps(hvit_plan* p) {
   const int M = g.M, Np = g.Np, heads = c.num_heads;
   const float scale = 0.125f;  // head_dim^-0.5 with head_dim = 64
   const float eps = c.ln_eps;
-  CUtensorMap tq;
+  CUtensorMap tq, to;
   if (bf && c.num_layers > 0) {
     r = tmap_qkv(&tq, qkv, B, Np, D);
+    if (r) return r;
+    r = tmap_attn_out(&to, att, B, Np, D);
     if (r) return r;
   }
   for (int l = 0; l < c.num_layers; ++l) {
@@ -641,7 +651,7 @@ static int build_steps(hvit_plan* p) {
           const int e = launch_attn_probs_16(qkv, f16, k.probs + probs_off, B, Np, heads, D, scale, k.stream);
           if (e) return e;
         }
-        return launch_attn_tc(tq, att, f16, B, Np, heads, D, scale, k.stream);
+        return launch_attn_tc(tq, to, f16, B, Np, heads, D, scale, k.stream);
       });
       p->tag(L + ".attn", "attn_tc", 4.0 * B * heads * Np * Np * 64.0, 4.0 * B * heads * Np * Np * 64.0,
              static_cast<double>(M) * 4 * D * g.es);
@@ -1065,10 +1075,29 @@ int hvit_attention_16(const void* qkv, void* out, int B, int N, int heads, int f
   int r = require_sm100();
   if (r) return r;
   g_tmap_f16 = f16 ? 1 : 0;
-  CUtensorMap tq;
+  CUtensorMap tq, to;
   r = tmap_qkv(&tq, qkv, B, N, heads * 64);
   if (r) return r;
-  return launch_attn_tc(tq, out, f16 ? 1 : 0, B, N, heads, heads * 64, 0.125f, reinterpret_cast<cudaStream_t>(stream));
+  r = tmap_attn_out(&to, out, B, N, heads * 64);
+  if (r) return r;
+  if (getenv("HVIT_PROF") != nullptr) {  // diagnostics: per-phase cycle counters of the softmax groups
+    const int nc = num_sms();
+    long long* d = nullptr;
+    cudaMalloc(&d, sizeof(long long) * 32 * nc);
+    cudaMemset(d, 0, sizeof(long long) * 32 * nc);
+    r = launch_attn_tc(tq, to, f16 ? 1 : 0, B, N, heads, heads * 64, 0.125f, reinterpret_cast<cudaStream_t>(stream), d);
+    cudaDeviceSynchronize();
+    std::vector<long long> hst(32 * nc);
+    cudaMemcpy(hst.data(), d, sizeof(long long) * 32 * nc, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    double sa[16] = {0};
+    for (int c = 0; c < nc; ++c)
+      for (int k = 0; k < 16; ++k) sa[k] += static_cast<double>(hst[c * 32 + k]) / nc;
+    fprintf(stderr, "[attn prof B=%d N=%d] group A per CTA (%.1f items): wait_s %.0f ld %.0f max %.0f wait_pv/rescale %.0f exp %.0f arrive %.0f finish %.0f total %.0f cycles\n",
+            B, N, sa[7], sa[0], sa[1], sa[2], sa[3], sa[4], sa[5], sa[8], sa[6]);
+    return r;
+  }
+  return launch_attn_tc(tq, to, f16 ? 1 : 0, B, N, heads, heads * 64, 0.125f, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int hvit_attention_f32(const float* qkv, float* out, float* probs, int B, int N, int heads, void* stream) {

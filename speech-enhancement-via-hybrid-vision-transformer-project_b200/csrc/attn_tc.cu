@@ -1,69 +1,155 @@
 // Fused flash-style multi-head self-attention on tcgen05 (head_dim 64), replacing the reference's unfused
 // q@k^T -> softmax -> @v that materialises [B, heads, N, N] (models/attention.py:86-105).
 //
-// One CTA per (clip, head, 128-query tile); 6 warps:
-//   warp 0     TMA producer: Q once, K/V blocks of 128 keys double-buffered (boxes straight out of the
-//              [B*N, 3D] qkv activation: head h of q|k|v lives at columns s*D + h*64)
-//   warp 1     MMA issuer:   S = Q K^T (128x128, fp32 in TMEM), then O_blk = P V (128x64, fp32 in TMEM)
-//   warps 2-5  softmax:      one query row per thread (TMEM lane == row): online max/sum in fp32 registers,
-//              P written to shared memory as bf16 in the 128B-swizzled K-major layout the PV MMA reads,
-//              running output kept in registers and rescaled per block (no TMEM read-modify-write).
-// Keys beyond N (last block) are masked to -inf; TMA zero-fills out-of-range rows of Q/K/V.
+// One CTA per (clip, head, PAIR of 128-query tiles), one CTA per SM, 12 warps:
+//   warp 8      TMA producer: Q tiles once, K/V blocks of 128 keys double-buffered (boxes straight out of the
+//               [B*N, 3D] qkv activation: head h of q|k|v lives at columns s*D + h*64)
+//   warp 9      MMA issuer (one thread): S_w = Q_w K^T (128x128 fp32 in TMEM) and O_w += P_w V (128x64 fp32 in TMEM)
+//               for the two query tiles w = A, B
+//   warps 0-3   softmax group A, warps 4-7 softmax group B: one query row per thread (TMEM lane == row)
+//
+// The two softmax groups work on different query tiles against the same K/V stream, so while one group is in its
+// exp phase (MUFU-bound) the tensor core computes the other group's S / PV and nobody waits on the MMA latency.
+// Per key block a thread pulls its whole 128-score row out of TMEM in one go (the S buffer is released to the MMA
+// warp immediately, S(j+1) is computed while softmax(j) runs), takes the row max with 3-input max, evaluates
+// p = 2^(s*scale*log2e - m) with packed FFMA2 + MUFU.EX2, and writes P as 16-bit into the 128B-swizzled K-major
+// layout the PV MMA reads.  O stays in TMEM for the whole key loop (accumulating MMAs); it is only touched when the
+// running maximum has grown by more than 2^8 since the last rescale ("lazy rescale": P and the row sum simply use
+// the stale maximum, which is exact in real arithmetic and harmless in fp16/bf16/fp32 ranges), and once at the end
+// for the 1/l normalisation + TMA store.
+// Keys beyond N (last block) are masked to -inf; TMA zero-fills out-of-range rows of Q/K/V and clips the store.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace hvit {
 namespace {
 
-constexpr int AT_THREADS = 192;
-constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows x 64 bf16
-constexpr int OFF_Q = 0;
-constexpr int OFF_K = TILE_BYTES;          // 2 stages
-constexpr int OFF_V = 3 * TILE_BYTES;      // 2 stages
-constexpr int OFF_P = 5 * TILE_BYTES;      // 128 x 128 bf16 = two 64-key K-major blocks
-constexpr int OFF_BAR = 7 * TILE_BYTES;
+constexpr int AT_THREADS = 384;  // warpgroups: 0 = softmax A, 1 = softmax B, 2 = {TMA producer, MMA issuer, 2 idle warps}
+constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows x 64 16-bit
+constexpr int KV_STAGES = 3;
+constexpr int OFF_Q = 0;                                  // [2] query tiles
+constexpr int OFF_K = 2 * TILE_BYTES;                     // [KV_STAGES]
+constexpr int OFF_V = OFF_K + KV_STAGES * TILE_BYTES;     // [KV_STAGES]
+constexpr int OFF_P = OFF_V + KV_STAGES * TILE_BYTES;     // [2] x (128 x 128 16-bit = two 64-key K-major blocks)
+constexpr int OFF_O = OFF_P + 4 * TILE_BYTES;                // [2] output staging tiles (TMA store)
+constexpr int OFF_BAR = OFF_O + 2 * TILE_BYTES;
 constexpr int AT_SMEM = OFF_BAR + 256;
-constexpr int TMEM_COLS = 256;             // S: cols [0,128), O_blk: cols [128,192)
+constexpr int TMEM_COLS = 512;  // S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384)
+constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(m),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 
-__global__ void __launch_bounds__(AT_THREADS, 2)
-attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, bf16* __restrict__ out, int N, int D, float scale_log2,
-               int f16) {
+// exp + row-sum + pack of one 128-score row held in registers; P chunks go to shared memory as they are produced.
+//
+// The fp32 -> 16-bit conversion instruction (F2FP) shares the 16-lane/clk XU pipe with MUFU.EX2 (measured: with F2FP
+// packing the exp phase ran at 26 cycles per warp-element instead of MUFU's 8), so P is converted with integer
+// arithmetic on the FMA/ALU pipes instead: the exponent re-bias of fp16 (127 - 15 = 112) is folded into the exp2
+// argument (nbias = m + 112; ex2.approx.ftz flushes what would be an fp16 subnormal to exactly 0), after which
+//   16-bit float = upper half of (bits(e) * mul + 0x8000)      mul = 8 (fp16: 23 -> 10 mantissa bits), 1 (bf16)
+// (round-half-up), and two results are merged with one PRMT.  The row sum uses the same (2^-112-scaled) values; the
+// scale is undone in the final 1/l normalisation.
+__device__ __forceinline__ float exp_pack_row(const uint32_t (&s)[128], float scale_log2, float nbias, uint32_t mul,
+                                              uint8_t* p_row, int sw) {
+  const float2 sc2 = make_float2(scale_log2, scale_log2);
+  const float2 nm2 = make_float2(-nbias, -nbias);
+  float2 sum0 = make_float2(0.f, 0.f), sum1 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {  // 16-byte chunk c = keys 8c .. 8c+7
+    float2 t[4];
+    uint32_t pk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      t[i] = __ffma2_rn(make_float2(__uint_as_float(s[8 * c + 2 * i]), __uint_as_float(s[8 * c + 2 * i + 1])), sc2, nm2);
+      t[i].x = ex2_approx(t[i].x);
+      t[i].y = ex2_approx(t[i].y);
+      pk[i] = __byte_perm(__float_as_uint(t[i].x) * mul + 0x8000u, __float_as_uint(t[i].y) * mul + 0x8000u, 0x7632);
+    }
+    sum0 = __fadd2_rn(sum0, __fadd2_rn(t[0], t[1]));
+    sum1 = __fadd2_rn(sum1, __fadd2_rn(t[2], t[3]));
+    *reinterpret_cast<uint4*>(p_row + (c >> 3) * TILE_BYTES + (((c & 7) ^ sw) << 4)) =
+        make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+  return (sum0.x + sum0.y) + (sum1.x + sum1.y);
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out, int N,
+               int D, int heads, int n_items, float scale_log2, int f16, long long* prof) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B swizzle needs 1024-byte aligned tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* q_full = bars;          // 1
-  uint64_t* k_full = bars + 1;      // [2]
-  uint64_t* v_full = bars + 3;      // [2]
-  uint64_t* kv_empty = bars + 5;    // [2]
-  uint64_t* s_full = bars + 7;
-  uint64_t* p_full = bars + 8;
-  uint64_t* o_full = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* q_full = bars;                      // Q tiles of the current item landed
+  uint64_t* q_empty = bars + 1;                 // every S MMA of the current item has completed (Q may be reloaded)
+  uint64_t* k_full = bars + 2;                  // [KV_STAGES]
+  uint64_t* v_full = k_full + KV_STAGES;        // [KV_STAGES]
+  uint64_t* kv_empty = v_full + KV_STAGES;      // [KV_STAGES]
+  uint64_t* s_full = kv_empty + KV_STAGES;      // [2]  S_w(block) complete in TMEM
+  uint64_t* s_free = s_full + 2;                // [2]  S_w(block) copied to registers by all 128 rows
+  uint64_t* p_full = s_free + 2;                // [2]  P_w(block) in shared memory (and O_w rescaled if needed)
+  uint64_t* pv_done = p_full + 2;               // [2]  O_w += P_w(block) V(block) complete
+  uint64_t* o_free = pv_done + 2;               // [2]  final O_w of an item copied to registers by all 128 rows
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int nkv = (N + 127) / 128;
+  const int qpairs = (N + 255) / 256;
+  // persistent work loop: item -> (clip b, head h, query-tile pair); the pairs of one (b, h) are adjacent items, so
+  // they run at the same time on neighbouring CTAs and share K / V in L2
+  auto decode = [&](int item, int& b, int& h, int& q0) {
+    q0 = (item % qpairs) * 256;
+    const int bh = item / qpairs;
+    h = bh % heads;
+    b = bh / heads;
+  };
 
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_qkv);
-  if (warp == 1 && lane == 0) {
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_out);
+  }
+  if (warp == 9 && lane == 0) {
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    mbar_init(q_empty, 1);
+    for (int s = 0; s < KV_STAGES; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&v_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
+    for (int w = 0; w < 2; ++w) {
+      mbar_init(&s_full[w], 1);
+      mbar_init(&s_free[w], 128);
+      mbar_init(&p_full[w], 128);
+      mbar_init(&pv_done[w], 1);
+      mbar_init(&o_free[w], 128);
+    }
     mbar_fence_init();
   }
-  if (warp == 2) {
+  if (warp == 0) {
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
@@ -71,175 +157,275 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, bf16* __restrict__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
 
-  if (warp == 0) {
-    if (elect_one()) {
-      mbar_expect_tx(q_full, TILE_BYTES);
-      tma_load_3d(smem + OFF_Q, &tmap_qkv, q_full, h * 64, q0, b);
-      for (int j = 0; j < nkv; ++j) {
-        const int st = j & 1;
-        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
-        mbar_expect_tx(&k_full[st], TILE_BYTES);
-        tma_load_3d(smem + OFF_K + st * TILE_BYTES, &tmap_qkv, &k_full[st], D + h * 64, j * 128, b);
-        mbar_expect_tx(&v_full[st], TILE_BYTES);
-        tma_load_3d(smem + OFF_V + st * TILE_BYTES, &tmap_qkv, &v_full[st], 2 * D + h * 64, j * 128, b);
+  // Register re-allocation between warpgroups (the kernel is compiled for 168 registers at 384 threads): the
+  // producer / MMA warpgroup gives registers back, the softmax warpgroups take them - a 128-score row plus the
+  // exp working set must stay in registers (with 168 the row spilled to local memory: 3x slower exp phase).
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    if (warp == 8) {
+      // ------------------------------------------------------------ TMA producer
+      if (elect_one()) {
+        uint32_t it = 0, kv = 0;  // items / K-V blocks issued so far by this CTA
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+          int b, h, q0;
+          decode(item, b, h, q0);
+          const bool hasB = q0 + 128 < N;
+          mbar_wait(q_empty, (it & 1) ^ 1);
+          mbar_expect_tx(q_full, hasB ? 2 * TILE_BYTES : TILE_BYTES);
+          tma_load_3d(smem + OFF_Q, &tmap_qkv, q_full, h * 64, q0, b);
+          if (hasB) tma_load_3d(smem + OFF_Q + TILE_BYTES, &tmap_qkv, q_full, h * 64, q0 + 128, b);
+          for (int j = 0; j < nkv; ++j, ++kv) {
+            const int st = kv % KV_STAGES;
+            mbar_wait(&kv_empty[st], ((kv / KV_STAGES) & 1) ^ 1);
+            mbar_expect_tx(&k_full[st], TILE_BYTES);
+            tma_load_3d(smem + OFF_K + st * TILE_BYTES, &tmap_qkv, &k_full[st], D + h * 64, j * 128, b);
+            mbar_expect_tx(&v_full[st], TILE_BYTES);
+            tma_load_3d(smem + OFF_V + st * TILE_BYTES, &tmap_qkv, &v_full[st], 2 * D + h * 64, j * 128, b);
+          }
+        }
       }
-    }
-  } else if (warp == 1) {
-    if (elect_one()) {
-      const uint32_t idesc_s = make_idesc_16(128, 128, 0, 0, f16);   // Q (K-major) x K (K-major)
-      const uint32_t idesc_pv = make_idesc_16(128, 64, 0, 1, f16);   // P (K-major) x V (MN-major)
-      const uint32_t q_addr = smem_u32(smem + OFF_Q);
-      const uint32_t p_addr = smem_u32(smem + OFF_P);
-      auto issue_s = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(&k_full[st], (j >> 1) & 1);
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(smem + OFF_K + st * TILE_BYTES);
+    } else if (warp == 9) {
+      // ------------------------------------------------------------ MMA issuer
+      if (elect_one()) {
+        const uint32_t idesc_s = make_idesc_16(128, 128, 0, 0, f16);   // Q (K-major) x K (K-major)
+        const uint32_t idesc_pv = make_idesc_16(128, 64, 0, 1, f16);   // P (K-major) x V (MN-major)
+        uint32_t it = 0, kv = 0;
+        uint32_t blk[2] = {0, 0};   // key blocks processed so far per softmax group (barrier phases)
+        uint32_t itw[2] = {0, 0};   // items processed so far per softmax group
+        auto issue_s = [&](int w, uint32_t kvi) {
+          const int st = kvi % KV_STAGES;
+          mbar_wait(&k_full[st], (kvi / KV_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t q_addr = smem_u32(smem + OFF_Q + w * TILE_BYTES);
+          const uint32_t k_addr = smem_u32(smem + OFF_K + st * TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_s, make_smem_desc_sw128(q_addr + k * 32, 1024, 16),
-                    make_smem_desc_sw128(k_addr + k * 32, 1024, 16), idesc_s, k != 0 ? 1u : 0u);
-        umma_commit(s_full);
-      };
-      mbar_wait(q_full, 0);
-      issue_s(0);
-      for (int j = 0; j < nkv; ++j) {
-        const int st = j & 1;
-        mbar_wait(p_full, j & 1);
-        mbar_wait(&v_full[st], (j >> 1) & 1);
-        tc_fence_after();
-        const uint32_t v_addr = smem_u32(smem + OFF_V + st * TILE_BYTES);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + w * 128, make_smem_desc_sw128(q_addr + k * 32, 1024, 16),
+                      make_smem_desc_sw128(k_addr + k * 32, 1024, 16), idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(&s_full[w]);
+        };
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+          int b, h, q0;
+          decode(item, b, h, q0);
+          const int nw = (q0 + 128 < N) ? 2 : 1;
+          mbar_wait(q_full, it & 1);
+          for (int w = 0; w < nw; ++w) {
+            if (blk[w] > 0) {  // the group's last score block of its previous item has left TMEM
+              mbar_wait(&s_free[w], (blk[w] - 1) & 1);
+              tc_fence_after();
+            }
+            issue_s(w, kv);
+          }
+          if (nkv == 1) umma_commit(q_empty);
+          for (int j = 0; j < nkv; ++j, ++kv) {
+            const int st = kv % KV_STAGES;
+            if (j + 1 < nkv) {
+              for (int w = 0; w < nw; ++w) {  // S_w(j+1) as soon as the softmax group has S_w(j) in registers
+                mbar_wait(&s_free[w], (blk[w] + j) & 1);
+                tc_fence_after();
+                issue_s(w, kv + 1);
+              }
+              if (j + 2 == nkv) umma_commit(q_empty);  // last S MMAs of this item issued
+            }
+            mbar_wait(&v_full[st], (kv / KV_STAGES) & 1);
+            for (int w = 0; w < nw; ++w) {
+              mbar_wait(&p_full[w], (blk[w] + j) & 1);
+              if (j == 0 && itw[w] > 0) mbar_wait(&o_free[w], (itw[w] - 1) & 1);  // previous item's O_w read out
+              tc_fence_after();
+              const uint32_t p_addr = smem_u32(smem + OFF_P + w * 2 * TILE_BYTES);
+              const uint32_t v_addr = smem_u32(smem + OFF_V + st * TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_bf16(tmem_o, make_smem_desc_sw128(p_addr + (k >> 2) * TILE_BYTES + (k & 3) * 32, 1024, 16),
-                    make_smem_desc_sw128(v_addr + k * 2048, 1024, 1024), idesc_pv, k != 0 ? 1u : 0u);
-        umma_commit(o_full);
-        umma_commit(&kv_empty[st]);
-        if (j + 1 < nkv) issue_s(j + 1);
+              for (int k = 0; k < 8; ++k)
+                umma_bf16(tmem_base + 256 + w * 64,
+                          make_smem_desc_sw128(p_addr + (k >> 2) * TILE_BYTES + (k & 3) * 32, 1024, 16),
+                          make_smem_desc_sw128(v_addr + k * 2048, 1024, 1024), idesc_pv, (j | k) != 0 ? 1u : 0u);
+              umma_commit(&pv_done[w]);
+            }
+            umma_commit(&kv_empty[st]);  // K / V stage free once everything issued so far has completed
+          }
+          for (int w = 0; w < nw; ++w) {
+            blk[w] += nkv;
+            ++itw[w];
+          }
+        }
       }
     }
   } else {
+    // ------------------------------------------------------------ softmax groups
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    const int w = warp >> 2;  // 0: tile A, 1: tile B
     const int sub = warp & 3;
     const int row = sub * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(sub * 32) << 16;
-    uint8_t* p_row = smem + OFF_P + row * 128;
+    const uint32_t tmem_s = tmem_base + w * 128 + lane_addr;
+    const uint32_t tmem_o = tmem_base + 256 + w * 64 + lane_addr;
+    uint8_t* p_row = smem + OFF_P + w * 2 * TILE_BYTES + row * 128;
+    uint8_t* o_stage = smem + OFF_O + w * TILE_BYTES;
     const int sw = row & 7;
-    float m_run = -INFINITY, l_run = 0.f;
-    float o[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) o[i] = 0.f;
+    const float ebias = f16 ? 112.0f : 0.0f;   // see exp_pack_row
+    const uint32_t emul = f16 ? 8u : 1u;
+    const float unbias = f16 ? 1.925929944387236e-34f /* 2^-112 */ : 1.0f;
+    uint32_t blk = 0, itw = 0;
+    long long t_sfull = 0, t_ld = 0, t_max = 0, t_pv = 0, t_exp = 0, t_arr = 0, t_fin = 0;
+    const long long T0 = clock64();
 
-    for (int j = 0; j < nkv; ++j) {
-      const int nvalid = min(128, N - j * 128);
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      // Instruction diet (ncu: this kernel is issue-bound): the row maximum is taken on the raw scores (one FMNMX
-      // per element, scaled once), exp2 is a bare MUFU.EX2 fed by one FFMA, and key masking only exists in the code
-      // path of a partial last block.
-      const bool full = nvalid == 128;
-      float mraw = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_s + lane_addr + c * 32, r);
-        tmem_ld_wait(r);
-        if (full) {
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      int b, h, q0;
+      decode(item, b, h, q0);
+      if (w == 1 && !(q0 + 128 < N)) continue;  // this pair has no second query tile
+      float m_used = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < nkv; ++j, ++blk) {
+        const int nvalid = min(128, N - j * 128);
+        const long long c0 = clock64();
+        mbar_wait(&s_full[w], blk & 1);
+        tc_fence_after();
+        const long long c1 = clock64();
+        uint32_t s[128];
+        {
+          uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
+          uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
+          uint32_t(&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
+          uint32_t(&s3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[96]);
+          tmem_ld32(tmem_s, s0);
+          tmem_ld32(tmem_s + 32, s1);
+          tmem_ld32(tmem_s + 64, s2);
+          tmem_ld32(tmem_s + 96, s3);
+          tmem_ld_wait(s0);
+          tmem_ld_wait(s1);
+          tmem_ld_wait(s2);
+          tmem_ld_wait(s3);
+        }
+        tc_fence_before();
+        mbar_arrive(&s_free[w]);  // the MMA warp may overwrite S_w with the next block
+        const long long c2 = clock64();
+        if (nvalid < 128) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mraw = fmaxf(mraw, __uint_as_float(r[i]));
+          for (int i = 0; i < 128; ++i)
+            if (i >= nvalid) s[i] = 0xFF800000u;  // -inf: exp2 -> exactly 0
+        }
+        // row maximum: 8 independent 3-input max chains (short dependency chains, 1 instruction per 2 scores)
+        float mr[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mr[i] = fmaxf(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]));
+#pragma unroll
+        for (int i = 16; i < 128; i += 16) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) mr[k] = max3(mr[k], __uint_as_float(s[i + 2 * k]), __uint_as_float(s[i + 2 * k + 1]));
+        }
+        const float mnew =
+            fmaxf(max3(mr[0], mr[1], mr[2]), max3(max3(mr[3], mr[4], mr[5]), mr[6], mr[7])) * scale_log2;
+        const long long c3 = clock64();
+        if (j == 0) {
+          m_used = mnew;
         } else {
+          const bool need = mnew > m_used + RESCALE_THRESHOLD;
+          mbar_wait(&pv_done[w], (blk - 1) & 1);  // O_w up to the previous block complete; P_w may be overwritten
+          if (__any_sync(0xFFFFFFFFu, need)) {
+            const float alpha = need ? ex2_approx(m_used - mnew) : 1.0f;
+            if (need) m_used = mnew;
+            l_run *= alpha;
+            tc_fence_after();
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < nvalid) mraw = fmaxf(mraw, __uint_as_float(r[i]));
-        }
-      }
-      const float mx = fmaxf(m_run, mraw * scale_log2);
-      const float alpha = ex2_approx(m_run - mx);
-      float rowsum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_s + lane_addr + c * 32, r);
-        tmem_ld_wait(r);
+            for (int c = 0; c < 2; ++c) {
+              uint32_t r[32];
+              tmem_ld32(tmem_o + c * 32, r);
+              tmem_ld_wait(r);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float pv[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            pv[i] = ex2_approx(fmaf(__uint_as_float(r[q * 8 + i]), scale_log2, -mx));
-            if (!full && c * 32 + q * 8 + i >= nvalid) pv[i] = 0.f;
+              for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+              tmem_st32(tmem_o + c * 32, r);
+            }
+            tmem_st_wait();
           }
-          rowsum += ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7]));
-          const int cidx = c * 4 + q;  // 16-byte chunk index along the 128 keys
-          uint4 pk;
-          pk.x = pack_16x2(pv[0], pv[1], f16);
-          pk.y = pack_16x2(pv[2], pv[3], f16);
-          pk.z = pack_16x2(pv[4], pv[5], f16);
-          pk.w = pack_16x2(pv[6], pv[7], f16);
-          *reinterpret_cast<uint4*>(p_row + (cidx >> 3) * TILE_BYTES + (((cidx & 7) ^ sw) << 4)) = pk;
         }
+        const long long c4 = clock64();
+        l_run += exp_pack_row(s, scale_log2, m_used + ebias, emul, p_row, sw);
+        const long long c5 = clock64();
+        fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor-core async proxy
+        tc_fence_before();
+        mbar_arrive(&p_full[w]);
+        const long long c6 = clock64();
+        t_sfull += c1 - c0; t_ld += c2 - c1; t_max += c3 - c2; t_pv += c4 - c3; t_exp += c5 - c4; t_arr += c6 - c5;
       }
-      l_run = l_run * alpha + rowsum;
-      m_run = mx;
-      fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor-core async proxy
-      tc_fence_before();
-      mbar_arrive(p_full);
 
-      mbar_wait(o_full, j & 1);
+      // ---- end of item: O_w / l -> 16-bit -> swizzled staging -> TMA store (clipped at N)
+      const long long f0 = clock64();
+      mbar_wait(&pv_done[w], (blk - 1) & 1);
       tc_fence_after();
+      const float inv = (1.0f / l_run) * unbias;
+      uint32_t o0[32], o1[32];
+      tmem_ld32(tmem_o, o0);
+      tmem_ld32(tmem_o + 32, o1);
+      tmem_ld_wait(o0);
+      tmem_ld_wait(o1);
+      tc_fence_before();
+      mbar_arrive(&o_free[w]);  // the next item's first PV may overwrite O_w
+      if (sub == 0 && lane == 0) tma_store_wait_read0();  // the previous item's store has released the staging tile
+      named_bar_sync(1 + w, 128);
+      uint8_t* o_row = o_stage + row * 128;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_o + lane_addr + c * 32, r);
-        tmem_ld_wait(r);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha, __uint_as_float(r[i]));
-      }
-    }
-    if (q0 + row < N) {
-      const float inv = 1.0f / l_run;
-      bf16* dst = out + (static_cast<long long>(b) * N + q0 + row) * D + h * 64;
-#pragma unroll
-      for (int i = 0; i < 64; i += 8) {
+      for (int q = 0; q < 8; ++q) {
+        const uint32_t(&r)[32] = q < 4 ? o0 : o1;
+        const int e = (q & 3) * 8;
         uint4 pk;
-        pk.x = pack_16x2(o[i] * inv, o[i + 1] * inv, f16);
-        pk.y = pack_16x2(o[i + 2] * inv, o[i + 3] * inv, f16);
-        pk.z = pack_16x2(o[i + 4] * inv, o[i + 5] * inv, f16);
-        pk.w = pack_16x2(o[i + 6] * inv, o[i + 7] * inv, f16);
-        *reinterpret_cast<uint4*>(dst + i) = pk;
+        pk.x = pack_16x2(__uint_as_float(r[e + 0]) * inv, __uint_as_float(r[e + 1]) * inv, f16);
+        pk.y = pack_16x2(__uint_as_float(r[e + 2]) * inv, __uint_as_float(r[e + 3]) * inv, f16);
+        pk.z = pack_16x2(__uint_as_float(r[e + 4]) * inv, __uint_as_float(r[e + 5]) * inv, f16);
+        pk.w = pack_16x2(__uint_as_float(r[e + 6]) * inv, __uint_as_float(r[e + 7]) * inv, f16);
+        *reinterpret_cast<uint4*>(o_row + ((q ^ sw) << 4)) = pk;
       }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + w, 128);
+      if (sub == 0 && lane == 0) {
+        tma_store_3d(&tmap_out, o_stage, h * 64, q0 + w * 128, b);
+        tma_store_commit();
+      }
+      ++itw;
+      t_fin += clock64() - f0;
+    }
+    if (sub == 0 && lane == 0) tma_store_wait_all();
+    if (prof != nullptr && row == 0) {
+      long long* pp = prof + blockIdx.x * 32 + w * 16;
+      pp[0] = t_sfull; pp[1] = t_ld; pp[2] = t_max; pp[3] = t_pv; pp[4] = t_exp; pp[5] = t_arr; pp[6] = clock64() - T0;
+      pp[7] = itw; pp[8] = t_fin;
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 }  // namespace
 
-int launch_attn_tc(const CUtensorMap& tmap_qkv, void* out16, int f16, int B, int N, int heads, int D, float scale,
-                   cudaStream_t stream) {
+int launch_attn_tc(const CUtensorMap& tmap_qkv, const CUtensorMap& tmap_out, int f16, int B, int N, int heads, int D,
+                   float scale, cudaStream_t stream, long long* prof) {
   if (D != heads * 64) {
     set_error("attention: head_dim must be 64 (D=%d heads=%d)", D, heads);
     return -1;
   }
   static bool configured = false;
+  static int sms = 148;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                               cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) {
       set_error("attn_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return -4;
     }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
     configured = true;
   }
-  dim3 grid((N + 127) / 128, heads, B);
-  attn_tc_kernel<<<grid, AT_THREADS, AT_SMEM, stream>>>(tmap_qkv, reinterpret_cast<bf16*>(out16), N, D,
-                                                         scale * 1.4426950408889634f, f16);
+  const long long items = static_cast<long long>((N + 255) / 256) * heads * B;
+  if (items <= 0 || items > 0x7FFFFFFF) {
+    set_error("attention: bad problem size B=%d N=%d heads=%d", B, N, heads);
+    return -1;
+  }
+  const int grid = items < sms ? static_cast<int>(items) : sms;
+  attn_tc_kernel<<<grid, AT_THREADS, AT_SMEM, stream>>>(tmap_qkv, tmap_out, N, D, heads, static_cast<int>(items),
+                                                        scale * 1.4426950408889634f, f16, prof);
   return check_launch("attn_tc");
 }
 

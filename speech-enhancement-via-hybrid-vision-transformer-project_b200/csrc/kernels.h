@@ -71,8 +71,8 @@ int launch_igemm_f32(const IgemmParams& p, const float* A, int lda, const float*
 // ---------------------------------------------------------------------------------------------
 // Attention. qkv: [B*N, 3*D] (q | k | v, head h at columns h*64 .. h*64+63 of each third), out: [B*N, D].
 // ---------------------------------------------------------------------------------------------
-int launch_attn_tc(const CUtensorMap& tmap_qkv, void* out16, int f16, int B, int N, int heads, int D, float scale,
-                   cudaStream_t stream);
+int launch_attn_tc(const CUtensorMap& tmap_qkv, const CUtensorMap& tmap_out /*[B*N, D] 16-bit*/, int f16, int B, int N, int heads, int D, float scale,
+                   cudaStream_t stream, long long* prof = nullptr);
 int launch_attn_f32(const float* qkv, float* out, float* probs /*nullable [B,h,N,N]*/, int B, int N, int heads, int D,
                     float scale, cudaStream_t stream);
 // probabilities only (return_attentions=True slow path) from bf16 qkv
