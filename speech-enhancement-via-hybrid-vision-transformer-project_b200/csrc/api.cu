@@ -58,7 +58,7 @@ static thread_local int g_tmap_f16 = 0;
 
 // 16-bit tensor (bf16 or fp16), 128-byte swizzle, zero fill out of bounds. dims/box innermost first; strides (bytes) for dims 1..rank-1.
 static int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                     const uint32_t* box, int f32 = 0) {
+                     const uint32_t* box, int f32 = 0, int no_swizzle = 0) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -74,7 +74,8 @@ static int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t*
     if (i > 0) gs[i - 1] = strides[i - 1];
   }
   const CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (g_tmap_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), static_cast<cuuint32_t>(rank), const_cast<void*>(base),
-                        gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        no_swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d) rank=%d dims=[%llu,%llu,%llu,...] box=[%u,%u,...]",
@@ -400,6 +401,7 @@ static int build_geometry(const hvit_model_cfg& c, int B, int F, int T, int n_sa
     }
   }
   if (!bf && tmp_elems > 0) add("conv_tmp", 4, 1, static_cast<int>(tmp_elems), 0, 0, 0, tmp_elems);
+  if (bf) add("stem_a", 2, 1, 4 * 128 * 64, 0, 0, 0, 4 * 128 * 64);
   const size_t M = g.M;
   add("tokens", 4, 2, g.M, c.embed_dim, 0, 0, M * c.embed_dim);
   add("ln", g.es, 2, g.M, c.embed_dim, 0, 0, M * c.embed_dim);
@@ -564,10 +566,30 @@ static int build_steps(hvit_plan* p) {
     void* out = at<void>(p, "enc0");
     const int C0 = c.enc_channels[0], pool = c.enc_pool[0], F = g.F, T = g.T;
     const float *sw = w.stem_w, *ss = w.stem_scale, *sh = w.stem_shift;
-    p->steps.push_back([=](const Ctx& k) { return launch_stem(k.x, k.mag_max, sw, ss, sh, out, dt, B, F, T, C0, pool, k.stream); });
+    const bool stem_tc = bf && C0 == 64 && pool == 2 && g.enc[0].pitch == g.enc[0].H && getenv("HVIT_STEM_SIMT") == nullptr;
+    if (stem_tc) {
+      // tensor-core stem: the position matrices are derived from the weights once, here
+      void* apack = at<void>(p, "stem_a");
+      r = launch_stem_pack(sw, ss, apack, f16, nullptr);
+      if (r) return r;
+      if (cudaStreamSynchronize(nullptr) != cudaSuccess) return check_launch("stem_pack(sync)");
+      const int sms = num_sms();
+      const int Ho = g.enc[0].H, Wo = g.enc[0].W;
+      CUtensorMap tmo;  // (64 channels, Wo, Ho, B), un-swizzled 32-channel x 32-pixel store boxes (one per epilogue warp)
+      {
+        const uint64_t dims[4] = {64, static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho), static_cast<uint64_t>(B)};
+        const uint64_t strides[3] = {128, static_cast<uint64_t>(Wo) * 128, static_cast<uint64_t>(Ho) * Wo * 128};
+        const uint32_t box[4] = {32, 32, 1, 1};
+        r = make_tmap(&tmo, out, 4, dims, strides, box, 0, 1);
+        if (r) return r;
+      }
+      p->steps.push_back([=](const Ctx& k) { return launch_stem_tc(k.x, k.mag_max, apack, sh, tmo, f16, B, F, T, sms, k.stream); });
+    } else {
+      p->steps.push_back([=](const Ctx& k) { return launch_stem(k.x, k.mag_max, sw, ss, sh, out, dt, B, F, T, C0, pool, k.stream); });
+    }
     {
       const double fl = 2.0 * B * F * T * C0 * 9.0;
-      p->tag("encoder.0", "stem", fl, fl, static_cast<double>(B) * F * T * 4 + static_cast<double>(B) * g.enc[0].H * g.enc[0].W * C0 * g.es);
+      p->tag("encoder.0", stem_tc ? "stem_tc" : "stem", fl, fl, static_cast<double>(B) * F * T * 4 + static_cast<double>(B) * g.enc[0].H * g.enc[0].W * C0 * g.es);
     }
   }
   // 2. encoder blocks 1.. : implicit-GEMM 3x3 conv + folded BN + ReLU (+ fused 2x2 max-pool)
