@@ -205,6 +205,7 @@ def run_ours(args):
     ev2.record()
     for _ in range(args.steps):
         enh.enhance_pinned(pin_in, pin_out, synchronize=False)
+    enh.join()  # the timed stream waits for every outstanding D2H copy: all K copies-out are inside the region
     ev3.record()
     barrier()
     e2e_wall = time.perf_counter() - t_wall

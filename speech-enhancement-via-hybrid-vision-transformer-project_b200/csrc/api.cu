@@ -24,6 +24,15 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("HVIT_NO_PDL");
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int check_launch(const char* what) {
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -1020,31 +1029,6 @@ int hvit_gemm_16(const void* a, int lda, const void* w, const float* scale, cons
   if (r) return r;
   r = make_out_maps(q, &mp);
   if (r) return r;
-  if (getenv("HVIT_PROF") != nullptr) {  // diagnostics: per-role cycle counters of one launch, printed to stderr
-    const int ncta = num_sms();
-    long long* d = nullptr;
-    cudaMalloc(&d, sizeof(long long) * 16 * ncta);
-    cudaMemset(d, 0, sizeof(long long) * 16 * ncta);
-    q.prof = d;
-    r = launch_igemm_any(q, mp, bn, ncta, reinterpret_cast<cudaStream_t>(stream));
-    cudaDeviceSynchronize();
-    std::vector<long long> h(16 * ncta);
-    cudaMemcpy(h.data(), d, sizeof(long long) * 16 * ncta, cudaMemcpyDeviceToHost);
-    cudaFree(d);
-    double s[16] = {0};
-    int n = 0;
-    for (int c = 0; c < ncta; c += 2) {  // leader CTAs
-      for (int k = 0; k < 16; ++k) s[k] += static_cast<double>(h[c * 16 + k]);
-      ++n;
-    }
-    for (int k = 0; k < 16; ++k) s[k] /= n;
-    fprintf(stderr,
-            "[prof M=%d N=%d K=%d act=%d f32=%d res=%d] tiles/cta %.1f | producer wait_empty %.0f total %.0f | mma "
-            "wait_tmem_empty %.0f wait_full %.0f total %.0f | epi cst %.0f wait_full %.0f blocks %.0f total %.0f "
-            "[fence %.0f wait_read %.0f bar %.0f] (cycles, mean over leader CTAs)\n",
-            M, N, K, act, out_f32, residual != nullptr, s[9], s[0], s[1], s[2], s[3], s[4], s[6], s[5], s[7], s[8], s[10], s[11], s[12]);
-    return r;
-  }
   return launch_igemm_any(q, mp, bn, num_sms(), reinterpret_cast<cudaStream_t>(stream));
 }
 

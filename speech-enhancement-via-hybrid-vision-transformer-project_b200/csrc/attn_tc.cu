@@ -157,6 +157,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();
+  griddep_wait();  // PDL: everything above overlapped the previous kernel's tail
 
   // Register re-allocation between warpgroups (the kernel is compiled for 168 registers at 384 threads): the
   // producer / MMA warpgroup gives registers back, the softmax warpgroups take them - a 128-score row plus the
@@ -424,8 +426,12 @@ int launch_attn_tc(const CUtensorMap& tmap_qkv, const CUtensorMap& tmap_out, int
     return -1;
   }
   const int grid = items < sms ? static_cast<int>(items) : sms;
-  attn_tc_kernel<<<grid, AT_THREADS, AT_SMEM, stream>>>(tmap_qkv, tmap_out, N, D, heads, static_cast<int>(items),
-                                                        scale * 1.4426950408889634f, f16, prof);
+  const cudaError_t le = launch_pdl(attn_tc_kernel, dim3(grid), dim3(AT_THREADS), AT_SMEM, stream, tmap_qkv, tmap_out, N, D,
+                                    heads, static_cast<int>(items), scale * 1.4426950408889634f, f16, prof);
+  if (le != cudaSuccess) {
+    set_error("attn_tc: %s", cudaGetErrorString(le));
+    return -4;
+  }
   return check_launch("attn_tc");
 }
 

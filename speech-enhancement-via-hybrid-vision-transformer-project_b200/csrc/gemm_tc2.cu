@@ -26,7 +26,10 @@
 // Epilogue organisation: 8 warps = 2 groups x 4 warps (a group covers the four TMEM lane quarters).  Group g owns
 // the column blocks j = g, g+2, ... of the tile (a block is 128 bytes of every output row: 64 16-bit or 32 fp32
 // columns), with two 16 KB staging buffers, its own named barrier and its own store-issuing thread.
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -276,6 +279,8 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
   cluster_sync_all();  // barrier inits and TMEM allocation of both CTAs visible before any cross-CTA traffic
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();  // PDL: the next kernel's prologue may overlap this kernel ...
+  griddep_wait();               // ... and everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
@@ -559,9 +564,9 @@ int launch_impl2(const IgemmParams& p, const IgemmMaps& maps, int num_ctiles, in
   }
   const int max_clusters = num_sms / 2;
   const int clusters = num_ctiles < max_clusters ? num_ctiles : max_clusters;
-  igemm_tc2_kernel<BLOCK_N, EPI><<<2 * clusters, NUM_THREADS, C::SMEM_BYTES, stream>>>(maps, p, num_ctiles, n_tiles_n,
-                                                                                       pairs_per_group);
-  const cudaError_t le = cudaGetLastError();
+  cudaError_t le = launch_pdl(igemm_tc2_kernel<BLOCK_N, EPI>, dim3(2 * clusters), dim3(NUM_THREADS), C::SMEM_BYTES,
+                              stream, maps, p, num_ctiles, n_tiles_n, pairs_per_group);
+  if (le == cudaSuccess) le = cudaGetLastError();
   if (le != cudaSuccess) {
     cudaFuncAttributes fa;
     memset(&fa, 0, sizeof(fa));
@@ -632,6 +637,32 @@ int launch_igemm_tc2(const IgemmParams& p, const IgemmMaps& maps, int block_n, i
     return -1;
   }
   const int a = static_cast<int>(nct), b = static_cast<int>(pairs_per_group);
+  if (getenv("HVIT_PROF") != nullptr && pp.prof == nullptr) {
+    // diagnostics: per-role cycle counters of this launch (mean over the leader CTAs), printed to stderr
+    long long* d = nullptr;
+    cudaMalloc(&d, sizeof(long long) * 16 * num_sms);
+    cudaMemset(d, 0, sizeof(long long) * 16 * num_sms);
+    IgemmParams q = pp;
+    q.prof = d;
+    const int r = launch_igemm_tc2(q, maps, block_n, num_sms, stream);
+    cudaDeviceSynchronize();
+    std::vector<long long> h(16 * num_sms);
+    cudaMemcpy(h.data(), d, sizeof(long long) * 16 * num_sms, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    double s[16] = {0};
+    int n = 0;
+    for (int c = 0; c < num_sms; c += 2) {
+      if (h[c * 16 + 9] == 0) continue;
+      for (int k = 0; k < 16; ++k) s[k] += static_cast<double>(h[c * 16 + k]);
+      ++n;
+    }
+    for (int k = 0; k < 16; ++k) s[k] /= (n > 0 ? n : 1);
+    fprintf(stderr,
+            "[igemm prof mode=%d M=%d N=%d K=%d bn=%d epi=%d] tiles/cta %.1f | producer wait_empty %.0f total %.0f | mma "
+            "wait_tmem_empty %.0f wait_full %.0f total %.0f | epi cst %.0f wait_full %.0f blocks %.0f total %.0f (cycles)\n",
+            p.mode, p.M, p.N, p.K, block_n, pick_epi(pp), s[9], s[0], s[1], s[2], s[3], s[4], s[6], s[5], s[7], s[8]);
+    return r;
+  }
   switch (block_n) {
     case 256: return launch_n<256>(pp, maps, a, n_tiles_n, b, num_sms, stream);
     case 128: return launch_n<128>(pp, maps, a, n_tiles_n, b, num_sms, stream);

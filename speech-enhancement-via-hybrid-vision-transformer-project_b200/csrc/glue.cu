@@ -119,6 +119,8 @@ __device__ __forceinline__ void fft512_warp(float2* x, int lane) {
 
 // ------------------------------------------------------------------ peak |x| per clip (enhancer.py:72-79)
 __global__ void peak_kernel(const float* __restrict__ wave, int n, unsigned* __restrict__ max_bits) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int b = blockIdx.y;
   const float* w = wave + static_cast<long long>(b) * n;
   float m = 0.f;
@@ -127,6 +129,8 @@ __global__ void peak_kernel(const float* __restrict__ wave, int n, unsigned* __r
   if ((threadIdx.x & 31) == 0) atomicMax(max_bits + b, __float_as_uint(m));
 }
 __global__ void fill_u32_kernel(unsigned* p, int n, unsigned v) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
@@ -136,6 +140,8 @@ __global__ void __launch_bounds__(FR * 32, 5) stft_kernel(const float* __restric
                                                        const unsigned* __restrict__ max_bits,
                                                        float2* __restrict__ spec, float* __restrict__ mag,
                                                        unsigned* __restrict__ mag_max_bits) {
+  griddep_launch_dependents();
+  griddep_wait();
   extern __shared__ float2 sm[];
   float2* xs = sm;                // [FR][XS]
   const int b = blockIdx.y, t0 = blockIdx.x * FR;
@@ -198,6 +204,8 @@ __global__ void __launch_bounds__(FR * 32, 5) istft_frames_kernel(float* __restr
                                                                const float2* __restrict__ spec,
                                                                const unsigned* __restrict__ mag_max_bits, int T,
                                                                float* __restrict__ frames) {
+  griddep_launch_dependents();
+  griddep_wait();
   extern __shared__ float2 sm[];
   float2* xs = sm;
   const int b = blockIdx.y, t0 = blockIdx.x * FR;
@@ -242,6 +250,8 @@ __global__ void __launch_bounds__(FR * 32, 5) istft_frames_kernel(float* __restr
 // iSTFT part 2: overlap-add, trim n_fft/2, divide by the window sum-square envelope, de-normalise.
 __global__ void istft_ola_kernel(const float* __restrict__ frames, const unsigned* __restrict__ max_bits, int n, int T,
                                  float* __restrict__ wave_out) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int b = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -299,6 +309,8 @@ template <typename T, int POOL>
 __global__ void stem_kernel(const float* __restrict__ x, const unsigned* __restrict__ mag_max_bits,
                             const float* __restrict__ w9c, const float* __restrict__ scale,
                             const float* __restrict__ shift, T* __restrict__ out, int H, int W, int C, int Ho, int Wo) {
+  griddep_launch_dependents();
+  griddep_wait();
   constexpr int WIN = POOL + 2;
   constexpr int TW = 32 * POOL + 2;
   extern __shared__ float sf[];
@@ -412,6 +424,8 @@ __device__ __forceinline__ void st4<__half>(__half* p, const float* v) {
 template <typename T, int V>
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ bb,
                                  T* __restrict__ out, int rows, int D, float eps) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -472,6 +486,8 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
 template <typename T>
 __global__ void skip_sample_kernel(const T* __restrict__ src, int Hs, int HsPitch, int Ws, int C, int Hd, int Wd,
                                    T* __restrict__ dst, long long total) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int cv = C / 4;
@@ -532,6 +548,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) head_kernel(const T* __restrict__ x, const float* __restrict__ w9c, int B, int H,
                                                    int W, int C, float* __restrict__ logits,
                                                    float* __restrict__ out_tanh) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int lane8 = threadIdx.x & 7;
   const long long npix = static_cast<long long>(B) * H * W;
   const long long stride = static_cast<long long>(gridDim.x) * 32;  // pixels per grid sweep (32 per block)
@@ -569,6 +587,8 @@ __global__ void __launch_bounds__(256) head_kernel(const T* __restrict__ x, cons
 // ------------------------------------------------------------------ final bilinear resize [B,Hs,Ws] -> [B,Hd,Wd]
 __global__ void resize_kernel(const float* __restrict__ src, int Hs, int Ws, float* __restrict__ dst, int Hd, int Wd,
                               long long total) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int wd = static_cast<int>(idx % Wd);
@@ -613,13 +633,13 @@ constexpr int FFT_SMEM = FR * XS * sizeof(float2);
 int launch_peak(const float* wave, int B, int n, float* max_val, int normalize, cudaStream_t s) {
   unsigned* bits = reinterpret_cast<unsigned*>(max_val);
   if (!normalize) {
-    fill_u32_kernel<<<(B + 255) / 256, 256, 0, s>>>(bits, B, 0x3F800000u);  // 1.0f
+    launch_pdl(fill_u32_kernel, dim3((B + 255) / 256), dim3(256), 0, s, bits, B, 0x3F800000u);  // 1.0f
     return check_launch("fill(max_val)");
   }
-  fill_u32_kernel<<<(B + 255) / 256, 256, 0, s>>>(bits, B, 0u);
+  launch_pdl(fill_u32_kernel, dim3((B + 255) / 256), dim3(256), 0, s, bits, B, 0u);
   if (n > 0) {
     dim3 grid(8, B);
-    peak_kernel<<<grid, 256, 0, s>>>(wave, n, bits);
+    launch_pdl(peak_kernel, dim3(grid), dim3(256), 0, s, wave, n, bits);
   }
   return check_launch("peak");
 }
@@ -639,9 +659,9 @@ int ensure_fft_tables(cudaStream_t s) {
 
 int launch_stft(const float* wave, int B, int n, int T, const float* max_val, float2* spec, float* mag,
                 unsigned* mag_max_bits, cudaStream_t s) {
-  fill_u32_kernel<<<(B + 255) / 256, 256, 0, s>>>(mag_max_bits, B, 0u);
+  launch_pdl(fill_u32_kernel, dim3((B + 255) / 256), dim3(256), 0, s, mag_max_bits, B, 0u);
   dim3 grid((T + FR - 1) / FR, B);
-  stft_kernel<<<grid, FR * 32, FFT_SMEM, s>>>(wave, n, T, reinterpret_cast<const unsigned*>(max_val), spec, mag,
+  launch_pdl(stft_kernel, dim3(grid), dim3(FR * 32), FFT_SMEM, s, wave, n, T, reinterpret_cast<const unsigned*>(max_val), spec, mag,
                                                mag_max_bits);
   return check_launch("stft");
 }
@@ -652,14 +672,14 @@ int launch_istft_frames(float* model_out, const float* lowres, int Hs, int Ws, c
                         const unsigned* mag_max_bits, float* frames, int B, int T, cudaStream_t s) {
   fft_smem_config();
   dim3 grid((T + FR - 1) / FR, B);
-  istft_frames_kernel<<<grid, FR * 32, FFT_SMEM, s>>>(model_out, lowres, Hs, Ws, spec, mag_max_bits, T, frames);
+  launch_pdl(istft_frames_kernel, dim3(grid), dim3(FR * 32), FFT_SMEM, s, model_out, lowres, Hs, Ws, spec, mag_max_bits, T, frames);
   return check_launch("istft_frames");
 }
 
 int launch_istft_ola(const float* frames, const float* max_val, float* wave_out, int B, int n, int T, cudaStream_t s) {
   if (n <= 0) return 0;
   dim3 g2((n + 255) / 256, B);
-  istft_ola_kernel<<<g2, 256, 0, s>>>(frames, reinterpret_cast<const unsigned*>(max_val), n, T, wave_out);
+  launch_pdl(istft_ola_kernel, dim3(g2), dim3(256), 0, s, frames, reinterpret_cast<const unsigned*>(max_val), n, T, wave_out);
   return check_launch("istft_ola");
 }
 
@@ -668,9 +688,9 @@ static void stem_dispatch(const float* x, const unsigned* mm, const float* w, co
                           void* out, int H, int W, int C, int pool, dim3 grid, dim3 block, int smem, cudaStream_t s) {
   const int Ho = H / pool, Wo = W / pool;
   if (pool == 2)
-    stem_kernel<T, 2><<<grid, block, smem, s>>>(x, mm, w, scale, shift, reinterpret_cast<T*>(out), H, W, C, Ho, Wo);
+    launch_pdl(stem_kernel<T, 2>, dim3(grid), dim3(block), smem, s, x, mm, w, scale, shift, reinterpret_cast<T*>(out), H, W, C, Ho, Wo);
   else
-    stem_kernel<T, 1><<<grid, block, smem, s>>>(x, mm, w, scale, shift, reinterpret_cast<T*>(out), H, W, C, Ho, Wo);
+    launch_pdl(stem_kernel<T, 1>, dim3(grid), dim3(block), smem, s, x, mm, w, scale, shift, reinterpret_cast<T*>(out), H, W, C, Ho, Wo);
 }
 
 int launch_stem(const float* x, const unsigned* mag_max_bits, const float* w, const float* scale, const float* shift,
@@ -693,12 +713,12 @@ static void ln_dispatch(const float* x, const float* g, const float* b, void* ou
                         cudaStream_t s) {
   const int grid = (rows + 7) / 8;
   T* o = reinterpret_cast<T*>(out);
-  if (D == 512) layernorm_kernel<T, 4><<<grid, 256, 0, s>>>(x, g, b, o, rows, D, eps);
-  else if (D == 768) layernorm_kernel<T, 6><<<grid, 256, 0, s>>>(x, g, b, o, rows, D, eps);
-  else if (D == 1024) layernorm_kernel<T, 8><<<grid, 256, 0, s>>>(x, g, b, o, rows, D, eps);
-  else if (D == 256) layernorm_kernel<T, 2><<<grid, 256, 0, s>>>(x, g, b, o, rows, D, eps);
-  else if (D == 128) layernorm_kernel<T, 1><<<grid, 256, 0, s>>>(x, g, b, o, rows, D, eps);
-  else layernorm_kernel<T, 0><<<grid, 256, 0, s>>>(x, g, b, o, rows, D, eps);
+  if (D == 512) launch_pdl(layernorm_kernel<T, 4>, dim3(grid), dim3(256), 0, s, x, g, b, o, rows, D, eps);
+  else if (D == 768) launch_pdl(layernorm_kernel<T, 6>, dim3(grid), dim3(256), 0, s, x, g, b, o, rows, D, eps);
+  else if (D == 1024) launch_pdl(layernorm_kernel<T, 8>, dim3(grid), dim3(256), 0, s, x, g, b, o, rows, D, eps);
+  else if (D == 256) launch_pdl(layernorm_kernel<T, 2>, dim3(grid), dim3(256), 0, s, x, g, b, o, rows, D, eps);
+  else if (D == 128) launch_pdl(layernorm_kernel<T, 1>, dim3(grid), dim3(256), 0, s, x, g, b, o, rows, D, eps);
+  else launch_pdl(layernorm_kernel<T, 0>, dim3(grid), dim3(256), 0, s, x, g, b, o, rows, D, eps);
 }
 
 int launch_layernorm(const float* x, const float* g, const float* b, void* out, int dt, int rows, int D,
@@ -718,13 +738,13 @@ int launch_skip_sample(const void* src, int dt, int B, int Hs, int HsPitch, int 
   const long long total = static_cast<long long>(B) * Hd * Wd * (C / 4);
   const unsigned grid = static_cast<unsigned>((total + 255) / 256);
   if (dt == DT_BF16)
-    skip_sample_kernel<bf16><<<grid, 256, 0, s>>>(reinterpret_cast<const bf16*>(src), Hs, HsPitch, Ws, C, Hd, Wd,
+    launch_pdl(skip_sample_kernel<bf16>, dim3(grid), dim3(256), 0, s, reinterpret_cast<const bf16*>(src), Hs, HsPitch, Ws, C, Hd, Wd,
                                                   reinterpret_cast<bf16*>(dst), total);
   else if (dt == DT_F16)
-    skip_sample_kernel<__half><<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(src), Hs, HsPitch, Ws, C, Hd, Wd,
+    launch_pdl(skip_sample_kernel<__half>, dim3(grid), dim3(256), 0, s, reinterpret_cast<const __half*>(src), Hs, HsPitch, Ws, C, Hd, Wd,
                                                     reinterpret_cast<__half*>(dst), total);
   else
-    skip_sample_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(src), Hs, HsPitch, Ws, C, Hd, Wd,
+    launch_pdl(skip_sample_kernel<float>, dim3(grid), dim3(256), 0, s, reinterpret_cast<const float*>(src), Hs, HsPitch, Ws, C, Hd, Wd,
                                                    reinterpret_cast<float*>(dst), total);
   return check_launch("skip_sample");
 }
@@ -740,17 +760,17 @@ int launch_head(const void* x, int dt, const float* w, int B, int H, int W, int 
   if (blocks > 148 * 64) blocks = 148 * 64;
   const unsigned grid = static_cast<unsigned>(blocks);
   if (dt == DT_BF16)
-    head_kernel<bf16><<<grid, 256, 0, s>>>(reinterpret_cast<const bf16*>(x), w, B, H, W, C, logits, out_tanh);
+    launch_pdl(head_kernel<bf16>, dim3(grid), dim3(256), 0, s, reinterpret_cast<const bf16*>(x), w, B, H, W, C, logits, out_tanh);
   else if (dt == DT_F16)
-    head_kernel<__half><<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(x), w, B, H, W, C, logits, out_tanh);
+    launch_pdl(head_kernel<__half>, dim3(grid), dim3(256), 0, s, reinterpret_cast<const __half*>(x), w, B, H, W, C, logits, out_tanh);
   else
-    head_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(x), w, B, H, W, C, logits, out_tanh);
+    launch_pdl(head_kernel<float>, dim3(grid), dim3(256), 0, s, reinterpret_cast<const float*>(x), w, B, H, W, C, logits, out_tanh);
   return check_launch("head");
 }
 
 int launch_resize(const float* src, int B, int Hs, int Ws, float* dst, int Hd, int Wd, cudaStream_t s) {
   const long long total = static_cast<long long>(B) * Hd * Wd;
-  resize_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(src, Hs, Ws, dst, Hd, Wd, total);
+  launch_pdl(resize_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, src, Hs, Ws, dst, Hd, Wd, total);
   return check_launch("resize");
 }
 

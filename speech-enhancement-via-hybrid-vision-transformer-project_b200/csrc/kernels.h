@@ -109,6 +109,24 @@ int launch_head(const void* x, int dt, const float* w /*[9][C]*/, int B, int H, 
 int launch_resize(const float* src, int B, int Hs, int Ws, float* dst, int Hd, int Wd, cudaStream_t s);
 int launch_maxpool2(const float* src, float* dst, int B, int H, int W, int C, cudaStream_t s);
 
+// Kernel launch with programmatic stream serialization (PDL); HVIT_NO_PDL=1 falls back to plain stream order.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // error plumbing (api.cu)
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);

@@ -148,6 +148,8 @@ stem_tc_kernel(const float* __restrict__ x, const unsigned* __restrict__ mag_max
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  griddep_launch_dependents();
+  griddep_wait();  // PDL: everything above overlapped the previous kernel's tail
   // weights -> shared memory in the 128B-swizzled K-major layout (row pitch 128 B, 16-byte chunk c of row r at c ^ (r & 7))
   for (int i = threadIdx.x; i < 4 * 128 * 8; i += ST_THREADS) {
     const int chunk = i & 7, row = (i >> 3) & 127, pos = i >> 10;
@@ -381,11 +383,11 @@ int launch_stem_tc(const float* x, const unsigned* mag_max_bits, const void* apa
   const int grid = nt < num_sms ? static_cast<int>(nt) : num_sms;
   const uint16_t* ap = reinterpret_cast<const uint16_t*>(apack);
   if (f16)
-    stem_tc_kernel<true><<<grid, ST_THREADS, ST_SMEM, s>>>(x, mag_max_bits, ap, shift, tmap_out, H, W, Ho, Wo, tiles_w,
-                                                           row_pairs, static_cast<int>(nt), prof);
+    launch_pdl(stem_tc_kernel<true>, dim3(grid), dim3(ST_THREADS), ST_SMEM, s, x, mag_max_bits, ap, shift, tmap_out, H, W,
+               Ho, Wo, tiles_w, row_pairs, static_cast<int>(nt), prof);
   else
-    stem_tc_kernel<false><<<grid, ST_THREADS, ST_SMEM, s>>>(x, mag_max_bits, ap, shift, tmap_out, H, W, Ho, Wo, tiles_w,
-                                                            row_pairs, static_cast<int>(nt), prof);
+    launch_pdl(stem_tc_kernel<false>, dim3(grid), dim3(ST_THREADS), ST_SMEM, s, x, mag_max_bits, ap, shift, tmap_out, H, W,
+               Ho, Wo, tiles_w, row_pairs, static_cast<int>(nt), prof);
   if (prof != nullptr) {
     cudaDeviceSynchronize();
     long long h[16 * 256];

@@ -42,6 +42,7 @@ class AudioEnhancer:
         self.sample_rate = sample_rate
         self.n_fft, self.hop_length, self.win_length, self.window = n_fft, hop_length, win_length, window
         self._pinned = {}
+        self._pipes = {}
 
     # ------------------------------------------------------------------ helpers
     def _staging(self, B: int, n: int):
@@ -74,19 +75,66 @@ class AudioEnhancer:
                                              _lib.current_stream_ptr()), "hvit_enhance")
         return out
 
+    def _pipeline(self, B: int, n: int):
+        """Two-slot copy/compute pipeline for the host-to-host path: device staging buffers, one H2D and one D2H
+        stream and the events that order them against the compute (current) stream."""
+        key = (B, n)
+        pipe = self._pipes.get(key)
+        if pipe is None:
+            if len(self._pipes) >= 4:
+                self._pipes.pop(next(iter(self._pipes)))
+            with torch.cuda.device(self._dev):
+                pipe = dict(
+                    slot=0,
+                    d_in=[torch.empty((B, n), dtype=torch.float32, device=self._dev) for _ in range(2)],
+                    d_out=[torch.empty((B, n), dtype=torch.float32, device=self._dev) for _ in range(2)],
+                    s_in=torch.cuda.Stream(device=self._dev), s_out=torch.cuda.Stream(device=self._dev),
+                    ev_in=[torch.cuda.Event() for _ in range(2)],      # H2D of the slot landed
+                    ev_comp=[torch.cuda.Event() for _ in range(2)],    # enhance of the slot finished
+                    ev_out=[torch.cuda.Event() for _ in range(2)])     # D2H of the slot finished
+            self._pipes[key] = pipe
+        return pipe
+
     def enhance_pinned(self, pinned_in: torch.Tensor, pinned_out: torch.Tensor, normalize: bool = True,
                        synchronize: bool = True) -> torch.Tensor:
-        """Host-to-host batch API on caller-owned pinned buffers [B, n] fp32: async H2D, enhance, async D2H on the
-        current stream (what ``enhance_batch`` does after staging the numpy input)."""
+        """Host-to-host batch API on caller-owned pinned buffers [B, n] fp32 (what ``enhance_batch`` does after
+        staging the numpy input).  The H2D copy, the kernels and the D2H copy run on three streams over two device
+        slots, so consecutive calls overlap: copy-in of batch i+1 and copy-out of batch i-1 hide behind the compute
+        of batch i.  With ``synchronize=False`` the call only enqueues; call :meth:`join` (or pass
+        ``synchronize=True`` on the last batch) before reading ``pinned_out``."""
         B, n = pinned_in.shape
-        _, _, d_in, d_out = self._staging(B, n)
+        pipe = self._pipeline(B, n)
+        k = pipe["slot"]
+        pipe["slot"] = k ^ 1
         with torch.cuda.device(self._dev):
-            d_in.copy_(pinned_in, non_blocking=True)
-            self.enhance_device(d_in, normalize=normalize, out=d_out)
-            pinned_out.copy_(d_out, non_blocking=True)
+            cur = torch.cuda.current_stream()
+            s_in, s_out = pipe["s_in"], pipe["s_out"]
+            s_in.wait_event(pipe["ev_comp"][k])          # the kernels that last read this input slot are done
+            with torch.cuda.stream(s_in):
+                pipe["d_in"][k].copy_(pinned_in, non_blocking=True)
+                pipe["ev_in"][k].record(s_in)
+            cur.wait_event(pipe["ev_in"][k])
+            cur.wait_event(pipe["ev_out"][k])            # the D2H that last read this output slot is done
+            self.enhance_device(pipe["d_in"][k], normalize=normalize, out=pipe["d_out"][k])
+            pipe["ev_comp"][k].record(cur)
+            s_out.wait_event(pipe["ev_comp"][k])
+            with torch.cuda.stream(s_out):
+                pinned_out.copy_(pipe["d_out"][k], non_blocking=True)
+                pipe["ev_out"][k].record(s_out)
             if synchronize:
-                torch.cuda.current_stream().synchronize()
+                pipe["ev_out"][k].synchronize()
         return pinned_out
+
+    def join(self, block: bool = False) -> None:
+        """Order the current stream after every outstanding D2H copy of :meth:`enhance_pinned`
+        (``block=True`` additionally waits on the host)."""
+        with torch.cuda.device(self._dev):
+            cur = torch.cuda.current_stream()
+            for pipe in self._pipes.values():
+                for ev in pipe["ev_out"]:
+                    cur.wait_event(ev)
+                    if block:
+                        ev.synchronize()
 
     @torch.no_grad()
     def enhance_batch(self, noisy_audio: Union[np.ndarray, Sequence[np.ndarray]], normalize: bool = True) -> np.ndarray:
