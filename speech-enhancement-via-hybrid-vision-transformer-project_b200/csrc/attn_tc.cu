@@ -42,6 +42,21 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + r, |r| <= 0.5, degree-4 minimax 2^r (relative
+// error 3.4e-6 - far below the 16-bit rounding of P), exponent added as an integer.  x is clamped at -127, where
+// the result is exactly 0 (bits 0x3F800000 - 127 * 2^23), like ex2.approx.ftz below its normal range; results for
+// x in (-127, -126) are (harmless) fp32 subnormal bit patterns.  Returns the fp32 BIT PATTERN.
+__device__ __forceinline__ uint32_t exp2_poly_bits(float x) {
+  const float xf = fmaxf(x, -127.0f);
+  const float t = xf + 12582912.0f;  // 1.5 * 2^23: the integer n = rint(xf) lands in the low mantissa bits
+  const float r = xf - (t - 12582912.0f);
+  float p = 0.009570018388330936f;
+  p = fmaf(p, r, 0.05591766536235809f);
+  p = fmaf(p, r, 0.240247443318367f);
+  p = fmaf(p, r, 0.6931218504905701f);
+  p = fmaf(p, r, 1.0f);
+  return __float_as_uint(p) + (__float_as_uint(t) << 23);
+}
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -74,21 +89,37 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
 //   16-bit float = upper half of (bits(e) * mul + 0x8000)      mul = 8 (fp16: 23 -> 10 mantissa bits), 1 (bf16)
 // (round-half-up), and two results are merged with one PRMT.  The row sum uses the same (2^-112-scaled) values; the
 // scale is undone in the final 1/l normalisation.
-__device__ __forceinline__ float exp_pack_row(const uint32_t (&s)[128], float scale_log2, float nbias, uint32_t mul,
+__device__ __forceinline__ float exp_pack_row(uint32_t (&s)[128], float scale_log2, float nbias, uint32_t mul,
                                               uint8_t* p_row, int sw) {
   const float2 sc2 = make_float2(scale_log2, scale_log2);
   const float2 nm2 = make_float2(-nbias, -nbias);
   float2 sum0 = make_float2(0.f, 0.f), sum1 = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int c = 0; c < 16; ++c) {  // 16-byte chunk c = keys 8c .. 8c+7
-    float2 t[4];
-    uint32_t pk[4];
+  // Software pipeline with a lag of LAG chunks between the MUFU stage and the convert / sum / store stage: each
+  // softmax group has ONE warp per scheduler, so a MUFU result consumed right after its issue would stall the warp
+  // for the MUFU latency (measured: 16 cycles per score instead of the unit's 8).
+  constexpr int LAG = 3;
+  auto exp_chunk = [&](int c) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      t[i] = __ffma2_rn(make_float2(__uint_as_float(s[8 * c + 2 * i]), __uint_as_float(s[8 * c + 2 * i + 1])), sc2, nm2);
-      t[i].x = ex2_approx(t[i].x);
-      t[i].y = ex2_approx(t[i].y);
-      pk[i] = __byte_perm(__float_as_uint(t[i].x) * mul + 0x8000u, __float_as_uint(t[i].y) * mul + 0x8000u, 0x7632);
+      const float2 t = __ffma2_rn(make_float2(__uint_as_float(s[8 * c + 2 * i]), __uint_as_float(s[8 * c + 2 * i + 1])),
+                                  sc2, nm2);
+      s[8 * c + 2 * i] = __float_as_uint(ex2_approx(t.x));
+      // (measured: moving half of the exponentials to exp2_poly_bits makes this phase 30 % SLOWER - the phase is
+      // bound by instruction issue of the single warp per scheduler, not by the MUFU unit)
+      s[8 * c + 2 * i + 1] = __float_as_uint(ex2_approx(t.y));
+    }
+  };
+#pragma unroll
+  for (int c = 0; c < LAG; ++c) exp_chunk(c);
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {  // 16-byte chunk c = keys 8c .. 8c+7
+    if (c + LAG < 16) exp_chunk(c + LAG);
+    uint32_t pk[4];
+    float2 t[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      t[i] = make_float2(__uint_as_float(s[8 * c + 2 * i]), __uint_as_float(s[8 * c + 2 * i + 1]));
+      pk[i] = __byte_perm(s[8 * c + 2 * i] * mul + 0x8000u, s[8 * c + 2 * i + 1] * mul + 0x8000u, 0x7632);
     }
     sum0 = __fadd2_rn(sum0, __fadd2_rn(t[0], t[1]));
     sum1 = __fadd2_rn(sum1, __fadd2_rn(t[2], t[3]));
@@ -275,7 +306,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       int b, h, q0;
       decode(item, b, h, q0);
-      if (w == 1 && !(q0 + 128 < N)) continue;  // this pair has no second query tile
+      const bool hasB = q0 + 128 < N;
+      if (w == 1 && !hasB) continue;  // this pair has no second query tile
       float m_used = -INFINITY, l_run = 0.f;
       for (int j = 0; j < nkv; ++j, ++blk) {
         const int nvalid = min(128, N - j * 128);
