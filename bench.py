@@ -54,12 +54,26 @@ def peaks():
     return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback")
 
 
+def ncu_traffic(args, family):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel family, from the committed
+    `ncu --set full` capture of this very workload (profiles/); None for any other workload."""
+    if args.widened or args.batch != 64 or args.seconds != 4.0 or args.precision != "fp16" or family != "igemm_tc":
+        return None
+    path = os.path.join(ROOT, "profiles", "r1m_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f)["dram_bytes_per_launch"]
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        self.window = [None, None]  # perf_counter() bounds of the timed region; only samples inside are reported
+        self.ready = threading.Event()
 
     def run(self):
         try:
@@ -74,19 +88,25 @@ class ClockSampler(threading.Thread):
                 getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
                 getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
             }
+            self.ready.set()
             while not self.stop_flag:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                t = time.perf_counter()
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, nm in names.items():
-                    if r & bit:
-                        self.reasons.add(nm)
-                time.sleep(0.02)
+                self.samples.append((t, mhz, frozenset(nm for bit, nm in names.items() if r & bit)))
+                time.sleep(0.002)
         except Exception as e:  # pragma: no cover
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+            self.ready.set()
 
     def summary(self):
-        return dict(sm_mhz=statistics.median(self.samples) if self.samples else None, sm_max_mhz=self.max_mhz,
-                    samples=len(self.samples), reasons=sorted(self.reasons))
+        lo, hi = self.window
+        inside = [x for x in self.samples if (lo is None or x[0] >= lo) and (hi is None or x[0] <= hi)]
+        reasons = set(self.reasons)
+        for x in inside:
+            reasons |= set(x[2])
+        return dict(sm_mhz=statistics.median(x[1] for x in inside) if inside else None, sm_max_mhz=self.max_mhz,
+                    samples=len(inside), reasons=sorted(reasons))
 
 
 def model_cfg(args):
@@ -186,9 +206,11 @@ def run_ours(args):
     # ---- device-resident leg (value)
     for _ in range(args.warmup):
         enh.enhance_device(d_in, out=d_out)
-    barrier()
     sampler = ClockSampler(local)
     sampler.start()
+    sampler.ready.wait(timeout=10)
+    barrier()
+    sampler.window[0] = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
@@ -209,6 +231,7 @@ def run_ours(args):
     ev3.record()
     barrier()
     e2e_wall = time.perf_counter() - t_wall
+    sampler.window[1] = time.perf_counter()
     e2e_ms = max_over_ranks(max(ev2.elapsed_time(ev3), 0.0))
     sampler.stop_flag = True
     sampler.join(timeout=2)
@@ -244,7 +267,10 @@ def run_ours(args):
         if t["algo_flops"] > 0:
             ach = t["algo_flops"] / (t["ms"] / 1e3) / 1e12
             roofline = dict(kernel=top, bound="tensor", achieved=ach, peak=pk["tflops_sustained"], unit="TFLOP/s",
-                            frac=ach / pk["tflops_sustained"], traffic=None, peak_source=pk["source"] + " (sustained bf16)",
+                            frac=ach / pk["tflops_sustained"], traffic=ncu_traffic(args, top),
+                            algo_flops_per_launch=t["algo_flops"] / t["launches"],
+                            avg_launch_ms=t["ms"] / t["launches"],
+                            peak_source=pk["source"] + " (sustained bf16)",
                             executed=t["exec_flops"] / (t["ms"] / 1e3) / 1e12, share_of_step=t["ms"] / total_ms,
                             launches_per_step=t["launches"], ms_per_step=t["ms"])
         else:
