@@ -192,7 +192,7 @@ static int make_out_maps(const IgemmParams& q, IgemmMaps* mp) {
   } else if (q.mode == IG_CONV3) {
     const uint64_t img = static_cast<uint64_t>(q.HoPitch) * q.Wo * ld;
     if (q.pool)
-      r = tmap_out4(&mp->out[0], out, f32, N, q.Wo, q.Ho, q.B, ld, ld * q.Wo, img, 8, 4);
+      r = tmap_out4(&mp->out[0], out, f32, N, q.Wo, q.Ho, q.B, ld, ld * q.Wo, img, q.Wt / 2, q.Ht / 2);
     else
       r = tmap_out4(&mp->out[0], out, f32, N, q.W, q.H, q.B, ld, ld * q.Wo, img, q.Wt, q.Ht);
   } else if (q.mode == IG_UP2) {
@@ -518,7 +518,13 @@ static int add_conv(hvit_plan* p, const std::string& name, const void* in, int B
     q.Ho = pool ? H / 2 : Hfull;
     q.Wo = pool ? W / 2 : Wfull;
     q.HoPitch = HoPitch;
-    if (pool) {
+    // 3x3 convs keep the input tile + halo in shared memory (igemm_halo_kernel); HVIT_NO_HALO=1 selects the
+    // tap-shifted TMA boxes of igemm_tc2_kernel instead (A/B comparison)
+    static const bool no_halo = getenv("HVIT_NO_HALO") != nullptr && getenv("HVIT_NO_HALO")[0] == '1';
+    q.halo = (!up2 && use_2cta() && !no_halo && Cin % 64 == 0 && Cout <= 2048) ? 1 : 0;
+    if (q.halo) {
+      q.Wt = 8; q.Ht = 16;
+    } else if (pool) {
       q.Wt = 16; q.Ht = 8;
     } else {
       pick_tile(H, W, &q.Wt, &q.Ht);
@@ -527,7 +533,17 @@ static int add_conv(hvit_plan* p, const std::string& name, const void* in, int B
     q.tiles_h = (H + q.Ht - 1) / q.Ht;
     IgemmMaps mp;
     const int bn = pick_block_n(Cout);
-    int r = tmap_image(&mp.a, in, B, H, H, W, Cin, q.Wt, q.Ht);
+    int r;
+    if (q.halo) {  // (8 channels, W, H, Cin / 8, B): one un-swizzled box = tile + halo of 64 channels as 8 chunk planes
+      const uint64_t dims[5] = {8, static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(Cin / 8),
+                                static_cast<uint64_t>(B)};
+      const uint64_t strides[4] = {static_cast<uint64_t>(Cin) * 2, static_cast<uint64_t>(W) * Cin * 2, 16,
+                                   static_cast<uint64_t>(H) * W * Cin * 2};
+      const uint32_t box[5] = {8, 10, 18, 8, 1};
+      r = make_tmap(&mp.a, in, 5, dims, strides, box, 0, 1);
+    } else {
+      r = tmap_image(&mp.a, in, B, H, H, W, Cin, q.Wt, q.Ht);
+    }
     if (r) return r;
     r = tmap_matrix(&mp.b, Wt, static_cast<long long>(up2 ? 4 : 1) * Cout, q.K, q.K, b_box_rows(bn));
     if (r) return r;

@@ -127,7 +127,7 @@ __device__ __forceinline__ void tile_out_coords(const IgemmParams& p, const Tile
 template <int EPI, bool F16>
 __device__ __forceinline__ void emit16(const uint32_t (&cur)[32], const float* sc, const float* sh,
                                        const IgemmParams& p, float relu_lo, uint8_t* row, int half, int sw,
-                                       bool writer) {
+                                       bool writer, int hxor = 16) {
   float v[32];
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
@@ -164,7 +164,7 @@ __device__ __forceinline__ void emit16(const uint32_t (&cur)[32], const float* s
 #pragma unroll
     for (int e = 0; e < 32; ++e) {
       v[e] = fmaxf(v[e], __shfl_xor_sync(0xFFFFFFFFu, v[e], 1));
-      v[e] = fmaxf(v[e], __shfl_xor_sync(0xFFFFFFFFu, v[e], 16));
+      v[e] = fmaxf(v[e], __shfl_xor_sync(0xFFFFFFFFu, v[e], hxor));
     }
   }
   if (writer) {
@@ -548,6 +548,276 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
   if (warp == 2) tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// 3x3 convolution with the input tile + halo held in shared memory (IgemmParams::halo).
+//
+// The tap-shifted TMA boxes of igemm_tc2_kernel read every input pixel nine times out of L2; these reads are private
+// to an SM (no L2 request merging), which pins encoder.1 at the L2 -> SM throughput cap (measured 36 B/clk/SM,
+// 35 % tensor-pipe activity).  Here a CTA loads its 8 x 16 pixel tile plus a one-pixel halo ONCE per 64 input
+// channels - one 5-D TMA box (8 ch, 10, 18, 8 chunks) into the un-swizzled K-major "chunk plane" layout
+// [chunk][hh][ww][8 ch = 16 B] - and the nine taps are nine UMMA descriptors into that buffer: with 8-pixel-wide tiles
+// every 8-row core matrix is one contiguous 128-byte run (row h + dy, columns w + dx ..), consecutive core matrices
+// are a constant WW * 16 bytes apart (SBO) and the two 8-channel chunks of a K = 16 step a constant plane apart (LBO),
+// for any (dy, dx).  Weights still stream through a ring of 128B-swizzled half tiles (shared by all CTAs: these L2
+// reads merge).  Epilogue: 16-bit BN (+ReLU) (+2x2 pool) paths of the kernel above with the 8 x 16 tile's lane map.
+// ---------------------------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+struct CfgH {
+  static constexpr int WW = 10, HH = 18;                      // tile 8 x 16 + halo
+  static constexpr int PLANE = HH * WW * 16;                  // bytes per 8-channel chunk plane
+  static constexpr int HALO_BYTES = 8 * PLANE;                // 64 channels: 23040 B
+  static constexpr int A_STAGES = BLOCK_N == 256 ? 2 : 3;
+  static constexpr int B_HALF_ROWS = BLOCK_N / 2;
+  static constexpr int B_STAGE_BYTES = B_HALF_ROWS * BLOCK_K * 2;
+  static constexpr int B_STAGES = BLOCK_N == 256 ? 6 : 8;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+  static constexpr int STAGING_BYTES = 4 * STG_BUF_BYTES;
+  static constexpr int CONST_N = 2048;
+  static constexpr int CONST_BYTES = 2 * CONST_N * 4;
+  static constexpr int OFF_B = 0;
+  static constexpr int OFF_STG = OFF_B + B_STAGES * B_STAGE_BYTES;
+  static constexpr int OFF_A = OFF_STG + STAGING_BYTES;
+  static constexpr int OFF_CONST = OFF_A + A_STAGES * HALO_BYTES;
+  static constexpr int OFF_BAR = OFF_CONST + CONST_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+};
+
+// shared-memory matrix descriptor, no swizzle (layout_type 0), K-major: 8-row x 16-byte core matrices;
+// lbo = bytes between core matrices adjacent in K, sbo = bytes between core matrices adjacent in M
+__device__ __forceinline__ uint64_t make_smem_desc_nosw(uint32_t saddr, uint32_t sbo_bytes, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
+
+template <int BLOCK_N, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+igemm_halo_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, int num_ctiles, int n_tiles_n,
+                  int pairs_per_group) {
+  using C = CfgH<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + C::OFF_STG;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* a_full = bars;                          // [A_STAGES] (leader)
+  uint64_t* a_empty = a_full + C::A_STAGES;         // [A_STAGES]
+  uint64_t* b_full = a_empty + C::A_STAGES;         // [B_STAGES] (leader)
+  uint64_t* b_empty = b_full + C::B_STAGES;         // [B_STAGES]
+  uint64_t* tmem_full = b_empty + C::B_STAGES;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;             // [2] (leader)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = static_cast<int>(cluster_ctarank());
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int cblocks = p.Cin / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a);
+    tma_prefetch_desc(&maps.b);
+    tma_prefetch_desc(&maps.out[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::A_STAGES; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < C::B_STAGES; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 2 * NUM_EPI_WARPS);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();
+  griddep_wait();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (elect_one()) {
+      uint32_t ai = 0, bi = 0;  // halo tiles / weight tiles issued so far
+      for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
+        const TileCoord c = decode_ctile(p, ct, n_tiles_n, BLOCK_N, pairs_per_group, rank);
+        const int b_row = c.n0 + rank * C::B_HALF_ROWS;
+        for (int cb = 0; cb < cblocks; ++cb, ++ai) {
+          const int as = ai % C::A_STAGES;
+          mbar_wait(&a_empty[as], ((ai / C::A_STAGES) & 1) ^ 1);
+          if (rank == 0) mbar_expect_tx(&a_full[as], 2 * C::HALO_BYTES);
+          tma_load_5d_2sm(smem + C::OFF_A + as * C::HALO_BYTES, &maps.a, &a_full[as], 0, c.w0 - 1, c.h0 - 1, cb * 8, c.b);
+          for (int tap = 0; tap < 9; ++tap, ++bi) {
+            const int bs = bi % C::B_STAGES;
+            mbar_wait(&b_empty[bs], ((bi / C::B_STAGES) & 1) ^ 1);
+            if (rank == 0) mbar_expect_tx(&b_full[bs], 2 * C::B_STAGE_BYTES);
+            tma_load_2d_2sm(smem + C::OFF_B + bs * C::B_STAGE_BYTES, &maps.b, &b_full[bs], (tap * cblocks + cb) * BLOCK_K,
+                            b_row);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (one thread of the leader CTA)
+    if (rank == 0 && elect_one()) {
+      const uint32_t idesc = make_idesc_16(2 * BLOCK_M, BLOCK_N, 0, 0, p.f16);
+      uint32_t ai = 0, bi = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int cb = 0; cb < cblocks; ++cb, ++ai) {
+          const int as = ai % C::A_STAGES;
+          mbar_wait(&a_full[as], (ai / C::A_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + C::OFF_A + as * C::HALO_BYTES);
+          for (int tap = 0; tap < 9; ++tap, ++bi) {
+            const int bs = bi % C::B_STAGES;
+            mbar_wait(&b_full[bs], (bi / C::B_STAGES) & 1);
+            tc_fence_after();
+            const uint32_t b_addr = smem_u32(smem + C::OFF_B + bs * C::B_STAGE_BYTES);
+            const int dy = tap / 3, dx = tap % 3;  // already offset by the halo: (h + dy, w + dx) in halo coordinates
+            const uint32_t a_tap = a_addr + (dy * C::WW + dx) * 16;
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t adesc = make_smem_desc_nosw(a_tap + k * 2 * C::PLANE, C::WW * 16, C::PLANE);
+              const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * UMMA_K * 2, 1024, 16);
+              umma_16_2sm(d_tmem, adesc, bdesc, idesc, (cb | tap | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_2sm(&b_empty[bs], 3);
+          }
+          umma_commit_2sm(&a_empty[as], 3);
+        }
+        umma_commit_2sm(&tmem_full[acc], 3);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (16-bit output, BN / ReLU / pool)
+    const int ew = warp - 2;
+    const int sub = warp & 3;
+    const int grp = ew >> 2;
+    const int m = sub * 32 + lane;       // accumulator row: pixel (h = m >> 3, w = m & 7) of the 8 x 16 tile
+    const bool issuer = (ew & 3) == 0 && lane == 0;
+    constexpr bool pool = EPI == EPI_BNPOOL16;
+    constexpr int nblk = BLOCK_N / 64;
+    const int J = (nblk - grp + 1) / 2;
+    uint8_t* stg0 = staging + grp * 2 * STG_BUF_BYTES;
+    // pooled tile: 4 x 8 pixels, row = (h / 2) * 4 + w / 2; the lanes with even h and even w write
+    const bool writer = pool ? ((lane & 9) == 0) : true;
+    const int srow = pool ? ((sub * 2 + (lane >> 4)) * 4 + ((lane & 7) >> 1)) : m;
+    const int sw = srow & 7;
+    const float relu_lo = p.act == ACT_RELU ? 0.0f : -INFINITY;
+    float* cscale = reinterpret_cast<float*>(smem + C::OFF_CONST);
+    float* cshift = cscale + C::CONST_N;
+    for (int e = ew * 32 + lane; e < p.N; e += NUM_EPI_WARPS * 32) {
+      cscale[e] = p.scale != nullptr ? __ldg(p.scale + e) : 1.0f;
+      cshift[e] = p.shift != nullptr ? __ldg(p.shift + e) : 0.0f;
+    }
+    named_bar_sync(3, NUM_EPI_WARPS * 32);
+
+    uint32_t it = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
+      const TileCoord c = decode_ctile(p, ct, n_tiles_n, BLOCK_N, pairs_per_group, rank);
+      int o1, o2, o3;
+      tile_out_coords(p, c, pool, o1, o2, o3);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BLOCK_N;
+      uint32_t ra[32], rb[32];
+      if (J > 0) tmem_ld32(t_base + grp * 64, ra);
+      for (int j = 0; j < J; ++j) {
+        const int blk = 2 * j + grp;
+        uint8_t* buf = stg0 + (it & 1) * STG_BUF_BYTES;
+        uint8_t* row = buf + srow * 128;
+        const float* sc = cscale + c.n0 + blk * 64;
+        const float* sh = cshift + c.n0 + blk * 64;
+        tmem_ld_wait(ra);
+        tmem_ld32(t_base + blk * 64 + 32, rb);
+        if (p.f16) emit16<EPI, true>(ra, sc, sh, p, relu_lo, row, 0, sw, writer, 8);
+        else emit16<EPI, false>(ra, sc, sh, p, relu_lo, row, 0, sw, writer, 8);
+        tmem_ld_wait(rb);
+        if (j + 1 < J) tmem_ld32(t_base + (blk + 2) * 64, ra);
+        if (p.f16) emit16<EPI, true>(rb, sc + 32, sh + 32, p, relu_lo, row, 1, sw, writer, 8);
+        else emit16<EPI, false>(rb, sc + 32, sh + 32, p, relu_lo, row, 1, sw, writer, 8);
+        fence_proxy_async_smem();
+        if (issuer) tma_store_wait_read0();
+        named_bar_sync(1 + grp, 128);
+        if (issuer) {
+          tma_store_4d(&maps.out[0], buf, c.n0 + blk * 64, o1, o2, o3);
+          tma_store_commit();
+        }
+        ++it;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    if (issuer) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
+}
+
+template <int BLOCK_N, int EPI>
+int launch_halo_impl(const IgemmParams& p, const IgemmMaps& maps, int num_ctiles, int n_tiles_n, int pairs_per_group,
+                     int num_sms, cudaStream_t stream) {
+  using C = CfgH<BLOCK_N>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_halo_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("igemm_halo: cudaFuncSetAttribute(%d B smem) failed: %s", C::SMEM_BYTES, cudaGetErrorString(e));
+      return -4;
+    }
+    configured = true;
+  }
+  const int max_clusters = num_sms / 2;
+  const int clusters = num_ctiles < max_clusters ? num_ctiles : max_clusters;
+  cudaError_t le = launch_pdl(igemm_halo_kernel<BLOCK_N, EPI>, dim3(2 * clusters), dim3(NUM_THREADS), C::SMEM_BYTES,
+                              stream, maps, p, num_ctiles, n_tiles_n, pairs_per_group);
+  if (le == cudaSuccess) le = cudaGetLastError();
+  if (le != cudaSuccess) {
+    set_error("igemm_halo<%d,%d>: %s (dyn smem %d)", BLOCK_N, EPI, cudaGetErrorString(le), C::SMEM_BYTES);
+    return -4;
+  }
+  return 0;
+}
+
+template <int BLOCK_N>
+int launch_halo_n(const IgemmParams& p, const IgemmMaps& maps, int a, int n_tiles_n, int b, int num_sms,
+                  cudaStream_t stream) {
+  if (p.pool) return launch_halo_impl<BLOCK_N, EPI_BNPOOL16>(p, maps, a, n_tiles_n, b, num_sms, stream);
+  return launch_halo_impl<BLOCK_N, EPI_BN16>(p, maps, a, n_tiles_n, b, num_sms, stream);
+}
+
 template <int BLOCK_N, int EPI>
 int launch_impl2(const IgemmParams& p, const IgemmMaps& maps, int num_ctiles, int n_tiles_n, int pairs_per_group,
                  int num_sms, cudaStream_t stream) {
@@ -610,7 +880,12 @@ int launch_igemm_tc2(const IgemmParams& p, const IgemmMaps& maps, int block_n, i
     set_error("igemm_tc2: unsupported shape N=%d K=%d Cin=%d block_n=%d", p.N, p.K, p.Cin, block_n);
     return -1;
   }
-  if (p.pool && !(p.mode == IG_CONV3 && p.Wt == 16 && p.Ht == 8)) {
+  if (p.halo && !(p.mode == IG_CONV3 && p.Wt == 8 && p.Ht == 16 && !p.out_f32 && p.residual == nullptr &&
+                  p.act != ACT_GELU && p.N <= 2048)) {
+    set_error("igemm_tc2: the halo convolution path needs a 16-bit 3x3 conv with an 8x16 tile");
+    return -1;
+  }
+  if (p.pool && !p.halo && !(p.mode == IG_CONV3 && p.Wt == 16 && p.Ht == 8)) {
     set_error("igemm_tc2: fused pool needs a 16x8 spatial tile");
     return -1;
   }
@@ -662,6 +937,14 @@ int launch_igemm_tc2(const IgemmParams& p, const IgemmMaps& maps, int block_n, i
             "wait_tmem_empty %.0f wait_full %.0f total %.0f | epi cst %.0f wait_full %.0f blocks %.0f total %.0f (cycles)\n",
             p.mode, p.M, p.N, p.K, block_n, pick_epi(pp), s[9], s[0], s[1], s[2], s[3], s[4], s[6], s[5], s[7], s[8]);
     return r;
+  }
+  if (pp.halo) {
+    switch (block_n) {
+      case 256: return launch_halo_n<256>(pp, maps, a, n_tiles_n, b, num_sms, stream);
+      case 128: return launch_halo_n<128>(pp, maps, a, n_tiles_n, b, num_sms, stream);
+      case 64: return launch_halo_n<64>(pp, maps, a, n_tiles_n, b, num_sms, stream);
+      default: set_error("igemm_tc2: block_n must be 64/128/256"); return -1;
+    }
   }
   switch (block_n) {
     case 256: return launch_n<256>(pp, maps, a, n_tiles_n, b, num_sms, stream);
