@@ -2,6 +2,8 @@
 // conv+BN+ReLU+pool, LayerNorm, bilinear skip sampling, 64->1 head conv + tanh, final bilinear resize and the
 // iSTFT (inverse FFT, window, overlap-add, window-sum-square normalisation).
 // Reference arithmetic: inference/enhancer.py:55-135, models/components.py:15-99,160-167, models/hybrid_vit.py:367-389,458-465.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -584,6 +586,79 @@ __global__ void __launch_bounds__(256) head_kernel(const T* __restrict__ x, cons
   }
 }
 
+// Row-streaming head for the 16-bit modes with C = 64: one block per (clip, strip of HEAD_STRIP output rows) slides a
+// window of input rows (contiguous W*C*2 bytes each in NHWC) through a 4-slot shared-memory ring filled by 16-byte
+// async copies - every input row is read once per strip, fully coalesced, and row h+2 streams in while row h is
+// computed.  8 lanes per output pixel (8 channels = one conflict-free 16-byte shared-memory load per tap) accumulate
+// in fp32 against register-resident weights.  (The per-pixel global-load kernel above was latency / L1 bound:
+// 116 us for 65 MB of input.)
+constexpr int HEAD_STRIP = 8;
+template <typename T>
+__global__ void __launch_bounds__(256) head_rows_kernel(const T* __restrict__ x, const float* __restrict__ w9c, int H, int W,
+                                                        float* __restrict__ logits, float* __restrict__ out_tanh) {
+  griddep_launch_dependents();
+  griddep_wait();
+  constexpr int C = 64;
+  extern __shared__ __align__(16) uint8_t hsm[];
+  const int h0 = blockIdx.x * HEAD_STRIP, b = blockIdx.y;
+  const int h1 = min(h0 + HEAD_STRIP, H);
+  const int row_bytes = W * C * 2;
+  // input row ih -> ring slot (ih + 1) & 3; rows outside the image are zero (conv padding)
+  auto load_row = [&](int ih) {
+    uint8_t* dst = hsm + ((ih + 1) & 3) * row_bytes;
+    if (ih >= 0 && ih < H) {
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(x + (static_cast<long long>(b) * H + ih) * W * C);
+      for (int o = threadIdx.x * 16; o < row_bytes; o += 256 * 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + o)), "l"(src + o) : "memory");
+    } else {
+      for (int o = threadIdx.x * 16; o < row_bytes; o += 256 * 16) *reinterpret_cast<uint4*>(dst + o) = make_uint4(0, 0, 0, 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  load_row(h0 - 1);
+  load_row(h0);
+  load_row(h0 + 1);
+  const int lane8 = threadIdx.x & 7;
+  float wr[9][8];  // this lane's 8 channels of the 9 taps
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(w9c + tap * C + lane8 * 8));
+    const float4 c = __ldg(reinterpret_cast<const float4*>(w9c + tap * C + lane8 * 8 + 4));
+    wr[tap][0] = a.x; wr[tap][1] = a.y; wr[tap][2] = a.z; wr[tap][3] = a.w;
+    wr[tap][4] = c.x; wr[tap][5] = c.y; wr[tap][6] = c.z; wr[tap][7] = c.w;
+  }
+  for (int h = h0; h < h1; ++h) {
+    load_row(h + 2);  // slot of row h-2, whose last readers passed the barrier at the end of the previous iteration
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // rows <= h+1 have landed (this thread's copies)
+    __syncthreads();                                       // ... and everybody else's
+    for (int w0 = threadIdx.x >> 3; w0 - (static_cast<int>(threadIdx.x) >> 3) < W; w0 += 32) {
+      const bool live = w0 < W;
+      float acc = 0.f;
+      if (live) {
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int ix = w0 + tap % 3 - 1;
+          if (ix < 0 || ix >= W) continue;
+          float v[8];
+          ld8<T>(reinterpret_cast<const T*>(hsm + ((h + tap / 3) & 3) * row_bytes) + ix * C + lane8 * 8, v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc = fmaf(v[e], wr[tap][e], acc);
+        }
+      }
+      acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
+      acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
+      acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 4);
+      if (live && lane8 == 0) {
+        const long long pix = (static_cast<long long>(b) * H + h) * W + w0;
+        if (logits != nullptr) logits[pix] = acc;
+        out_tanh[pix] = tanhf(acc);
+      }
+    }
+    __syncthreads();  // row h-1's slot may be overwritten by the next iteration's copy
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // ------------------------------------------------------------------ final bilinear resize [B,Hs,Ws] -> [B,Hd,Wd]
 __global__ void resize_kernel(const float* __restrict__ src, int Hs, int Ws, float* __restrict__ dst, int Hd, int Wd,
                               long long total) {
@@ -756,6 +831,22 @@ int launch_head(const void* x, int dt, const float* w, int B, int H, int W, int 
     return -1;
   }
   const long long npix = static_cast<long long>(B) * H * W;
+  const size_t rows_smem = static_cast<size_t>(4) * W * C * 2;
+  if (C == 64 && dt != DT_F32 && rows_smem <= 72 * 1024 && B <= 65535 && getenv("HVIT_HEAD_SIMPLE") == nullptr) {
+    static bool configured = false;
+    if (!configured) {
+      cudaFuncSetAttribute(head_rows_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+      cudaFuncSetAttribute(head_rows_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+      configured = true;
+    }
+    if (dt == DT_BF16)
+      launch_pdl(head_rows_kernel<bf16>, dim3((H + HEAD_STRIP - 1) / HEAD_STRIP, B), dim3(256), rows_smem, s, reinterpret_cast<const bf16*>(x), w, H, W,
+                 logits, out_tanh);
+    else
+      launch_pdl(head_rows_kernel<__half>, dim3((H + HEAD_STRIP - 1) / HEAD_STRIP, B), dim3(256), rows_smem, s, reinterpret_cast<const __half*>(x), w, H,
+                 W, logits, out_tanh);
+    return check_launch("head_rows");
+  }
   long long blocks = (npix + 31) / 32;
   if (blocks > 148 * 64) blocks = 148 * 64;
   const unsigned grid = static_cast<unsigned>(blocks);
