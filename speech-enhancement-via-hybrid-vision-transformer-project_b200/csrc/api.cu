@@ -521,7 +521,7 @@ static int add_conv(hvit_plan* p, const std::string& name, const void* in, int B
     // 3x3 convs keep the input tile + halo in shared memory (igemm_halo_kernel); HVIT_NO_HALO=1 selects the
     // tap-shifted TMA boxes of igemm_tc2_kernel instead (A/B comparison)
     static const bool no_halo = getenv("HVIT_NO_HALO") != nullptr && getenv("HVIT_NO_HALO")[0] == '1';
-    q.halo = (!up2 && use_2cta() && !no_halo && Cin % 64 == 0 && Cout <= 2048) ? 1 : 0;
+    q.halo = (use_2cta() && !no_halo && Cin % 64 == 0 && Cout <= 512 && (!up2 || pick_block_n(Cout) <= 128)) ? 1 : 0;
     if (q.halo) {
       q.Wt = 8; q.Ht = 16;
     } else if (pool) {

@@ -561,7 +561,7 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
 // for any (dy, dx).  Weights still stream through a ring of 128B-swizzled half tiles (shared by all CTAs: these L2
 // reads merge).  Epilogue: 16-bit BN (+ReLU) (+2x2 pool) paths of the kernel above with the 8 x 16 tile's lane map.
 // ---------------------------------------------------------------------------------------------------------------
-template <int BLOCK_N>
+template <int BLOCK_N, bool UP2>
 struct CfgH {
   static constexpr int WW = 10, HH = 18;                      // tile 8 x 16 + halo
   static constexpr int PLANE = HH * WW * 16;                  // bytes per 8-channel chunk plane
@@ -570,7 +570,14 @@ struct CfgH {
   static constexpr int B_HALF_ROWS = BLOCK_N / 2;
   static constexpr int B_STAGE_BYTES = B_HALF_ROWS * BLOCK_K * 2;
   static constexpr int B_STAGES = BLOCK_N == 256 ? 6 : 8;
-  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+  // UP2 (nearest x2 + 3x3 as four parity 2x2 convs): the four parity outputs of a low-resolution tile share ONE halo
+  // tile and accumulate side by side in TMEM (4 * BLOCK_N columns per stage; a single stage when BLOCK_N = 128)
+  static constexpr int NPAR = UP2 ? 4 : 1;
+  static constexpr int NTAP = UP2 ? 4 : 9;
+  static constexpr int ACC_COLS = NPAR * BLOCK_N;
+  static constexpr int ACC_STAGES = 2 * ACC_COLS <= 512 ? 2 : 1;
+  static constexpr int TMEM_COLS = ACC_STAGES * ACC_COLS;
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "accumulators must fit the 512 TMEM columns");
   static constexpr int STAGING_BYTES = 4 * STG_BUF_BYTES;
   static constexpr int CONST_N = 2048;
   static constexpr int CONST_BYTES = 2 * CONST_N * 4;
@@ -593,11 +600,11 @@ __device__ __forceinline__ uint64_t make_smem_desc_nosw(uint32_t saddr, uint32_t
   return d;
 }
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, bool UP2>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 igemm_halo_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, int num_ctiles, int n_tiles_n,
                   int pairs_per_group) {
-  using C = CfgH<BLOCK_N>;
+  using C = CfgH<BLOCK_N, UP2>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + C::OFF_STG;
@@ -660,12 +667,13 @@ igemm_halo_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, i
           mbar_wait(&a_empty[as], ((ai / C::A_STAGES) & 1) ^ 1);
           if (rank == 0) mbar_expect_tx(&a_full[as], 2 * C::HALO_BYTES);
           tma_load_5d_2sm(smem + C::OFF_A + as * C::HALO_BYTES, &maps.a, &a_full[as], 0, c.w0 - 1, c.h0 - 1, cb * 8, c.b);
-          for (int tap = 0; tap < 9; ++tap, ++bi) {
+          for (int pt = 0; pt < C::NPAR * C::NTAP; ++pt, ++bi) {
+            const int par = pt / C::NTAP, tap = pt % C::NTAP;
             const int bs = bi % C::B_STAGES;
             mbar_wait(&b_empty[bs], ((bi / C::B_STAGES) & 1) ^ 1);
             if (rank == 0) mbar_expect_tx(&b_full[bs], 2 * C::B_STAGE_BYTES);
             tma_load_2d_2sm(smem + C::OFF_B + bs * C::B_STAGE_BYTES, &maps.b, &b_full[bs], (tap * cblocks + cb) * BLOCK_K,
-                            b_row);
+                            par * p.N + b_row);
           }
         }
       }
@@ -680,18 +688,21 @@ igemm_halo_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, i
       for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int cb = 0; cb < cblocks; ++cb, ++ai) {
           const int as = ai % C::A_STAGES;
           mbar_wait(&a_full[as], (ai / C::A_STAGES) & 1);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + C::OFF_A + as * C::HALO_BYTES);
-          for (int tap = 0; tap < 9; ++tap, ++bi) {
+          for (int pt = 0; pt < C::NPAR * C::NTAP; ++pt, ++bi) {
+            const int par = pt / C::NTAP, tap = pt % C::NTAP;
+            const uint32_t d_tmem = tmem_base + acc * C::ACC_COLS + par * BLOCK_N;
             const int bs = bi % C::B_STAGES;
             mbar_wait(&b_full[bs], (bi / C::B_STAGES) & 1);
             tc_fence_after();
             const uint32_t b_addr = smem_u32(smem + C::OFF_B + bs * C::B_STAGE_BYTES);
-            const int dy = tap / 3, dx = tap % 3;  // already offset by the halo: (h + dy, w + dx) in halo coordinates
+            // tap position in halo coordinates (tile pixel (h, w) sits at (h + 1, w + 1)):
+            // conv: (h + ky, w + kx); parity (py, px) of the x2 upsample, tap (a, b): (h + a + py, w + b + px)
+            const int dy = UP2 ? (tap >> 1) + (par >> 1) : tap / 3, dx = UP2 ? (tap & 1) + (par & 1) : tap % 3;
             const uint32_t a_tap = a_addr + (dy * C::WW + dx) * 16;
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
@@ -704,7 +715,7 @@ igemm_halo_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, i
           umma_commit_2sm(&a_empty[as], 3);
         }
         umma_commit_2sm(&tmem_full[acc], 3);
-        if (++acc == 2) {
+        if (++acc == C::ACC_STAGES) {
           acc = 0;
           acc_phase ^= 1;
         }
@@ -743,7 +754,8 @@ igemm_halo_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, i
       tile_out_coords(p, c, pool, o1, o2, o3);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BLOCK_N;
+      for (int par = 0; par < C::NPAR; ++par) {
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * C::ACC_COLS + par * BLOCK_N;
       uint32_t ra[32], rb[32];
       if (J > 0) tmem_ld32(t_base + grp * 64, ra);
       for (int j = 0; j < J; ++j) {
@@ -764,15 +776,16 @@ igemm_halo_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, i
         if (issuer) tma_store_wait_read0();
         named_bar_sync(1 + grp, 128);
         if (issuer) {
-          tma_store_4d(&maps.out[0], buf, c.n0 + blk * 64, o1, o2, o3);
+          tma_store_4d(&maps.out[par], buf, c.n0 + blk * 64, o1, o2, o3);
           tma_store_commit();
         }
         ++it;
       }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
-      if (++acc == 2) {
+      if (++acc == C::ACC_STAGES) {
         acc = 0;
         acc_phase ^= 1;
       }
@@ -785,13 +798,13 @@ igemm_halo_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, i
   if (warp == 2) tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
 }
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, bool UP2>
 int launch_halo_impl(const IgemmParams& p, const IgemmMaps& maps, int num_ctiles, int n_tiles_n, int pairs_per_group,
                      int num_sms, cudaStream_t stream) {
-  using C = CfgH<BLOCK_N>;
+  using C = CfgH<BLOCK_N, UP2>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_halo_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(igemm_halo_kernel<BLOCK_N, EPI, UP2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("igemm_halo: cudaFuncSetAttribute(%d B smem) failed: %s", C::SMEM_BYTES, cudaGetErrorString(e));
@@ -801,7 +814,7 @@ int launch_halo_impl(const IgemmParams& p, const IgemmMaps& maps, int num_ctiles
   }
   const int max_clusters = num_sms / 2;
   const int clusters = num_ctiles < max_clusters ? num_ctiles : max_clusters;
-  cudaError_t le = launch_pdl(igemm_halo_kernel<BLOCK_N, EPI>, dim3(2 * clusters), dim3(NUM_THREADS), C::SMEM_BYTES,
+  cudaError_t le = launch_pdl(igemm_halo_kernel<BLOCK_N, EPI, UP2>, dim3(2 * clusters), dim3(NUM_THREADS), C::SMEM_BYTES,
                               stream, maps, p, num_ctiles, n_tiles_n, pairs_per_group);
   if (le == cudaSuccess) le = cudaGetLastError();
   if (le != cudaSuccess) {
@@ -814,8 +827,13 @@ int launch_halo_impl(const IgemmParams& p, const IgemmMaps& maps, int num_ctiles
 template <int BLOCK_N>
 int launch_halo_n(const IgemmParams& p, const IgemmMaps& maps, int a, int n_tiles_n, int b, int num_sms,
                   cudaStream_t stream) {
-  if (p.pool) return launch_halo_impl<BLOCK_N, EPI_BNPOOL16>(p, maps, a, n_tiles_n, b, num_sms, stream);
-  return launch_halo_impl<BLOCK_N, EPI_BN16>(p, maps, a, n_tiles_n, b, num_sms, stream);
+  if (p.pool) return launch_halo_impl<BLOCK_N, EPI_BNPOOL16, false>(p, maps, a, n_tiles_n, b, num_sms, stream);
+  if (p.mode == IG_UP2) {
+    if constexpr (BLOCK_N <= 128) return launch_halo_impl<BLOCK_N, EPI_BN16, true>(p, maps, a, n_tiles_n, b, num_sms, stream);
+    set_error("igemm_halo: x2-upsample convs need block_n <= 128");
+    return -1;
+  }
+  return launch_halo_impl<BLOCK_N, EPI_BN16, false>(p, maps, a, n_tiles_n, b, num_sms, stream);
 }
 
 template <int BLOCK_N, int EPI>
@@ -880,8 +898,8 @@ int launch_igemm_tc2(const IgemmParams& p, const IgemmMaps& maps, int block_n, i
     set_error("igemm_tc2: unsupported shape N=%d K=%d Cin=%d block_n=%d", p.N, p.K, p.Cin, block_n);
     return -1;
   }
-  if (p.halo && !(p.mode == IG_CONV3 && p.Wt == 8 && p.Ht == 16 && !p.out_f32 && p.residual == nullptr &&
-                  p.act != ACT_GELU && p.N <= 2048)) {
+  if (p.halo && !((p.mode == IG_CONV3 || (p.mode == IG_UP2 && block_n <= 128 && !p.pool)) && p.Wt == 8 && p.Ht == 16 &&
+                  !p.out_f32 && p.residual == nullptr && p.act != ACT_GELU && 4 * p.N <= 2048)) {
     set_error("igemm_tc2: the halo convolution path needs a 16-bit 3x3 conv with an 8x16 tile");
     return -1;
   }
@@ -903,7 +921,7 @@ int launch_igemm_tc2(const IgemmParams& p, const IgemmMaps& maps, int block_n, i
     group_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   } else {
     group_tiles = static_cast<long long>(p.B) * p.tiles_h * p.tiles_w;
-    if (p.mode == IG_UP2) groups = 4;
+    if (p.mode == IG_UP2 && !p.halo) groups = 4;  // (the halo kernel handles the four parities inside a tile)
   }
   const long long pairs_per_group = (group_tiles + 1) / 2;
   const long long nct = pairs_per_group * groups * n_tiles_n;

@@ -126,7 +126,21 @@ __global__ void peak_kernel(const float* __restrict__ wave, int n, unsigned* __r
   const int b = blockIdx.y;
   const float* w = wave + static_cast<long long>(b) * n;
   float m = 0.f;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(w[i]));
+  // 16-byte loads where the clip base allows it (4 independent maxima per thread), scalar tail / fallback
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+  int i0 = 0;
+  if ((reinterpret_cast<uintptr_t>(w) & 15) == 0) {
+    const int n4 = n >> 2;
+    float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < n4; i += nthr) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(w) + i);
+      m4.x = fmaxf(m4.x, fabsf(v.x)); m4.y = fmaxf(m4.y, fabsf(v.y));
+      m4.z = fmaxf(m4.z, fabsf(v.z)); m4.w = fmaxf(m4.w, fabsf(v.w));
+    }
+    m = fmaxf(fmaxf(m4.x, m4.y), fmaxf(m4.z, m4.w));
+    i0 = n4 << 2;
+  }
+  for (int i = i0 + tid; i < n; i += nthr) m = fmaxf(m, fabsf(w[i]));
   m = warp_max(m);
   if ((threadIdx.x & 31) == 0) atomicMax(max_bits + b, __float_as_uint(m));
 }
@@ -713,7 +727,7 @@ int launch_peak(const float* wave, int B, int n, float* max_val, int normalize, 
   }
   launch_pdl(fill_u32_kernel, dim3((B + 255) / 256), dim3(256), 0, s, bits, B, 0u);
   if (n > 0) {
-    dim3 grid(8, B);
+    dim3 grid(16, B);
     launch_pdl(peak_kernel, dim3(grid), dim3(256), 0, s, wave, n, bits);
   }
   return check_launch("peak");
