@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--widened", action="store_true", help="12 layers / 768-d / 12 heads (BASELINE configs[4])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-step timing table (JSON) here")
+    ap.add_argument("--latency-sweep", default=None,
+                    help="also run BASELINE configs[2] (batch 1, clips of 1..10 s, host numpy -> host numpy through "
+                         "AudioEnhancer.enhance, p50/p95 of 200 calls each) and write the table (JSON) here")
     return ap.parse_args()
 
 
@@ -285,6 +288,27 @@ def run_ours(args):
             with open(args.profile_out, "w") as f:
                 json.dump(table, f, indent=1)
 
+    # ---- single-clip latency (BASELINE metric, second half): host numpy -> host numpy through AudioEnhancer.enhance
+    latency = None
+    if rank == 0:
+        def lat(seconds, runs):
+            clip = O.synth_clip(seed=99, n_samples=int(round(seconds * 16000)))[1].astype(np.float32)
+            for _ in range(5):
+                enh.enhance(clip)
+            ts = []
+            for _ in range(runs):
+                t0 = time.perf_counter()
+                enh.enhance(clip)
+                ts.append((time.perf_counter() - t0) * 1e3)
+            ts.sort()
+            return dict(clip_seconds=seconds, p50_ms=ts[len(ts) // 2], p95_ms=ts[int(len(ts) * 0.95)], runs=runs)
+        latency = dict(lat(args.seconds, 100), api="AudioEnhancer.enhance (batch 1, host numpy in / out)")
+        if args.latency_sweep:
+            sweep = [lat(float(L), 200) for L in range(1, 11)]
+            os.makedirs(os.path.dirname(os.path.abspath(args.latency_sweep)), exist_ok=True)
+            with open(args.latency_sweep, "w") as f:
+                json.dump(dict(api=latency["api"], precision=args.precision, sweep=sweep), f, indent=1)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -317,7 +341,7 @@ def run_ours(args):
                          d2h_bytes_per_step=int(pin_out.numel() * 4), ms_per_step=e2e_ms / args.steps,
                          wall_ms_per_step=e2e_wall * 1e3 / args.steps, api="AudioEnhancer.enhance_pinned"),
                 gpu_launches=plan.launch_count(True) * args.steps * 2,
-                roofline=roofline, model_roofline=model_roof, cpu_baseline=cpu)
+                latency=latency, roofline=roofline, model_roofline=model_roof, cpu_baseline=cpu)
     print(json.dumps(line), flush=True)
 
 

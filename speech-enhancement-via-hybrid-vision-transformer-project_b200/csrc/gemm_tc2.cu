@@ -234,8 +234,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, int num_ctiles, int n_tiles_n,
                  int pairs_per_group) {
   using C = Cfg2<BLOCK_N>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (declared aligned instead of rounding the pointer up by hand: integer arithmetic on the address loses the
+  // shared-memory address space and turns every staging store / constant load of the epilogue into a generic LD/ST)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B swizzle needs 1024-byte aligned tiles
   uint8_t* staging = smem + C::STAGES * C::STAGE_BYTES;
   uint8_t* consts = staging + C::STAGING_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(consts + C::CONST_BYTES);
@@ -605,8 +607,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 igemm_halo_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, int num_ctiles, int n_tiles_n,
                   int pairs_per_group) {
   using C = CfgH<BLOCK_N, UP2>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (declared aligned instead of rounding the pointer up by hand: integer arithmetic on the address loses the
+  // shared-memory address space and turns every staging store / constant load of the epilogue into a generic LD/ST)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B swizzle needs 1024-byte aligned tiles
   uint8_t* staging = smem + C::OFF_STG;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
   uint64_t* a_full = bars;                          // [A_STAGES] (leader)

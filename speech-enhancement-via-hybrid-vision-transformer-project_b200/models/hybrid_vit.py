@@ -200,8 +200,29 @@ class HybridViT(nn.Module):
         return c
 
     def _weights_version(self) -> tuple:
-        return tuple(t._version for t in self.state_dict(keep_vars=True).values()) + \
-            tuple(t.data_ptr() for t in self.parameters())
+        # (in-place version counter, storage address) of every parameter / buffer.  The tensor list is cached - walking
+        # the module tree on every call costs more than a whole single-clip enhance - and refreshed by _apply()
+        # (.to / .cuda / .half ...) and load_state_dict(); replace a submodule's Parameter object by hand and you must
+        # call model._refresh_version_tensors() yourself.
+        ts = getattr(self, "_version_tensors", None)
+        if ts is None:
+            ts = self._refresh_version_tensors()
+        return tuple(t._version for t in ts) + tuple(t.data_ptr() for t in ts)
+
+    def _refresh_version_tensors(self):
+        ts = list(self.state_dict(keep_vars=True).values())
+        object.__setattr__(self, "_version_tensors", ts)
+        return ts
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._refresh_version_tensors()
+        return out
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._refresh_version_tensors()
+        return out
 
     def _get_packed(self, precision: int) -> PackedWeights:
         ver = self._weights_version()
