@@ -221,3 +221,27 @@ def test_model_guards(oracle):
         model.decoder[3].block[0].weight.mul_(0.5)
     y1 = model(x)
     assert not torch.equal(y0, y1)
+
+
+def test_enhance_directory_batched_equals_per_file(oracle, tmp_path):
+    """the batched, length-bucketed directory path writes exactly the files the
+    reference's one-file-at-a-time loop (enhance_file) writes."""
+    from hvit_b200.inference import AudioEnhancer
+    from hvit_b200.utils.audio_processing import load_audio, save_audio
+    cfg, sd, model = _model(oracle, dict(encoder_channels=[64, 64, 128], embed_dim=128, num_heads=2, num_layers=2,
+                                         decoder_channels=[128, 64, 64, 1]), seed=4, precision="fp16")
+    enh = AudioEnhancer(model, device="cuda")
+    src, dst_b, dst_s = tmp_path / "in", tmp_path / "batched", tmp_path / "single"
+    lengths = [8000, 8000, 12345, 8000, 16000, 12345, 8000, 8000]
+    for i, n in enumerate(lengths):
+        save_audio(0.5 * oracle.synth_clip(seed=300 + i, n_samples=n)[1], src / f"clip{i:02d}.wav", 16000)
+    enh.enhance_directory(src, dst_b, batch_size=3)
+    dst_s.mkdir()
+    for f in sorted(src.glob("*.wav")):
+        enh.enhance_file(f, dst_s / f.name)
+    names = sorted(p.name for p in dst_b.glob("*.wav"))
+    assert names == sorted(p.name for p in src.glob("*.wav"))
+    for nm in names:
+        a, _ = load_audio(dst_b / nm)
+        b, _ = load_audio(dst_s / nm)
+        assert a.shape == b.shape and np.array_equal(a, b), nm
