@@ -160,6 +160,17 @@ int hvit_conv3x3_16(const void* x_dev, const void* w_dev, const float* scale_dev
                     int pool, int up2, void* out_dev, int B, int H, int W, int Cin, int Cout, int f16, void* stream);
 int hvit_conv3x3_f32(const float* x_dev, const float* w_dev, const float* scale_dev, const float* shift_dev,
                      int relu, int up2, float* out_dev, int B, int H, int W, int Cin, int Cout, void* stream);
+/* Encoder block 0 (components.py:15-99 as built at hybrid_vit.py:196-209): Conv3x3(1 -> C, pad 1, no bias) + folded
+ * BatchNorm + ReLU + MaxPool(pool) on the fp32 spectrogram x [B,H,W] (divided by mag_max[b] when mag_max_dev != NULL,
+ * enhancer.py:96-101), NHWC bf16/fp16 out [B,H/pool,W/pool,C].  w_dev fp32 [3][3][C].  C = 64, pool = 2 run on the
+ * tensor cores (stem_tc.cu; use_tc = 0 forces the CUDA-core kernel).  scratch_dev: 64 KB, 16-byte aligned. */
+int hvit_stem_16(const float* x_dev, const void* mag_max_dev, const float* w_dev, const float* scale_dev,
+                 const float* shift_dev, void* out_dev, void* scratch_dev, int B, int H, int W, int C, int pool,
+                 int f16, int use_tc, void* stream);
+/* Last decoder block (components.py:160-167): Conv3x3(C -> 1, pad 1, no bias) on NHWC bf16/fp16 x [B,H,W,C], fp32
+ * accumulation; logits_dev (nullable) receives the pre-activation, tanh_dev the tanh.  w_dev fp32 [3][3][C]. */
+int hvit_head_16(const void* x_dev, const float* w_dev, float* logits_dev, float* tanh_dev, int B, int H, int W, int C,
+                 int f16, void* stream);
 /* Multi-head self-attention core, head_dim 64 (attention.py:86-105). qkv: [B*N, 3D]; out: [B*N, D]. */
 int hvit_attention_16(const void* qkv_dev, void* out_dev, int B, int N, int heads, int f16, void* stream);
 int hvit_attention_f32(const float* qkv_dev, float* out_dev, float* probs_dev, int B, int N, int heads, void* stream);

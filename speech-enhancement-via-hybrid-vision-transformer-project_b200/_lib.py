@@ -67,6 +67,8 @@ SYMBOLS = {
     "hvit_gemm_f32": (_I, [_VP, _I, _VP, _VP, _VP, _I, _VP, _I, _VP, _I, _I, _I, _I, _VP]),
     "hvit_conv3x3_16": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP, _I, _I, _I, _I, _I, _I, _VP]),
     "hvit_conv3x3_f32": (_I, [_VP, _VP, _VP, _VP, _I, _I, _VP, _I, _I, _I, _I, _I, _VP]),
+    "hvit_stem_16": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
+    "hvit_head_16": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),
     "hvit_attention_16": (_I, [_VP, _VP, _I, _I, _I, _I, _VP]),
     "hvit_attention_f32": (_I, [_VP, _VP, _VP, _I, _I, _I, _VP]),
     "hvit_layernorm": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _F, _VP]),

@@ -1093,6 +1093,35 @@ int hvit_conv3x3_f32(const float* x, const float* w, const float* scale, const f
   return tmp.steps[0](c);
 }
 
+int hvit_stem_16(const float* x, const void* mag_max, const float* w, const float* scale, const float* shift, void* out,
+                 void* scratch, int B, int H, int W, int C, int pool, int f16, int use_tc, void* stream) {
+  int r = require_sm100();
+  if (r) return r;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned* mm = reinterpret_cast<const unsigned*>(mag_max);
+  if (use_tc && C == 64 && pool == 2 && scratch != nullptr) {
+    g_tmap_f16 = f16 ? 1 : 0;
+    r = launch_stem_pack(w, scale, scratch, f16 ? 1 : 0, s);
+    if (r) return r;
+    const int Ho = H / 2, Wo = W / 2;
+    CUtensorMap tmo;
+    const uint64_t dims[4] = {64, static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho), static_cast<uint64_t>(B)};
+    const uint64_t strides[3] = {128, static_cast<uint64_t>(Wo) * 128, static_cast<uint64_t>(Ho) * Wo * 128};
+    const uint32_t box[4] = {32, 32, 1, 1};
+    r = make_tmap(&tmo, out, 4, dims, strides, box, 0, 1);
+    if (r) return r;
+    return launch_stem_tc(x, mm, scratch, shift, tmo, f16 ? 1 : 0, B, H, W, num_sms(), s);
+  }
+  return launch_stem(x, mm, w, scale, shift, out, f16 ? DT_F16 : DT_BF16, B, H, W, C, pool, s);
+}
+
+int hvit_head_16(const void* x, const float* w, float* logits, float* out_tanh, int B, int H, int W, int C, int f16,
+                 void* stream) {
+  int r = require_sm100();
+  if (r) return r;
+  return launch_head(x, f16 ? DT_F16 : DT_BF16, w, B, H, W, C, logits, out_tanh, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int hvit_attention_16(const void* qkv, void* out, int B, int N, int heads, int f16, void* stream) {
   int r = require_sm100();
   if (r) return r;

@@ -251,3 +251,47 @@ def test_stft_batched_normalised(oracle):
         assert np.abs(spec[b].cpu().numpy() - ref).max() <= 2e-5 * np.abs(ref).max()
         assert abs(float(mm[b]) - np.abs(ref).max()) <= 2e-5 * np.abs(ref).max()
         assert np.abs(mag[b].cpu().numpy() - np.abs(ref)).max() <= 2e-5 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("B,H,W,use_tc", [(2, 257, 501, 1), (1, 64, 70, 1), (3, 33, 129, 1), (2, 40, 51, 0)])
+@pytest.mark.parametrize("kind", ["fp16", "bf16"])
+def test_stem_16(B, H, W, use_tc, kind):
+    """Encoder block 0: conv3x3(1->64)+BN+ReLU+pool, tensor-core window-GEMM kernel and CUDA-core kernel against torch
+    fp32 (incl. the /mag_max input scaling, odd sizes, partial tiles)."""
+    dt = torch.float16 if kind == "fp16" else torch.bfloat16
+    g = torch.Generator(device="cpu").manual_seed(H * W + B)
+    x = torch.rand((B, H, W), generator=g).to(DEV) * 3.0
+    w = (torch.randn((64, 1, 3, 3), generator=g) * 0.4).to(DEV)
+    scale = (torch.rand(64, generator=g) + 0.5).to(DEV)
+    shift = (torch.randn(64, generator=g) * 0.2).to(DEV)
+    mm = (torch.rand(B, generator=g) * 2 + 1.5).to(DEV)
+    out = torch.empty((B, H // 2, W // 2, 64), dtype=dt, device=DEV)
+    scratch = torch.empty(64 * 1024, dtype=torch.uint8, device=DEV)
+    w9c = w[:, 0].permute(1, 2, 0).contiguous()
+    _lib.check(U.lib().hvit_stem_16(U.P(x), U.P(mm.view(torch.int32)), U.P(w9c), U.P(scale), U.P(shift), U.P(out),
+                                    U.P(scratch), B, H, W, 64, 2, 1 if kind == "fp16" else 0, use_tc, U.stream()), "stem")
+    U.sync()
+    xin = (x / mm[:, None, None])[:, None].double()
+    ref = torch.nn.functional.conv2d(xin, w.double(), padding=1) * scale[None, :, None, None] + shift[None, :, None, None]
+    ref = torch.nn.functional.max_pool2d(torch.relu(ref), 2).permute(0, 2, 3, 1)
+    assert torch.isfinite(out.float()).all()
+    assert U.rel_err(out.float(), ref) < OUT_TOL[kind]
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 64, 124), (1, 5, 7), (3, 17, 33)])
+@pytest.mark.parametrize("kind", ["fp16", "bf16"])
+def test_head_16(B, H, W, kind):
+    """Last decoder block: conv3x3(64->1) + tanh with fp32 accumulation (row-streaming kernel) against torch."""
+    dt = torch.float16 if kind == "fp16" else torch.bfloat16
+    g = torch.Generator(device="cpu").manual_seed(B * H + W)
+    x = torch.randn((B, H, W, 64), generator=g).to(DEV).to(dt)
+    w = (torch.randn((1, 64, 3, 3), generator=g) * 0.05).to(DEV)
+    logits = torch.empty((B, H, W), dtype=torch.float32, device=DEV)
+    th = torch.empty_like(logits)
+    w9c = w[0].permute(1, 2, 0).contiguous()
+    _lib.check(U.lib().hvit_head_16(U.P(x), U.P(w9c), U.P(logits), U.P(th), B, H, W, 64, 1 if kind == "fp16" else 0,
+                                    U.stream()), "head")
+    U.sync()
+    ref = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), w.double(), padding=1)[:, 0]  # (fp64: no TF32)
+    assert U.rel_err(logits, ref) < 1e-5
+    assert (th.double() - torch.tanh(ref)).abs().max() < 1e-5
