@@ -563,6 +563,12 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
 // for any (dy, dx).  Weights still stream through a ring of 128B-swizzled half tiles (shared by all CTAs: these L2
 // reads merge).  Epilogue: 16-bit BN (+ReLU) (+2x2 pool) paths of the kernel above with the 8 x 16 tile's lane map.
 // ---------------------------------------------------------------------------------------------------------------
+// 16 epilogue warps: the conv epilogues (short K, pool) are latency-bound with two warps per scheduler and were
+// slower than the MMA main loop (encoder.1: ~4 000 vs 2 300 cycles per tile); four warps per scheduler, one 32-column
+// TMEM chunk per warp and block, hide those latencies.
+constexpr int NUM_EPI_WARPS_H = 16;
+constexpr int NUM_THREADS_H = 64 + NUM_EPI_WARPS_H * 32;
+
 template <int BLOCK_N, bool UP2>
 struct CfgH {
   static constexpr int WW = 10, HH = 18;                      // tile 8 x 16 + halo
@@ -603,7 +609,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_nosw(uint32_t saddr, uint32_t
 }
 
 template <int BLOCK_N, int EPI, bool UP2>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS_H, 1)
 igemm_halo_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, int num_ctiles, int n_tiles_n,
                   int pairs_per_group) {
   using C = CfgH<BLOCK_N, UP2>;
@@ -644,7 +650,7 @@ igemm_halo_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, i
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 2 * NUM_EPI_WARPS);
+      mbar_init(&tmem_empty[a], 2 * NUM_EPI_WARPS_H);
     }
     mbar_fence_init();
   }
@@ -728,10 +734,11 @@ igemm_halo_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, i
   } else {
     // ------------------------------------------------------------ epilogue (16-bit output, BN / ReLU / pool)
     const int ew = warp - 2;
-    const int sub = warp & 3;
-    const int grp = ew >> 2;
+    const int sub = warp & 3;            // TMEM lane quarter this warp may read
+    const int grp = ew >> 3;             // 8 warps per group; group g owns the 64-column blocks g, g + 2, ...
+    const int half = (ew >> 2) & 1;      // which 32-column half of a block this warp converts
     const int m = sub * 32 + lane;       // accumulator row: pixel (h = m >> 3, w = m & 7) of the 8 x 16 tile
-    const bool issuer = (ew & 3) == 0 && lane == 0;
+    const bool issuer = (ew & 7) == 0 && lane == 0;
     constexpr bool pool = EPI == EPI_BNPOOL16;
     constexpr int nblk = BLOCK_N / 64;
     const int J = (nblk - grp + 1) / 2;
@@ -743,11 +750,11 @@ igemm_halo_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, i
     const float relu_lo = p.act == ACT_RELU ? 0.0f : -INFINITY;
     float* cscale = reinterpret_cast<float*>(smem + C::OFF_CONST);
     float* cshift = cscale + C::CONST_N;
-    for (int e = ew * 32 + lane; e < p.N; e += NUM_EPI_WARPS * 32) {
+    for (int e = ew * 32 + lane; e < p.N; e += NUM_EPI_WARPS_H * 32) {
       cscale[e] = p.scale != nullptr ? __ldg(p.scale + e) : 1.0f;
       cshift[e] = p.shift != nullptr ? __ldg(p.shift + e) : 0.0f;
     }
-    named_bar_sync(3, NUM_EPI_WARPS * 32);
+    named_bar_sync(3, NUM_EPI_WARPS_H * 32);
 
     uint32_t it = 0;
     int acc = 0;
@@ -759,32 +766,28 @@ igemm_halo_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, i
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       for (int par = 0; par < C::NPAR; ++par) {
-      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * C::ACC_COLS + par * BLOCK_N;
-      uint32_t ra[32], rb[32];
-      if (J > 0) tmem_ld32(t_base + grp * 64, ra);
-      for (int j = 0; j < J; ++j) {
-        const int blk = 2 * j + grp;
-        uint8_t* buf = stg0 + (it & 1) * STG_BUF_BYTES;
-        uint8_t* row = buf + srow * 128;
-        const float* sc = cscale + c.n0 + blk * 64;
-        const float* sh = cshift + c.n0 + blk * 64;
-        tmem_ld_wait(ra);
-        tmem_ld32(t_base + blk * 64 + 32, rb);
-        if (p.f16) emit16<EPI, true>(ra, sc, sh, p, relu_lo, row, 0, sw, writer, 8);
-        else emit16<EPI, false>(ra, sc, sh, p, relu_lo, row, 0, sw, writer, 8);
-        tmem_ld_wait(rb);
-        if (j + 1 < J) tmem_ld32(t_base + (blk + 2) * 64, ra);
-        if (p.f16) emit16<EPI, true>(rb, sc + 32, sh + 32, p, relu_lo, row, 1, sw, writer, 8);
-        else emit16<EPI, false>(rb, sc + 32, sh + 32, p, relu_lo, row, 1, sw, writer, 8);
-        fence_proxy_async_smem();
-        if (issuer) tma_store_wait_read0();
-        named_bar_sync(1 + grp, 128);
-        if (issuer) {
-          tma_store_4d(&maps.out[par], buf, c.n0 + blk * 64, o1, o2, o3);
-          tma_store_commit();
+        const uint32_t t_base =
+            tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * C::ACC_COLS + par * BLOCK_N + half * 32;
+        for (int j = 0; j < J; ++j) {
+          const int blk = 2 * j + grp;
+          uint8_t* buf = stg0 + (it & 1) * STG_BUF_BYTES;
+          uint8_t* row = buf + srow * 128;
+          const float* sc = cscale + c.n0 + blk * 64 + half * 32;
+          const float* sh = cshift + c.n0 + blk * 64 + half * 32;
+          uint32_t ra[32];
+          tmem_ld32(t_base + blk * 64, ra);
+          tmem_ld_wait(ra);
+          if (p.f16) emit16<EPI, true>(ra, sc, sh, p, relu_lo, row, half, sw, writer, 8);
+          else emit16<EPI, false>(ra, sc, sh, p, relu_lo, row, half, sw, writer, 8);
+          fence_proxy_async_smem();
+          if (issuer) tma_store_wait_read0();
+          named_bar_sync(1 + grp, 256);
+          if (issuer) {
+            tma_store_4d(&maps.out[par], buf, c.n0 + blk * 64, o1, o2, o3);
+            tma_store_commit();
+          }
+          ++it;
         }
-        ++it;
-      }
       }
       tc_fence_before();
       __syncwarp();
@@ -818,7 +821,7 @@ int launch_halo_impl(const IgemmParams& p, const IgemmMaps& maps, int num_ctiles
   }
   const int max_clusters = num_sms / 2;
   const int clusters = num_ctiles < max_clusters ? num_ctiles : max_clusters;
-  cudaError_t le = launch_pdl(igemm_halo_kernel<BLOCK_N, EPI, UP2>, dim3(2 * clusters), dim3(NUM_THREADS), C::SMEM_BYTES,
+  cudaError_t le = launch_pdl(igemm_halo_kernel<BLOCK_N, EPI, UP2>, dim3(2 * clusters), dim3(NUM_THREADS_H), C::SMEM_BYTES,
                               stream, maps, p, num_ctiles, n_tiles_n, pairs_per_group);
   if (le == cudaSuccess) le = cudaGetLastError();
   if (le != cudaSuccess) {
