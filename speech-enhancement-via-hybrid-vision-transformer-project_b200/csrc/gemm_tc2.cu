@@ -93,7 +93,9 @@ enum {
   EPI_GELU16 = 2,    // + shift, erf-GELU,  16-bit out (fc1)
   EPI_BN16 = 3,      // * scale + shift, max(., lo), 16-bit out (3x3 convs; lo = 0 for ReLU, -inf for none)
   EPI_BNPOOL16 = 4,  // EPI_BN16 + fused 2x2 max-pool
-  EPI_F32 = 5        // + shift (+ fp32 residual), fp32 out (proj, fc2, patch embedding)
+  EPI_F32 = 5,       // + shift (+ fp32 residual), fp32 out (proj, fc2, patch embedding)
+  EPI_SH16 = 6,      // + shift, max(., lo), 16-bit out: 3x3 convs whose BN scale is folded into the weights
+  EPI_SHPOOL16 = 7   // EPI_SH16 + fused 2x2 max-pool
 };
 
 // GELU(v) = relu(v) - 0.5*|v|*erfc(|v|/sqrt2), erfc(u/sqrt2) = 2^q(u) with a weighted-minimax degree-5 q on [0, 6]
@@ -132,7 +134,7 @@ __device__ __forceinline__ void emit16(const uint32_t (&cur)[32], const float* s
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const float4 b = *reinterpret_cast<const float4*>(sh + 4 * q);
-    if (EPI == EPI_LIN16 || EPI == EPI_GELU16) {
+    if (EPI == EPI_LIN16 || EPI == EPI_GELU16 || EPI == EPI_SH16 || EPI == EPI_SHPOOL16) {
       v[4 * q + 0] = __uint_as_float(cur[4 * q + 0]) + b.x;
       v[4 * q + 1] = __uint_as_float(cur[4 * q + 1]) + b.y;
       v[4 * q + 2] = __uint_as_float(cur[4 * q + 2]) + b.z;
@@ -148,7 +150,7 @@ __device__ __forceinline__ void emit16(const uint32_t (&cur)[32], const float* s
   if (EPI == EPI_GELU16) {
 #pragma unroll
     for (int e = 0; e < 32; ++e) v[e] = gelu_erfc5(v[e]);
-  } else if (EPI == EPI_BN16 || EPI == EPI_BNPOOL16) {
+  } else if (EPI == EPI_BN16 || EPI == EPI_BNPOOL16 || EPI == EPI_SH16 || EPI == EPI_SHPOOL16) {
 #pragma unroll
     for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], relu_lo);
   } else if (EPI == EPI_GENERIC) {
@@ -160,7 +162,7 @@ __device__ __forceinline__ void emit16(const uint32_t (&cur)[32], const float* s
       for (int e = 0; e < 32; ++e) v[e] = gelu_erfc5(v[e]);
     }
   }
-  if (EPI == EPI_BNPOOL16 || (EPI == EPI_GENERIC && p.pool)) {
+  if (EPI == EPI_BNPOOL16 || EPI == EPI_SHPOOL16 || (EPI == EPI_GENERIC && p.pool)) {
 #pragma unroll
     for (int e = 0; e < 32; ++e) {
       v[e] = fmaxf(v[e], __shfl_xor_sync(0xFFFFFFFFu, v[e], 1));
@@ -739,7 +741,7 @@ igemm_halo_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, i
     const int half = (ew >> 2) & 1;      // which 32-column half of a block this warp converts
     const int m = sub * 32 + lane;       // accumulator row: pixel (h = m >> 3, w = m & 7) of the 8 x 16 tile
     const bool issuer = (ew & 7) == 0 && lane == 0;
-    constexpr bool pool = EPI == EPI_BNPOOL16;
+    constexpr bool pool = EPI == EPI_BNPOOL16 || EPI == EPI_SHPOOL16;
     constexpr int nblk = BLOCK_N / 64;
     const int J = (nblk - grp + 1) / 2;
     uint8_t* stg0 = staging + grp * 2 * STG_BUF_BYTES;
@@ -834,13 +836,19 @@ int launch_halo_impl(const IgemmParams& p, const IgemmMaps& maps, int num_ctiles
 template <int BLOCK_N>
 int launch_halo_n(const IgemmParams& p, const IgemmMaps& maps, int a, int n_tiles_n, int b, int num_sms,
                   cudaStream_t stream) {
-  if (p.pool) return launch_halo_impl<BLOCK_N, EPI_BNPOOL16, false>(p, maps, a, n_tiles_n, b, num_sms, stream);
+  const bool sh = p.scale == nullptr;  // BN scale folded into the weights: the epilogue only adds the shift
+  if (p.pool)
+    return sh ? launch_halo_impl<BLOCK_N, EPI_SHPOOL16, false>(p, maps, a, n_tiles_n, b, num_sms, stream)
+              : launch_halo_impl<BLOCK_N, EPI_BNPOOL16, false>(p, maps, a, n_tiles_n, b, num_sms, stream);
   if (p.mode == IG_UP2) {
-    if constexpr (BLOCK_N <= 128) return launch_halo_impl<BLOCK_N, EPI_BN16, true>(p, maps, a, n_tiles_n, b, num_sms, stream);
+    if constexpr (BLOCK_N <= 128)
+      return sh ? launch_halo_impl<BLOCK_N, EPI_SH16, true>(p, maps, a, n_tiles_n, b, num_sms, stream)
+                : launch_halo_impl<BLOCK_N, EPI_BN16, true>(p, maps, a, n_tiles_n, b, num_sms, stream);
     set_error("igemm_halo: x2-upsample convs need block_n <= 128");
     return -1;
   }
-  return launch_halo_impl<BLOCK_N, EPI_BN16, false>(p, maps, a, n_tiles_n, b, num_sms, stream);
+  return sh ? launch_halo_impl<BLOCK_N, EPI_SH16, false>(p, maps, a, n_tiles_n, b, num_sms, stream)
+            : launch_halo_impl<BLOCK_N, EPI_BN16, false>(p, maps, a, n_tiles_n, b, num_sms, stream);
 }
 
 template <int BLOCK_N, int EPI>

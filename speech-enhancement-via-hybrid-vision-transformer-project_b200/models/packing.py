@@ -62,6 +62,11 @@ class PackedWeights:
             if i == 0:
                 c.stem_w = hold(w[:, 0].permute(1, 2, 0))           # [3,3,C0]
                 c.stem_scale, c.stem_shift = hold(scale), hold(shift)
+            elif precision != _lib.PREC_FP32:
+                # 16-bit modes: the BN scale is folded into the conv weights in fp32 (one rounding to 16 bits), the
+                # epilogue only adds the shift (no per-channel scale loads; scale pointer = NULL means 1.0)
+                c.enc_w[i] = hold(conv_khwc(w.float() * scale.to(w.device)[:, None, None, None]), act)
+                c.enc_shift[i] = hold(shift)
             else:
                 c.enc_w[i] = hold(conv_khwc(w), act)
                 c.enc_scale[i], c.enc_shift[i] = hold(scale), hold(shift)
@@ -88,12 +93,14 @@ class PackedWeights:
             if i == n_dec - 1:
                 c.head_w = hold(w[0].permute(1, 2, 0))              # [3,3,C]
                 continue
-            if up > 1 and precision != _lib.PREC_FP32:
-                c.dec_w[i] = hold(up2_parity_kernels(w), act)
+            scale, shift = fold_bn(sd, f"decoder.{i}.block.{ci + 1}")
+            if precision != _lib.PREC_FP32:  # BN scale folded into the weights (see the encoder above)
+                ws = w.float() * scale.to(w.device)[:, None, None, None]
+                c.dec_w[i] = hold(up2_parity_kernels(ws) if up > 1 else conv_khwc(ws), act)
+                c.dec_shift[i] = hold(shift)
             else:
                 c.dec_w[i] = hold(conv_khwc(w), act)
-            scale, shift = fold_bn(sd, f"decoder.{i}.block.{ci + 1}")
-            c.dec_scale[i], c.dec_shift[i] = hold(scale), hold(shift)
+                c.dec_scale[i], c.dec_shift[i] = hold(scale), hold(shift)
             if cfg["use_skip_connections"] and f"skip_projections.{i}.weight" in sd:
                 sw = sd[f"skip_projections.{i}.weight"]
                 c.skip_w[i] = hold(sw.reshape(sw.shape[0], sw.shape[1]), act)
