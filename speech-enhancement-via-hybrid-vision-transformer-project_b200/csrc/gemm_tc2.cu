@@ -310,6 +310,17 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
           if (p.mode == IG_PLAIN) {
             tma_load_2d_2sm(sa, &maps.a, &full_bar[stage], kb * BLOCK_K, c.m0);
+            // long-K GEMMs stream their A operand from HBM (fc2: 130 MB of hidden activations): pull the tile that the
+            // ring will ask for PF k-blocks from now into L2, so the ring's own loads see L2 latency
+            if (p.a_prefetch > 0) {
+              const int pk = kb + p.a_prefetch;
+              if (pk < kblocks) {
+                tma_prefetch_2d(&maps.a, pk * BLOCK_K, c.m0);
+              } else if (ct + num_clusters < num_ctiles) {  // first k-blocks of this CTA's next tile
+                const TileCoord cn = decode_ctile(p, ct + num_clusters, n_tiles_n, BLOCK_N, pairs_per_group, rank);
+                if (cn.m0 != c.m0) tma_prefetch_2d(&maps.a, (pk - kblocks) * BLOCK_K, cn.m0);
+              }
+            }
           } else {
             const int tap = kb / cblocks;
             const int c0 = (kb - tap * cblocks) * BLOCK_K;
@@ -927,6 +938,12 @@ int launch_igemm_tc2(const IgemmParams& p, const IgemmMaps& maps, int block_n, i
     return -1;
   }
   IgemmParams pp = p;
+  // A operand larger than what survives in L2 next to the rest of the step's traffic (fc2's 130 MB hidden activation):
+  // L2-prefetch it a few k-blocks ahead of the ring (measured: fc2 69.3 -> 65.3 us; an L2-resident A gets slower)
+  pp.a_prefetch = 0;
+  if (p.mode == IG_PLAIN && p.K >= 1024 && p.N / block_n <= 2 && static_cast<double>(p.M) * p.K * 2.0 >= 96e6)
+    pp.a_prefetch = 4;  // (few N tiles per A tile: every A byte really comes from HBM)
+  if (const char* e = getenv("HVIT_A_PREFETCH")) pp.a_prefetch = atoi(e);
   pp.res_inplace = (p.residual != nullptr && p.residual == p.out && p.ldr == p.ldc && p.res_mod == 0 &&
                     !(p.dbg & 32)) ? 1 : 0;
   const int n_tiles_n = p.N / block_n;

@@ -49,6 +49,7 @@ struct IgemmParams {
   int dbg;              // diagnostics only (HVIT_DBG): 1 skip global stores, 2 skip TMEM loads, 4 skip MMA issue
   int Ho, Wo;           // valid output image dims (conv modes)
   int HoPitch;          // image row pitch of the output buffer in pixel rows (>= Ho)
+  int a_prefetch;       // set by the launcher: L2-prefetch distance (k-blocks) for an A operand that streams from HBM, 0 = off
   int halo;             // IG_CONV3 on the tensor-core path: input tile + halo staged once in shared memory (8x16 tile;
                         // maps.a is then the 5-D un-swizzled halo map), see igemm_halo_kernel
   long long* prof;      // diagnostics only (HVIT_PROF): per-CTA cycle counters [gridDim.x][16], or null
