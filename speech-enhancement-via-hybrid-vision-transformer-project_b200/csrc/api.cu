@@ -600,14 +600,9 @@ static int build_steps(hvit_plan* p) {
       if (cudaStreamSynchronize(nullptr) != cudaSuccess) return check_launch("stem_pack(sync)");
       const int sms = num_sms();
       const int Ho = g.enc[0].H, Wo = g.enc[0].W;
-      CUtensorMap tmo;  // (64 channels, Wo, Ho, B), un-swizzled 32-channel x 32-pixel store boxes (one per epilogue warp)
-      {
-        const uint64_t dims[4] = {64, static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho), static_cast<uint64_t>(B)};
-        const uint64_t strides[3] = {128, static_cast<uint64_t>(Wo) * 128, static_cast<uint64_t>(Ho) * Wo * 128};
-        const uint32_t box[4] = {32, 32, 1, 1};
-        r = make_tmap(&tmo, out, 4, dims, strides, box, 0, 1);
-        if (r) return r;
-      }
+      CUtensorMap tmo;  // (64 channels, Wo, Ho, B): one pooled row of a tile = 64 pixels x 128 bytes, 128B-swizzled
+      r = tmap_out4(&tmo, out, 0, 64, Wo, Ho, B, 128, static_cast<uint64_t>(Wo) * 128, static_cast<uint64_t>(Ho) * Wo * 128, 64, 1);
+      if (r) return r;
       p->steps.push_back([=](const Ctx& k) { return launch_stem_tc(k.x, k.mag_max, apack, sh, tmo, f16, B, F, T, sms, k.stream); });
     } else {
       p->steps.push_back([=](const Ctx& k) { return launch_stem(k.x, k.mag_max, sw, ss, sh, out, dt, B, F, T, C0, pool, k.stream); });
@@ -1105,10 +1100,7 @@ int hvit_stem_16(const float* x, const void* mag_max, const float* w, const floa
     if (r) return r;
     const int Ho = H / 2, Wo = W / 2;
     CUtensorMap tmo;
-    const uint64_t dims[4] = {64, static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho), static_cast<uint64_t>(B)};
-    const uint64_t strides[3] = {128, static_cast<uint64_t>(Wo) * 128, static_cast<uint64_t>(Ho) * Wo * 128};
-    const uint32_t box[4] = {32, 32, 1, 1};
-    r = make_tmap(&tmo, out, 4, dims, strides, box, 0, 1);
+    r = tmap_out4(&tmo, out, 0, 64, Wo, Ho, B, 128, static_cast<uint64_t>(Wo) * 128, static_cast<uint64_t>(Ho) * Wo * 128, 64, 1);
     if (r) return r;
     return launch_stem_tc(x, mm, scratch, shift, tmo, f16 ? 1 : 0, B, H, W, num_sms(), s);
   }

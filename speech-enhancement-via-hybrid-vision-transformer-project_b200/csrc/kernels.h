@@ -97,10 +97,10 @@ int launch_istft_ola(const float* frames, const float* max_val, float* wave_out,
 int launch_stem(const float* x /*[B,H,W]*/, const unsigned* mag_max_bits /*nullable*/, const float* w /*[9][C]*/,
                 const float* scale, const float* shift, void* out, int dt, int B, int H, int W, int C, int pool,
                 cudaStream_t s);
-// tensor-core stem (C = 64, pool 2, 16-bit output): apack = [4][128][64] 16-bit position matrices built once per
+// tensor-core stem (C = 64, pool 2, 16-bit output): apack = [4][64][64] 16-bit position matrices built once per
 // weight set by launch_stem_pack (BN scale folded in), see stem_tc.cu
 int launch_stem_pack(const float* w9c, const float* scale, void* apack, int f16, cudaStream_t s);
-// tmap_out: 4-D map (64 channels, Wo, Ho, B) of the NHWC output with an un-swizzled (32, 32, 1, 1) box
+// tmap_out: 4-D map (64 channels, Wo, Ho, B) of the NHWC output with a 128B-swizzled (64, 64, 1, 1) box
 int launch_stem_tc(const float* x, const unsigned* mag_max_bits, const void* apack, const float* shift,
                    const CUtensorMap& tmap_out, int f16, int B, int H, int W, int num_sms, cudaStream_t s);
 int launch_layernorm(const float* x, const float* g, const float* b, void* out, int dt, int rows, int D,
