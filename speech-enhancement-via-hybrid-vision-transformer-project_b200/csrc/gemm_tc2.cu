@@ -46,15 +46,21 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 constexpr int STG_BUF_BYTES = 128 * 128;  // 128 rows x 128 B
 
-template <int BLOCK_N>
+template <int BLOCK_N, int EPI = 0>
 struct Cfg2 {
   static constexpr int B_HALF_ROWS = BLOCK_N / 2;
   static constexpr int B_STAGE_BYTES = B_HALF_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 7);
+  // The GEMM main loops are sensitive to the ring depth (3 -> 4 stages: +10 %, 4 -> 5: +5 % on qkv).  Where the
+  // epilogue is far from critical - the plain 16-bit one (EPI_LIN16: qkv, to_feature_map, skip projections) and the
+  // fp32 one of long-K GEMMs (EPI_F32D: fc2) - each epilogue group gives up its second staging buffer (it waits for
+  // the previous TMA store to release the buffer) and the ring gets a fifth stage.
+  static constexpr bool DEEP = BLOCK_N == 256 && (EPI == 1 || EPI == 8);
+  static constexpr int NBUF = DEEP ? 1 : 2;                   // staging buffers per epilogue group
+  static constexpr int STAGES = BLOCK_N == 256 ? (DEEP ? 5 : 4) : (BLOCK_N == 128 ? 6 : 7);
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
-  static constexpr int STAGING_BYTES = 4 * STG_BUF_BYTES;    // [group][buffer]
-  static constexpr int CONST_N = BLOCK_N == 256 ? 4096 : 2048;  // scale[N] | shift[N] of the whole problem fit up to here
+  static constexpr int STAGING_BYTES = 2 * NBUF * STG_BUF_BYTES;    // [group][buffer]
+  static constexpr int CONST_N = DEEP ? 3072 : (BLOCK_N == 256 ? 4096 : 2048);  // scale[N] | shift[N] of the whole problem fit up to here
   static constexpr int CONST_BYTES = 2 * CONST_N * 4;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + CONST_BYTES + 1024 + 512;
 };
@@ -95,7 +101,8 @@ enum {
   EPI_BNPOOL16 = 4,  // EPI_BN16 + fused 2x2 max-pool
   EPI_F32 = 5,       // + shift (+ fp32 residual), fp32 out (proj, fc2, patch embedding)
   EPI_SH16 = 6,      // + shift, max(., lo), 16-bit out: 3x3 convs whose BN scale is folded into the weights
-  EPI_SHPOOL16 = 7   // EPI_SH16 + fused 2x2 max-pool
+  EPI_SHPOOL16 = 7,  // EPI_SH16 + fused 2x2 max-pool
+  EPI_F32D = 8       // EPI_F32 without a TMA-loaded residual and K >= 1024 (fc2): deep-ring configuration
 };
 
 // GELU(v) = relu(v) - 0.5*|v|*erfc(|v|/sqrt2), erfc(u/sqrt2) = 2^q(u) with a weighted-minimax degree-5 q on [0, 6]
@@ -194,7 +201,7 @@ __device__ __forceinline__ void emit32(const uint32_t (&cur)[32], const float* s
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const float4 b = *reinterpret_cast<const float4*>(sh + 4 * q);
-    if (EPI == EPI_F32) {
+    if (EPI == EPI_F32 || EPI == EPI_F32D) {
       v[4 * q + 0] = __uint_as_float(cur[4 * q + 0]) + b.x;
       v[4 * q + 1] = __uint_as_float(cur[4 * q + 1]) + b.y;
       v[4 * q + 2] = __uint_as_float(cur[4 * q + 2]) + b.z;
@@ -235,7 +242,7 @@ template <int BLOCK_N, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, int num_ctiles, int n_tiles_n,
                  int pairs_per_group) {
-  using C = Cfg2<BLOCK_N>;
+  using C = Cfg2<BLOCK_N, EPI>;
   // (declared aligned instead of rounding the pointer up by hand: integer arithmetic on the address loses the
   // shared-memory address space and turns every staging store / constant load of the epilogue into a generic LD/ST)
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -409,13 +416,13 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
     const int grp = ew >> 2;             // column-block parity owned by this warp's group
     const int m = sub * 32 + lane;       // accumulator row == TMEM lane
     const bool issuer = (ew & 3) == 0 && lane == 0;
-    constexpr bool kF32 = EPI == EPI_F32;
+    constexpr bool kF32 = EPI == EPI_F32 || EPI == EPI_F32D;
     const bool out_f32 = EPI == EPI_GENERIC ? p.out_f32 != 0 : kF32;
     const bool pool = EPI == EPI_GENERIC ? p.pool != 0 : EPI == EPI_BNPOOL16;
     const int wcols = out_f32 ? 32 : 64;            // columns per 128-byte block
     const int nblk = BLOCK_N / wcols;
     const int J = (nblk - grp + 1) / 2;             // blocks of this group per tile
-    uint8_t* stg0 = staging + grp * 2 * STG_BUF_BYTES;
+    uint8_t* stg0 = staging + grp * C::NBUF * STG_BUF_BYTES;
     // In-place residual (x += f(x), the transformer's proj / fc2): nothing is loaded - the block is added into
     // global memory by a TMA reduce-add.  Otherwise the fp32 residual tile is TMA-loaded into the staging buffer.
     const bool red_add = (EPI == EPI_GENERIC || kF32) && p.residual != nullptr && p.res_inplace != 0;
@@ -465,7 +472,7 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
       if (has_res && issuer && J > 0) {
         // residual tile of the first block -> staging buffer; the NEXT tile's residual blocks -> L2, so that the
         // per-block TMA loads of the next tile are L2 hits instead of exposed HBM latency
-        uint8_t* buf = stg0 + (it & 1) * STG_BUF_BYTES;
+        uint8_t* buf = stg0 + (C::NBUF == 2 ? (it & 1) : 0) * STG_BUF_BYTES;
         mbar_expect_tx(&res_bar[grp * 2 + (it & 1)], STG_BUF_BYTES);
         tma_load_4d(buf, &maps.res, &res_bar[grp * 2 + (it & 1)], c.n0 + grp * wcols, o1, o2, r3);
         const int nct = ct + num_clusters;
@@ -508,10 +515,14 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
         // 16-bit output: a block is two 32-column TMEM chunks; the next chunk is always in flight
         for (int j = 0; j < J; ++j) {
           const int blk = 2 * j + grp;
-          uint8_t* buf = stg0 + (it & 1) * STG_BUF_BYTES;
+          uint8_t* buf = stg0 + (C::NBUF == 2 ? (it & 1) : 0) * STG_BUF_BYTES;
           uint8_t* row = buf + srow * 128;
           const float* sc = cscale + cbase + blk * 64;
           const float* sh = cshift + cbase + blk * 64;
+          if (C::NBUF == 1) {  // single staging buffer: the previous TMA store must have finished reading it
+            if (issuer) tma_store_wait_read0();
+            named_bar_sync(1 + grp, 128);
+          }
           tmem_ld_wait(ra);
           tmem_ld32(t_base + blk * 64 + 32, rb);
           if (p.f16) emit16<EPI, true>(ra, sc, sh, p, relu_lo, row, 0, sw, writer);
@@ -526,7 +537,11 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
         // fp32 output: a block is one chunk; ra / rb alternate as current / prefetch buffer
         auto block32 = [&](int j, uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
           const int blk = 2 * j + grp;
-          uint8_t* buf = stg0 + (it & 1) * STG_BUF_BYTES;
+          uint8_t* buf = stg0 + (C::NBUF == 2 ? (it & 1) : 0) * STG_BUF_BYTES;
+          if (C::NBUF == 1) {  // single staging buffer: the previous TMA store must have finished reading it
+            if (issuer) tma_store_wait_read0();
+            named_bar_sync(1 + grp, 128);
+          }
           if (has_res) mbar_wait(&res_bar[grp * 2 + (it & 1)], (it >> 1) & 1);
           tmem_ld_wait(cur);
           if (j + 1 < J) tmem_ld32(t_base + (blk + 2) * 32, nxt);
@@ -865,7 +880,7 @@ int launch_halo_n(const IgemmParams& p, const IgemmMaps& maps, int a, int n_tile
 template <int BLOCK_N, int EPI>
 int launch_impl2(const IgemmParams& p, const IgemmMaps& maps, int num_ctiles, int n_tiles_n, int pairs_per_group,
                  int num_sms, cudaStream_t stream) {
-  using C = Cfg2<BLOCK_N>;
+  using C = Cfg2<BLOCK_N, EPI>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(igemm_tc2_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -895,7 +910,10 @@ int launch_impl2(const IgemmParams& p, const IgemmMaps& maps, int num_ctiles, in
 // which compiled epilogue serves this parameter combination (see the EPI_* enum)
 int pick_epi(const IgemmParams& p) {
   if (p.dbg & 16) return EPI_GENERIC;
-  if (p.out_f32) return (p.act == ACT_NONE && p.scale == nullptr && !p.pool) ? EPI_F32 : EPI_GENERIC;
+  if (p.out_f32) {
+    if (!(p.act == ACT_NONE && p.scale == nullptr && !p.pool)) return EPI_GENERIC;
+    return (p.K >= 1024 && p.mode == IG_PLAIN && (p.residual == nullptr || p.res_inplace)) ? EPI_F32D : EPI_F32;
+  }
   if (p.residual != nullptr) return EPI_GENERIC;
   if (p.pool) return (p.act != ACT_GELU) ? EPI_BNPOOL16 : EPI_GENERIC;
   if (p.scale != nullptr) return (p.act != ACT_GELU) ? EPI_BN16 : EPI_GENERIC;
@@ -913,6 +931,7 @@ int launch_n(const IgemmParams& p, const IgemmMaps& maps, int a, int n_tiles_n, 
     case EPI_BN16: return launch_impl2<BLOCK_N, EPI_BN16>(p, maps, a, n_tiles_n, b, num_sms, stream);
     case EPI_BNPOOL16: return launch_impl2<BLOCK_N, EPI_BNPOOL16>(p, maps, a, n_tiles_n, b, num_sms, stream);
     case EPI_F32: return launch_impl2<BLOCK_N, EPI_F32>(p, maps, a, n_tiles_n, b, num_sms, stream);
+    case EPI_F32D: return launch_impl2<BLOCK_N, EPI_F32D>(p, maps, a, n_tiles_n, b, num_sms, stream);
     default: return launch_impl2<BLOCK_N, EPI_GENERIC>(p, maps, a, n_tiles_n, b, num_sms, stream);
   }
 }
