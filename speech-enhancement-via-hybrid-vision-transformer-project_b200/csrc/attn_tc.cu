@@ -129,6 +129,7 @@ __device__ __forceinline__ float exp_pack_row(uint32_t (&s)[128], float scale_lo
   return (sum0.x + sum0.y) + (sum1.x + sum1.y);
 }
 
+template <bool PROF>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out, int N,
                int D, int heads, int n_items, float scale_log2, int f16, long long* prof) {
@@ -165,11 +166,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
   }
   if (warp == 9 && lane == 0) {
     mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
+    mbar_init(q_empty, 2);
     for (int s = 0; s < KV_STAGES; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&v_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
+      mbar_init(&kv_empty[s], 2);
     }
     for (int w = 0; w < 2; ++w) {
       mbar_init(&s_full[w], 1);
@@ -218,15 +219,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
           }
         }
       }
-    } else if (warp == 9) {
-      // ------------------------------------------------------------ MMA issuer
+    } else if (warp == 9 || warp == 10) {
+      // ------------------------------------------------------------ MMA issuers: warp 9 serves softmax group A,
+      // warp 10 group B.  One issuing thread per group keeps the two S -> softmax -> PV chains independent (a single
+      // in-order issuer waits on one group's barrier while the other group's MMA is already due, which locks the two
+      // groups' MUFU-bound exp phases together); the tensor core serialises the MMAs of the two threads by itself.
+      // Barriers shared by both chains (q_empty, kv_empty) count one commit per issuer.
       if (elect_one()) {
+        const int w = warp - 9;
         const uint32_t idesc_s = make_idesc_16(128, 128, 0, 0, f16);   // Q (K-major) x K (K-major)
         const uint32_t idesc_pv = make_idesc_16(128, 64, 0, 1, f16);   // P (K-major) x V (MN-major)
         uint32_t it = 0, kv = 0;
-        uint32_t blk[2] = {0, 0};   // key blocks processed so far per softmax group (barrier phases)
-        uint32_t itw[2] = {0, 0};   // items processed so far per softmax group
-        auto issue_s = [&](int w, uint32_t kvi) {
+        uint32_t blk = 0;   // key blocks processed so far by this softmax group (barrier phases)
+        uint32_t itw = 0;   // items processed so far by this softmax group
+        auto issue_s = [&](uint32_t kvi) {
           const int st = kvi % KV_STAGES;
           mbar_wait(&k_full[st], (kvi / KV_STAGES) & 1);
           tc_fence_after();
@@ -241,46 +247,47 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
           int b, h, q0;
           decode(item, b, h, q0);
-          const int nw = (q0 + 128 < N) ? 2 : 1;
-          mbar_wait(q_full, it & 1);
-          for (int w = 0; w < nw; ++w) {
-            if (blk[w] > 0) {  // the group's last score block of its previous item has left TMEM
-              mbar_wait(&s_free[w], (blk[w] - 1) & 1);
-              tc_fence_after();
+          if (w == 1 && !(q0 + 128 < N)) {  // no second query tile: only keep the shared barriers' counts
+            // (each arrival waits for the matching "full" phase first, so it can never land in an earlier phase)
+            mbar_wait(q_full, it & 1);
+            mbar_arrive(q_empty);
+            for (int j = 0; j < nkv; ++j, ++kv) {
+              mbar_wait(&k_full[kv % KV_STAGES], (kv / KV_STAGES) & 1);
+              mbar_arrive(&kv_empty[kv % KV_STAGES]);
             }
-            issue_s(w, kv);
+            continue;
           }
+          mbar_wait(q_full, it & 1);
+          if (blk > 0) {  // the group's last score block of its previous item has left TMEM
+            mbar_wait(&s_free[w], (blk - 1) & 1);
+            tc_fence_after();
+          }
+          issue_s(kv);
           if (nkv == 1) umma_commit(q_empty);
           for (int j = 0; j < nkv; ++j, ++kv) {
             const int st = kv % KV_STAGES;
-            if (j + 1 < nkv) {
-              for (int w = 0; w < nw; ++w) {  // S_w(j+1) as soon as the softmax group has S_w(j) in registers
-                mbar_wait(&s_free[w], (blk[w] + j) & 1);
-                tc_fence_after();
-                issue_s(w, kv + 1);
-              }
-              if (j + 2 == nkv) umma_commit(q_empty);  // last S MMAs of this item issued
+            if (j + 1 < nkv) {  // S_w(j+1) as soon as the softmax group has S_w(j) in registers
+              mbar_wait(&s_free[w], (blk + j) & 1);
+              tc_fence_after();
+              issue_s(kv + 1);
+              if (j + 2 == nkv) umma_commit(q_empty);  // last S MMA of this item issued
             }
             mbar_wait(&v_full[st], (kv / KV_STAGES) & 1);
-            for (int w = 0; w < nw; ++w) {
-              mbar_wait(&p_full[w], (blk[w] + j) & 1);
-              if (j == 0 && itw[w] > 0) mbar_wait(&o_free[w], (itw[w] - 1) & 1);  // previous item's O_w read out
-              tc_fence_after();
-              const uint32_t p_addr = smem_u32(smem + OFF_P + w * 2 * TILE_BYTES);
-              const uint32_t v_addr = smem_u32(smem + OFF_V + st * TILE_BYTES);
+            mbar_wait(&p_full[w], (blk + j) & 1);
+            if (j == 0 && itw > 0) mbar_wait(&o_free[w], (itw - 1) & 1);  // previous item's O_w read out
+            tc_fence_after();
+            const uint32_t p_addr = smem_u32(smem + OFF_P + w * 2 * TILE_BYTES);
+            const uint32_t v_addr = smem_u32(smem + OFF_V + st * TILE_BYTES);
 #pragma unroll
-              for (int k = 0; k < 8; ++k)
-                umma_bf16(tmem_base + 256 + w * 64,
-                          make_smem_desc_sw128(p_addr + (k >> 2) * TILE_BYTES + (k & 3) * 32, 1024, 16),
-                          make_smem_desc_sw128(v_addr + k * 2048, 1024, 1024), idesc_pv, (j | k) != 0 ? 1u : 0u);
-              umma_commit(&pv_done[w]);
-            }
-            umma_commit(&kv_empty[st]);  // K / V stage free once everything issued so far has completed
+            for (int k = 0; k < 8; ++k)
+              umma_bf16(tmem_base + 256 + w * 64,
+                        make_smem_desc_sw128(p_addr + (k >> 2) * TILE_BYTES + (k & 3) * 32, 1024, 16),
+                        make_smem_desc_sw128(v_addr + k * 2048, 1024, 1024), idesc_pv, (j | k) != 0 ? 1u : 0u);
+            umma_commit(&pv_done[w]);
+            umma_commit(&kv_empty[st]);  // this group's share: K / V stage free once both groups' MMAs completed
           }
-          for (int w = 0; w < nw; ++w) {
-            blk[w] += nkv;
-            ++itw[w];
-          }
+          blk += nkv;
+          ++itw;
         }
       }
     }
@@ -301,7 +308,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
     const float unbias = f16 ? 1.925929944387236e-34f /* 2^-112 */ : 1.0f;
     uint32_t blk = 0, itw = 0;
     long long t_sfull = 0, t_ld = 0, t_max = 0, t_pv = 0, t_exp = 0, t_arr = 0, t_fin = 0;
-    const long long T0 = clock64();
+    auto tick = [&]() -> long long { return PROF ? clock64() : 0ll; };
+    const long long T0 = tick();
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       int b, h, q0;
@@ -311,10 +319,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
       float m_used = -INFINITY, l_run = 0.f;
       for (int j = 0; j < nkv; ++j, ++blk) {
         const int nvalid = min(128, N - j * 128);
-        const long long c0 = clock64();
+        const long long c0 = tick();
         mbar_wait(&s_full[w], blk & 1);
         tc_fence_after();
-        const long long c1 = clock64();
+        const long long c1 = tick();
         uint32_t s[128];
         {
           uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
@@ -332,7 +340,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
         }
         tc_fence_before();
         mbar_arrive(&s_free[w]);  // the MMA warp may overwrite S_w with the next block
-        const long long c2 = clock64();
+        const long long c2 = tick();
         if (nvalid < 128) {
 #pragma unroll
           for (int i = 0; i < 128; ++i)
@@ -349,7 +357,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
         }
         const float mnew =
             fmaxf(max3(mr[0], mr[1], mr[2]), max3(max3(mr[3], mr[4], mr[5]), mr[6], mr[7])) * scale_log2;
-        const long long c3 = clock64();
+        const long long c3 = tick();
         if (j == 0) {
           m_used = mnew;
         } else {
@@ -372,18 +380,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
             tmem_st_wait();
           }
         }
-        const long long c4 = clock64();
+        const long long c4 = tick();
         l_run += exp_pack_row(s, scale_log2, m_used + ebias, emul, p_row, sw);
-        const long long c5 = clock64();
+        const long long c5 = tick();
         fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor-core async proxy
         tc_fence_before();
         mbar_arrive(&p_full[w]);
-        const long long c6 = clock64();
+        const long long c6 = tick();
         t_sfull += c1 - c0; t_ld += c2 - c1; t_max += c3 - c2; t_pv += c4 - c3; t_exp += c5 - c4; t_arr += c6 - c5;
       }
 
       // ---- end of item: O_w / l -> 16-bit -> swizzled staging -> TMA store (clipped at N)
-      const long long f0 = clock64();
+      const long long f0 = tick();
       mbar_wait(&pv_done[w], (blk - 1) & 1);
       tc_fence_after();
       const float inv = (1.0f / l_run) * unbias;
@@ -415,12 +423,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
         tma_store_commit();
       }
       ++itw;
-      t_fin += clock64() - f0;
+      t_fin += tick() - f0;
     }
     if (sub == 0 && lane == 0) tma_store_wait_all();
-    if (prof != nullptr && row == 0) {
+    if (PROF && prof != nullptr && row == 0) {
       long long* pp = prof + blockIdx.x * 32 + w * 16;
-      pp[0] = t_sfull; pp[1] = t_ld; pp[2] = t_max; pp[3] = t_pv; pp[4] = t_exp; pp[5] = t_arr; pp[6] = clock64() - T0;
+      pp[0] = t_sfull; pp[1] = t_ld; pp[2] = t_max; pp[3] = t_pv; pp[4] = t_exp; pp[5] = t_arr; pp[6] = tick() - T0;
       pp[7] = itw; pp[8] = t_fin;
     }
   }
@@ -441,7 +449,8 @@ int launch_attn_tc(const CUtensorMap& tmap_qkv, const CUtensorMap& tmap_out, int
   static bool configured = false;
   static int sms = 148;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     if (e != cudaSuccess) {
       set_error("attn_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return -4;
@@ -458,8 +467,11 @@ int launch_attn_tc(const CUtensorMap& tmap_qkv, const CUtensorMap& tmap_out, int
     return -1;
   }
   const int grid = items < sms ? static_cast<int>(items) : sms;
-  const cudaError_t le = launch_pdl(attn_tc_kernel, dim3(grid), dim3(AT_THREADS), AT_SMEM, stream, tmap_qkv, tmap_out, N, D,
-                                    heads, static_cast<int>(items), scale * 1.4426950408889634f, f16, prof);
+  const cudaError_t le =
+      prof != nullptr ? launch_pdl(attn_tc_kernel<true>, dim3(grid), dim3(AT_THREADS), AT_SMEM, stream, tmap_qkv, tmap_out,
+                                   N, D, heads, static_cast<int>(items), scale * 1.4426950408889634f, f16, prof)
+                      : launch_pdl(attn_tc_kernel<false>, dim3(grid), dim3(AT_THREADS), AT_SMEM, stream, tmap_qkv, tmap_out,
+                                   N, D, heads, static_cast<int>(items), scale * 1.4426950408889634f, f16, prof);
   if (le != cudaSuccess) {
     set_error("attn_tc: %s", cudaGetErrorString(le));
     return -4;

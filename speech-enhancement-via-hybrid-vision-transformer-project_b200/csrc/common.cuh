@@ -254,6 +254,22 @@ __device__ __forceinline__ void umma_16_2sm(uint32_t d_tmem, uint64_t adesc, uin
       : "memory");
 }
 
+// same, operand descriptors given as (low, high) 32-bit words
+__device__ __forceinline__ void umma_16_2sm_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // Shared-memory matrix descriptor, 128-byte swizzle (layout_type = 2), descriptor version 1 (sm_100).
 //   K-major operand : rows of 64 bf16 (128 B), 8-row atoms of 1024 B; sbo = byte stride between 8-row groups.
 //   MN-major operand: rows (one k each) of 64 contiguous mn elements; sbo = byte stride between 8-k groups,

@@ -131,6 +131,15 @@ __device__ __forceinline__ void tile_out_coords(const IgemmParams& p, const Tile
   }
 }
 
+// max of two packed 16-bit pairs (fp16x2 or bf16x2)
+template <bool F16>
+__device__ __forceinline__ uint32_t max_16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  if (F16) asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  else asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+
 // 32 accumulator columns -> 64 bytes of this thread's 128-byte staging row (16-bit output).
 // sc / sh: shared-memory per-channel constants of these 32 columns; half: which 64-byte half of the row.
 template <int EPI, bool F16>
@@ -153,6 +162,30 @@ __device__ __forceinline__ void emit16(const uint32_t (&cur)[32], const float* s
       v[4 * q + 2] = fmaf(__uint_as_float(cur[4 * q + 2]), a.z, b.z);
       v[4 * q + 3] = fmaf(__uint_as_float(cur[4 * q + 3]), a.w, b.w);
     }
+  }
+  if (EPI == EPI_BNPOOL16 || EPI == EPI_SHPOOL16) {
+    // 2x2 max-pool on the PACKED 16-bit values: rounding is monotonic, so max(round(a), round(b)) == round(max(a, b))
+    // and relu commutes with both - bit-identical to pooling in fp32, with half the shuffles (the warp shuffle unit,
+    // ~1 instruction per clock and SM, bounds this epilogue: 1 024 -> 512 shuffles per 128 x 128 tile)
+    uint32_t u[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) u[e] = F16 ? pack_f16x2(v[2 * e], v[2 * e + 1]) : pack_bf16x2(v[2 * e], v[2 * e + 1]);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      u[e] = max_16x2<F16>(u[e], __shfl_xor_sync(0xFFFFFFFFu, u[e], 1));
+      u[e] = max_16x2<F16>(u[e], __shfl_xor_sync(0xFFFFFFFFu, u[e], hxor));
+    }
+    if (relu_lo == 0.0f) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) u[e] = max_16x2<F16>(u[e], 0u);
+    }
+    if (writer) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(row + (((half * 4 + q) ^ sw) << 4)) =
+            make_uint4(u[4 * q + 0], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
+    }
+    return;
   }
   if (EPI == EPI_GELU16) {
 #pragma unroll
@@ -605,7 +638,7 @@ struct CfgH {
   static constexpr int A_STAGES = BLOCK_N == 256 ? 2 : 3;
   static constexpr int B_HALF_ROWS = BLOCK_N / 2;
   static constexpr int B_STAGE_BYTES = B_HALF_ROWS * BLOCK_K * 2;
-  static constexpr int B_STAGES = BLOCK_N == 256 ? 6 : 8;
+  static constexpr int B_STAGES = BLOCK_N == 256 ? 6 : (UP2 ? 8 : 9);  // 9 = all taps of a 64-channel conv (resident mode)
   // UP2 (nearest x2 + 3x3 as four parity 2x2 convs): the four parity outputs of a low-resolution tile share ONE halo
   // tile and accumulate side by side in TMEM (4 * BLOCK_N columns per stage; a single stage when BLOCK_N = 128)
   static constexpr int NPAR = UP2 ? 4 : 1;
@@ -661,6 +694,9 @@ igemm_halo_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, i
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
   const int cblocks = p.Cin / BLOCK_K;
+  // all weight tiles of the layer fit the ring and every tile of this CTA pair uses the same ones (64 input channels,
+  // one n-tile: encoder.1): load them once and keep them - no per-tap barrier traffic, a quarter of the L2 reads
+  const bool resident = C::NPAR * C::NTAP == C::B_STAGES && cblocks == 1 && n_tiles_n == 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a);
@@ -696,67 +732,139 @@ igemm_halo_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, i
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
     if (elect_one()) {
-      uint32_t ai = 0, bi = 0;  // halo tiles / weight tiles issued so far
+      const bool prof = p.prof != nullptr;
+      int as = 0, bs = 0;                  // ring slots (running counters: no modulo in the loop)
+      uint32_t a_par = 1, b_par = 1;       // parity to wait for on the "empty" barriers
+      bool first = true;
+      long long pw_a = 0, pw_b = 0;
+      const long long pt0 = clock64();
       for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
         const TileCoord c = decode_ctile(p, ct, n_tiles_n, BLOCK_N, pairs_per_group, rank);
         const int b_row = c.n0 + rank * C::B_HALF_ROWS;
-        for (int cb = 0; cb < cblocks; ++cb, ++ai) {
-          const int as = ai % C::A_STAGES;
-          mbar_wait(&a_empty[as], ((ai / C::A_STAGES) & 1) ^ 1);
+        for (int cb = 0; cb < cblocks; ++cb) {
+          if (prof) {
+            const long long t = clock64();
+            mbar_wait(&a_empty[as], a_par);
+            pw_a += clock64() - t;
+          } else {
+            mbar_wait(&a_empty[as], a_par);
+          }
           if (rank == 0) mbar_expect_tx(&a_full[as], 2 * C::HALO_BYTES);
           tma_load_5d_2sm(smem + C::OFF_A + as * C::HALO_BYTES, &maps.a, &a_full[as], 0, c.w0 - 1, c.h0 - 1, cb * 8, c.b);
-          for (int pt = 0; pt < C::NPAR * C::NTAP; ++pt, ++bi) {
+          if (++as == C::A_STAGES) {
+            as = 0;
+            a_par ^= 1;
+          }
+          if (resident && !first) continue;  // the weight tiles of the first tile stay in their ring slots
+#pragma unroll
+          for (int pt = 0; pt < C::NPAR * C::NTAP; ++pt) {
             const int par = pt / C::NTAP, tap = pt % C::NTAP;
-            const int bs = bi % C::B_STAGES;
-            mbar_wait(&b_empty[bs], ((bi / C::B_STAGES) & 1) ^ 1);
+            if (prof) {
+              const long long t = clock64();
+              mbar_wait(&b_empty[bs], b_par);
+              pw_b += clock64() - t;
+            } else {
+              mbar_wait(&b_empty[bs], b_par);
+            }
             if (rank == 0) mbar_expect_tx(&b_full[bs], 2 * C::B_STAGE_BYTES);
             tma_load_2d_2sm(smem + C::OFF_B + bs * C::B_STAGE_BYTES, &maps.b, &b_full[bs], (tap * cblocks + cb) * BLOCK_K,
                             par * p.N + b_row);
+            if (++bs == C::B_STAGES) {
+              bs = 0;
+              b_par ^= 1;
+            }
           }
         }
+        first = false;
+      }
+      if (prof) {
+        p.prof[blockIdx.x * 16 + 0] = pw_a;
+        p.prof[blockIdx.x * 16 + 1] = pw_b;
+        p.prof[blockIdx.x * 16 + 2] = clock64() - pt0;
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (one thread of the leader CTA)
+    // At BLOCK_N <= 128 the four MMAs of a tap take 128-256 cycles, so this thread's own instruction stream is on the
+    // critical path (measured: 420 cycles per tap with a rolled loop that rebuilt both descriptors and divided by
+    // NTAP): the tap loop is fully unrolled, descriptors are a 32-bit add of a compile-time offset to a per-slot
+    // base word, ring slots are running counters.
     if (rank == 0 && elect_one()) {
+      const bool prof = p.prof != nullptr;
       const uint32_t idesc = make_idesc_16(2 * BLOCK_M, BLOCK_N, 0, 0, p.f16);
-      uint32_t ai = 0, bi = 0;
+      // descriptor words: lo = start address >> 4 | LBO >> 4 << 16, hi = SBO >> 4 | 1 << 14 (| 128B swizzle << 29)
+      constexpr uint32_t A_HI = static_cast<uint32_t>((C::WW * 16) >> 4) | (1u << 14);
+      constexpr uint32_t A_LBO = static_cast<uint32_t>(C::PLANE >> 4) << 16;
+      constexpr uint32_t B_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+      constexpr uint32_t B_LBO = (16u >> 4) << 16;
+      const uint32_t a_lo_base = ((smem_u32(smem + C::OFF_A) & 0x3FFFFu) >> 4) | A_LBO;
+      const uint32_t b_lo_base = ((smem_u32(smem + C::OFF_B) & 0x3FFFFu) >> 4) | B_LBO;
+      int as = 0, bs = 0;
+      uint32_t a_par = 0, b_par = 0;
+      bool first = true;
       int acc = 0;
       uint32_t acc_phase = 0;
+      long long mw_e = 0, mw_a = 0, mw_b = 0, m_tiles = 0;
+      const long long mt0 = clock64();
       for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
+        long long t = prof ? clock64() : 0;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        if (prof) mw_e += clock64() - t;
+        ++m_tiles;
         tc_fence_after();
-        for (int cb = 0; cb < cblocks; ++cb, ++ai) {
-          const int as = ai % C::A_STAGES;
-          mbar_wait(&a_full[as], (ai / C::A_STAGES) & 1);
+        const uint32_t d_acc = tmem_base + acc * C::ACC_COLS;
+        for (int cb = 0; cb < cblocks; ++cb) {
+          t = prof ? clock64() : 0;
+          mbar_wait(&a_full[as], a_par);
+          if (prof) mw_a += clock64() - t;
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + C::OFF_A + as * C::HALO_BYTES);
-          for (int pt = 0; pt < C::NPAR * C::NTAP; ++pt, ++bi) {
+          const uint32_t a_lo = a_lo_base + as * (C::HALO_BYTES >> 4);
+#pragma unroll
+          for (int pt = 0; pt < C::NPAR * C::NTAP; ++pt) {
             const int par = pt / C::NTAP, tap = pt % C::NTAP;
-            const uint32_t d_tmem = tmem_base + acc * C::ACC_COLS + par * BLOCK_N;
-            const int bs = bi % C::B_STAGES;
-            mbar_wait(&b_full[bs], (bi / C::B_STAGES) & 1);
-            tc_fence_after();
-            const uint32_t b_addr = smem_u32(smem + C::OFF_B + bs * C::B_STAGE_BYTES);
+            if (!resident || first) {
+              if (prof) {
+                t = clock64();
+                mbar_wait(&b_full[bs], b_par);
+                mw_b += clock64() - t;
+              } else {
+                mbar_wait(&b_full[bs], b_par);
+              }
+              tc_fence_after();
+            }
+            const uint32_t b_lo = b_lo_base + bs * (C::B_STAGE_BYTES >> 4);
             // tap position in halo coordinates (tile pixel (h, w) sits at (h + 1, w + 1)):
             // conv: (h + ky, w + kx); parity (py, px) of the x2 upsample, tap (a, b): (h + a + py, w + b + px)
             const int dy = UP2 ? (tap >> 1) + (par >> 1) : tap / 3, dx = UP2 ? (tap & 1) + (par & 1) : tap % 3;
-            const uint32_t a_tap = a_addr + (dy * C::WW + dx) * 16;
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              const uint64_t adesc = make_smem_desc_nosw(a_tap + k * 2 * C::PLANE, C::WW * 16, C::PLANE);
-              const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * UMMA_K * 2, 1024, 16);
-              umma_16_2sm(d_tmem, adesc, bdesc, idesc, (cb | tap | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_16_2sm_lh(d_acc + par * BLOCK_N, a_lo + (((dy * C::WW + dx) * 16 + k * 2 * C::PLANE) >> 4), A_HI,
+                             b_lo + ((k * UMMA_K * 2) >> 4), B_HI, idesc, (tap | k) != 0 ? 1u : (cb != 0 ? 1u : 0u));
+            if (!resident) umma_commit_2sm(&b_empty[bs], 3);
+            if (++bs == C::B_STAGES) {
+              bs = 0;
+              b_par ^= 1;
             }
-            umma_commit_2sm(&b_empty[bs], 3);
           }
           umma_commit_2sm(&a_empty[as], 3);
+          if (++as == C::A_STAGES) {
+            as = 0;
+            a_par ^= 1;
+          }
         }
+        first = false;
         umma_commit_2sm(&tmem_full[acc], 3);
         if (++acc == C::ACC_STAGES) {
           acc = 0;
           acc_phase ^= 1;
         }
+      }
+      if (prof) {
+        p.prof[blockIdx.x * 16 + 3] = mw_e;
+        p.prof[blockIdx.x * 16 + 4] = mw_a;
+        p.prof[blockIdx.x * 16 + 5] = mw_b;
+        p.prof[blockIdx.x * 16 + 6] = clock64() - mt0;
+        p.prof[blockIdx.x * 16 + 9] = m_tiles;
       }
     }
   } else {
@@ -787,11 +895,15 @@ igemm_halo_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, i
     uint32_t it = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    long long ew_full = 0, e_ld = 0, e_emit = 0, e_st = 0;
+    const long long et0 = clock64();
     for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
       const TileCoord c = decode_ctile(p, ct, n_tiles_n, BLOCK_N, pairs_per_group, rank);
       int o1, o2, o3;
       tile_out_coords(p, c, pool, o1, o2, o3);
+      const long long t = p.prof ? clock64() : 0;
       mbar_wait(&tmem_full[acc], acc_phase);
+      if (p.prof) ew_full += clock64() - t;
       tc_fence_after();
       for (int par = 0; par < C::NPAR; ++par) {
         const uint32_t t_base =
@@ -803,16 +915,23 @@ igemm_halo_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, i
           const float* sc = cscale + c.n0 + blk * 64 + half * 32;
           const float* sh = cshift + c.n0 + blk * 64 + half * 32;
           uint32_t ra[32];
+          const long long q0 = p.prof ? clock64() : 0;
           tmem_ld32(t_base + blk * 64, ra);
           tmem_ld_wait(ra);
+          const long long q1 = p.prof ? clock64() : 0;
           if (p.f16) emit16<EPI, true>(ra, sc, sh, p, relu_lo, row, half, sw, writer, 8);
           else emit16<EPI, false>(ra, sc, sh, p, relu_lo, row, half, sw, writer, 8);
+          const long long q2 = p.prof ? clock64() : 0;
           fence_proxy_async_smem();
           if (issuer) tma_store_wait_read0();
           named_bar_sync(1 + grp, 256);
           if (issuer) {
             tma_store_4d(&maps.out[par], buf, c.n0 + blk * 64, o1, o2, o3);
             tma_store_commit();
+          }
+          if (p.prof) {
+            const long long q3 = clock64();
+            e_ld += q1 - q0; e_emit += q2 - q1; e_st += q3 - q2;
           }
           ++it;
         }
@@ -826,6 +945,13 @@ igemm_halo_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, i
       }
     }
     if (issuer) tma_store_wait_all();
+    if (p.prof && ew == 0 && lane == 0) {
+      p.prof[blockIdx.x * 16 + 7] = ew_full;
+      p.prof[blockIdx.x * 16 + 8] = clock64() - et0;
+      p.prof[blockIdx.x * 16 + 10] = e_ld;
+      p.prof[blockIdx.x * 16 + 11] = e_emit;
+      p.prof[blockIdx.x * 16 + 12] = e_st;
+    }
   }
 
   tc_fence_before();
@@ -1001,6 +1127,15 @@ int launch_igemm_tc2(const IgemmParams& p, const IgemmMaps& maps, int block_n, i
       ++n;
     }
     for (int k = 0; k < 16; ++k) s[k] /= (n > 0 ? n : 1);
+    if (pp.halo) {
+      fprintf(stderr,
+              "[halo prof mode=%d M=%d N=%d K=%d bn=%d epi=%d] tiles/cta %.1f | producer wait_a_empty %.0f wait_b_empty %.0f "
+              "total %.0f | mma wait_tmem_empty %.0f wait_a_full %.0f wait_b_full %.0f total %.0f | epi wait_full %.0f ld %.0f "
+              "emit %.0f fence+bar+store %.0f total %.0f (cycles, leader CTAs)\n",
+              p.mode, p.M, p.N, p.K, block_n, pick_epi(pp), s[9], s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], s[10],
+              s[11], s[12], s[8]);
+      return r;
+    }
     fprintf(stderr,
             "[igemm prof mode=%d M=%d N=%d K=%d bn=%d epi=%d] tiles/cta %.1f | producer wait_empty %.0f total %.0f | mma "
             "wait_tmem_empty %.0f wait_full %.0f total %.0f | epi cst %.0f wait_full %.0f blocks %.0f total %.0f (cycles)\n",

@@ -3,7 +3,7 @@ import sys, torch
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
 import gpu_util as U
 from hvit_b200 import _lib
-for (B, N, h) in [(64, 496, 8), (64, 1248, 8), (8, 112, 8)]:
+for (B, N, h) in [(64, 496, 8), (64, 1248, 8), (8, 112, 8), (512, 128, 8)]:
     qkv = torch.randn(B * N, 3 * h * 64, device='cuda').half()
     out = torch.empty(B * N, h * 64, device='cuda', dtype=torch.float16)
     f = lambda: _lib.check(U.lib().hvit_attention_16(U.P(qkv), U.P(out), B, N, h, 1, U.stream()), "attn")
