@@ -73,18 +73,21 @@ struct TileCoord {
 __device__ __forceinline__ TileCoord decode_ctile(const IgemmParams& p, int ct, int n_tiles_n, int block_n,
                                                   int pairs_per_group, int rank) {
   TileCoord c;
-  c.n0 = (ct % n_tiles_n) * block_n;
-  const int pr = ct / n_tiles_n;
-  const int g = pr / pairs_per_group;
-  int i = 2 * (pr - g * pairs_per_group) + rank;
+  int pr, nt, g, ig;
+  fast_divmod(p.fd_ntn, ct, pr, nt);
+  c.n0 = nt * block_n;
+  fast_divmod(p.fd_ppg, pr, g, ig);
+  int i = 2 * ig + rank;
   c.m0 = 0; c.b = 0; c.h0 = 0; c.w0 = 0; c.par = g;
   if (p.mode == IG_PLAIN) {
     c.m0 = i * BLOCK_M;  // >= M for the padding tile: zero fill on load, clipped on store
   } else {
-    c.w0 = (i % p.tiles_w) * p.Wt;
-    i /= p.tiles_w;
-    c.h0 = (i % p.tiles_h) * p.Ht;
-    c.b = i / p.tiles_h;  // == B for the padding tile
+    int tw, th;
+    fast_divmod(p.fd_tw, i, i, tw);
+    c.w0 = tw * p.Wt;
+    fast_divmod(p.fd_th, i, i, th);
+    c.h0 = th * p.Ht;
+    c.b = i;  // == B for the padding tile
   }
   return c;
 }
@@ -1107,6 +1110,10 @@ int launch_igemm_tc2(const IgemmParams& p, const IgemmMaps& maps, int block_n, i
     return -1;
   }
   const int a = static_cast<int>(nct), b = static_cast<int>(pairs_per_group);
+  pp.fd_ntn = make_fastdiv(n_tiles_n);
+  pp.fd_ppg = make_fastdiv(b);
+  pp.fd_tw = make_fastdiv(p.mode == IG_PLAIN ? 1 : p.tiles_w);
+  pp.fd_th = make_fastdiv(p.mode == IG_PLAIN ? 1 : p.tiles_h);
   if (getenv("HVIT_PROF") != nullptr && pp.prof == nullptr) {
     // diagnostics: per-role cycle counters of this launch (mean over the leader CTAs), printed to stderr
     long long* d = nullptr;

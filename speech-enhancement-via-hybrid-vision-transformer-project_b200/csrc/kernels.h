@@ -22,6 +22,34 @@ enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
 // activation storage type of a plan: fp32 (CUDA-core mode) or one of the two 16-bit tensor-core operand types
 enum { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
 
+// Division by a launch-time constant without the ~100-cycle integer-division sequence (the tile decode sits on the
+// epilogue warps' critical path once per tile): q = umulhi(n, mul) >> shr for 0 <= n < 2^31, with
+// mul = ceil(2^(31 + ceil_log2 d) / d), shr = ceil_log2 d - 1; d == 1 is the identity.
+struct FastDiv {
+  unsigned mul, shr;
+  int d;
+};
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = d;
+  f.mul = 0;
+  f.shr = 0;
+  if (d > 1) {
+    int l = 0;
+    while ((1ll << l) < d) ++l;
+    const unsigned long long p2 = 1ull << (31 + l);
+    f.mul = static_cast<unsigned>((p2 + static_cast<unsigned long long>(d) - 1) / static_cast<unsigned long long>(d));
+    f.shr = static_cast<unsigned>(l - 1);
+  }
+  return f;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void fast_divmod(const FastDiv& f, int n, int& q, int& r) {
+  q = f.d == 1 ? n : static_cast<int>(__umulhi(static_cast<unsigned>(n), f.mul) >> f.shr);
+  r = n - q * f.d;
+}
+#endif
+
 struct IgemmParams {
   int mode;
   int M, N, K;          // IG_PLAIN: M rows. All modes: N output channels, K reduction length
@@ -53,6 +81,7 @@ struct IgemmParams {
   int halo;             // IG_CONV3 on the tensor-core path: input tile + halo staged once in shared memory (8x16 tile;
                         // maps.a is then the 5-D un-swizzled halo map), see igemm_halo_kernel
   long long* prof;      // diagnostics only (HVIT_PROF): per-CTA cycle counters [gridDim.x][16], or null
+  FastDiv fd_ntn, fd_ppg, fd_tw, fd_th;  // set by launch_igemm_tc2: n tiles, pairs per group, tiles_w, tiles_h
 };
 
 // tcgen05 path. A / Wt are described by TMA tensor maps built on the host (see tmap.cpp).
