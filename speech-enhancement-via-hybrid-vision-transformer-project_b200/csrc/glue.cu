@@ -13,7 +13,8 @@ namespace {
 constexpr int NFFT = 512;
 constexpr int HOP = 128;
 constexpr int NBIN = NFFT / 2 + 1;  // 257
-constexpr int FR = 8;               // frames per block (one warp each)
+constexpr int FR = 8;               // warps per block; every warp transforms a PAIR of frames
+constexpr int FRAMES = 2 * FR;      // frames per block
 constexpr int XS = 545;             // frame stride in float2: 512 + 32 in-frame padding + 1 (odd mod 16 -> the
                                     // 16-frame transposes are bank-conflict free)
 __device__ __forceinline__ int fpad(int i) { return i + (i >> 4); }  // in-frame padding against Stockham store conflicts
@@ -152,6 +153,8 @@ __global__ void fill_u32_kernel(unsigned* p, int n, unsigned v) {
 }
 
 // ------------------------------------------------------------------ STFT + |.| + per-clip max (enhancer.py:82-101)
+// Every warp transforms TWO real frames with one complex FFT (frame a in the real parts, frame b in the imaginary
+// parts): A[k] = (Z[k] + conj Z[N-k]) / 2, B[k] = (Z[k] - conj Z[N-k]) / 2i.  Half the butterflies per frame.
 __global__ void __launch_bounds__(FR * 32, 5) stft_kernel(const float* __restrict__ wave, int n, int T,
                                                        const unsigned* __restrict__ max_bits,
                                                        float2* __restrict__ spec, float* __restrict__ mag,
@@ -159,29 +162,35 @@ __global__ void __launch_bounds__(FR * 32, 5) stft_kernel(const float* __restric
   griddep_launch_dependents();
   griddep_wait();
   extern __shared__ float2 sm[];
-  float2* xs = sm;                // [FR][XS]
-  const int b = blockIdx.y, t0 = blockIdx.x * FR;
+  float2* xs = sm;                // [FR][XS]: one complex buffer per frame pair
+  const int b = blockIdx.y, t0 = blockIdx.x * FRAMES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float inv_mv = 1.0f / guard_scalar(max_bits[b]);
-  const int t = t0 + warp;
+  const int ta = t0 + 2 * warp;
   float2* x = xs + warp * XS;
-  if (t < T) {
+  if (ta < T) {
     const float* w = wave + static_cast<long long>(b) * n;
+    const bool has_b = ta + 1 < T;
     for (int i = lane; i < NFFT; i += 32) {
-      const int src = t * HOP - NFFT / 2 + i;  // centred frame, zero padding
-      float v = 0.f;
-      if (src >= 0 && src < n) v = (w[src] * inv_mv) * hann512(i);
-      x[fpad(i)] = make_float2(v, 0.f);
+      const int sa = ta * HOP - NFFT / 2 + i, sb = sa + HOP;  // centred frames, zero padding
+      const float h = hann512(i);
+      float va = 0.f, vb = 0.f;
+      if (sa >= 0 && sa < n) va = (w[sa] * inv_mv) * h;
+      if (has_b && sb >= 0 && sb < n) vb = (w[sb] * inv_mv) * h;
+      x[fpad(i)] = make_float2(va, vb);
     }
   }
   __syncwarp();
-  if (t < T) fft512_warp<false>(x, lane);
+  if (ta < T) fft512_warp<false>(x, lane);
   __syncthreads();
   float lmax = 0.f;
-  for (int idx = threadIdx.x; idx < NBIN * FR; idx += blockDim.x) {
-    const int tl = idx & (FR - 1), f = idx / FR;
+  for (int idx = threadIdx.x; idx < NBIN * FRAMES; idx += blockDim.x) {
+    const int tl = idx & (FRAMES - 1), f = idx / FRAMES;
     if (t0 + tl < T) {
-      const float2 z = xs[tl * XS + fpad(f)];
+      const float2* xw = xs + (tl >> 1) * XS;
+      const float2 z1 = xw[fpad(f)], z2 = xw[fpad((NFFT - f) & (NFFT - 1))];
+      const float2 z = (tl & 1) ? make_float2(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x))
+                                : make_float2(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
       const long long o = (static_cast<long long>(b) * NBIN + f) * T + t0 + tl;
       spec[o] = z;
       const float m = sqrtf(z.x * z.x + z.y * z.y);
@@ -224,42 +233,57 @@ __global__ void __launch_bounds__(FR * 32, 5) istft_frames_kernel(float* __restr
   griddep_wait();
   extern __shared__ float2 sm[];
   float2* xs = sm;
-  const int b = blockIdx.y, t0 = blockIdx.x * FR;
+  const int b = blockIdx.y, t0 = blockIdx.x * FRAMES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float mm = guard_scalar(mag_max_bits[b]);
+  // E(f, t) of one time-frequency bin
+  auto bin = [&](int f, int t) -> float2 {
+    const long long o = (static_cast<long long>(b) * NBIN + f) * T + t;
+    const float2 z = spec[o];
+    const float a = sqrtf(z.x * z.x + z.y * z.y);
+    float mo;
+    if (lowres != nullptr) {
+      const Lerp ly = make_lerp(f, Hs, NBIN), lx = make_lerp(t, Ws, T);
+      const float* src = lowres + static_cast<long long>(b) * Hs * Ws;
+      const float v00 = src[ly.i0 * Ws + lx.i0], v01 = src[ly.i0 * Ws + lx.i1];
+      const float v10 = src[ly.i1 * Ws + lx.i0], v11 = src[ly.i1 * Ws + lx.i1];
+      mo = ly.l0 * (lx.l0 * v00 + lx.l1 * v01) + ly.l1 * (lx.l0 * v10 + lx.l1 * v11);
+      model_out[o] = mo;
+    } else {
+      mo = model_out[o];
+    }
+    const float e = mo * mm;
+    const float ea = a > 0.f ? e / a : 0.f;
+    float2 E = a > 0.f ? make_float2(ea * z.x, ea * z.y) : make_float2(e, 0.f);
+    if (f == 0 || f == NFFT / 2) E.y = 0.f;  // c2r transforms ignore the imaginary part of DC / Nyquist
+    return E;
+  };
+  // Two frames per inverse FFT: Z = Ea + i Eb over the full (Hermitian-filled) spectrum; the real part of the
+  // transform is frame a, the imaginary part frame b.
   for (int idx = threadIdx.x; idx < NBIN * FR; idx += blockDim.x) {
-    const int tl = idx & (FR - 1), f = idx / FR;
-    if (t0 + tl < T) {
-      const long long o = (static_cast<long long>(b) * NBIN + f) * T + t0 + tl;
-      const float2 z = spec[o];
-      const float a = sqrtf(z.x * z.x + z.y * z.y);
-      float mo;
-      if (lowres != nullptr) {
-        const Lerp ly = make_lerp(f, Hs, NBIN), lx = make_lerp(t0 + tl, Ws, T);
-        const float* src = lowres + static_cast<long long>(b) * Hs * Ws;
-        const float v00 = src[ly.i0 * Ws + lx.i0], v01 = src[ly.i0 * Ws + lx.i1];
-        const float v10 = src[ly.i1 * Ws + lx.i0], v11 = src[ly.i1 * Ws + lx.i1];
-        mo = ly.l0 * (lx.l0 * v00 + lx.l1 * v01) + ly.l1 * (lx.l0 * v10 + lx.l1 * v11);
-        model_out[o] = mo;
-      } else {
-        mo = model_out[o];
-      }
-      const float e = mo * mm;
-      const float ea = a > 0.f ? e / a : 0.f;
-      float2 E = a > 0.f ? make_float2(ea * z.x, ea * z.y) : make_float2(e, 0.f);
-      if (f == 0 || f == NFFT / 2) E.y = 0.f;  // c2r transforms ignore the imaginary part of DC / Nyquist
-      float2* x = xs + tl * XS;
-      x[fpad(f)] = E;
-      if (f > 0 && f < NFFT / 2) x[fpad(NFFT - f)] = make_float2(E.x, -E.y);
+    const int q = idx & (FR - 1), f = idx / FR;
+    const int ta = t0 + 2 * q;
+    if (ta < T) {
+      const float2 Ea = bin(f, ta);
+      const float2 Eb = ta + 1 < T ? bin(f, ta + 1) : make_float2(0.f, 0.f);
+      float2* x = xs + q * XS;
+      x[fpad(f)] = make_float2(Ea.x - Eb.y, Ea.y + Eb.x);
+      if (f > 0 && f < NFFT / 2) x[fpad(NFFT - f)] = make_float2(Ea.x + Eb.y, Eb.x - Ea.y);
     }
   }
   __syncthreads();
-  const int t = t0 + warp;
-  if (t < T) {
+  const int ta = t0 + 2 * warp;
+  if (ta < T) {
     float2* x = xs + warp * XS;
     fft512_warp<true>(x, lane);
-    float* fr = frames + (static_cast<long long>(b) * T + t) * NFFT;
-    for (int i = lane; i < NFFT; i += 32) fr[i] = x[fpad(i)].x * (1.0f / NFFT) * hann512(i);
+    float* fa = frames + (static_cast<long long>(b) * T + ta) * NFFT;
+    const bool has_b = ta + 1 < T;
+    for (int i = lane; i < NFFT; i += 32) {
+      const float2 v = x[fpad(i)];
+      const float h = hann512(i) * (1.0f / NFFT);
+      fa[i] = v.x * h;
+      if (has_b) fa[NFFT + i] = v.y * h;
+    }
   }
 }
 
@@ -749,7 +773,7 @@ int ensure_fft_tables(cudaStream_t s) {
 int launch_stft(const float* wave, int B, int n, int T, const float* max_val, float2* spec, float* mag,
                 unsigned* mag_max_bits, cudaStream_t s) {
   launch_pdl(fill_u32_kernel, dim3((B + 255) / 256), dim3(256), 0, s, mag_max_bits, B, 0u);
-  dim3 grid((T + FR - 1) / FR, B);
+  dim3 grid((T + FRAMES - 1) / FRAMES, B);
   launch_pdl(stft_kernel, dim3(grid), dim3(FR * 32), FFT_SMEM, s, wave, n, T, reinterpret_cast<const unsigned*>(max_val), spec, mag,
                                                mag_max_bits);
   return check_launch("stft");
@@ -760,7 +784,7 @@ static void fft_smem_config() {}
 int launch_istft_frames(float* model_out, const float* lowres, int Hs, int Ws, const float2* spec,
                         const unsigned* mag_max_bits, float* frames, int B, int T, cudaStream_t s) {
   fft_smem_config();
-  dim3 grid((T + FR - 1) / FR, B);
+  dim3 grid((T + FRAMES - 1) / FRAMES, B);
   launch_pdl(istft_frames_kernel, dim3(grid), dim3(FR * 32), FFT_SMEM, s, model_out, lowres, Hs, Ws, spec, mag_max_bits, T, frames);
   return check_launch("istft_frames");
 }
