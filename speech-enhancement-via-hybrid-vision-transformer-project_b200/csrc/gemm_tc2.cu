@@ -394,6 +394,14 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
     // ------------------------------------------------------------ MMA issuer (one thread of the leader CTA)
     if (rank == 0 && elect_one()) {
       const uint32_t idesc = make_idesc_16(2 * BLOCK_M, BLOCK_N, 0, 0, p.f16);
+      // This thread's own instruction stream competes with the epilogue warps for issue slots (fc1's GELU epilogue
+      // keeps the schedulers 70 % busy), so the loop is kept lean: descriptors are (lo, hi) words, lo = a per-stage
+      // base + a compile-time k offset; diagnostics flags are hoisted.
+      constexpr uint32_t D_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version bit 46, 128B swizzle
+      constexpr uint32_t D_LBO = (16u >> 4) << 16;
+      const uint32_t a_lo_base = ((smem_u32(smem) & 0x3FFFFu) >> 4) | D_LBO;
+      const bool prof = p.prof != nullptr;
+      const bool skip_mma = (p.dbg & 4) != 0;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -401,7 +409,7 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
       long long mw_e = 0, mw_f = 0;
       const long long mt0 = clock64();
       for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
-        if (p.prof) {
+        if (prof) {
           const long long t = clock64();
           mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
           mw_e += clock64() - t;
@@ -411,7 +419,7 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < kblocks; ++kb) {
-          if (p.prof) {
+          if (prof) {
             const long long t = clock64();
             mbar_wait(&full_bar[stage], phase);
             mw_f += clock64() - t;
@@ -419,13 +427,13 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
             mbar_wait(&full_bar[stage], phase);
           }
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+          const uint32_t a_lo = a_lo_base + stage * (C::STAGE_BYTES >> 4);
+          const uint32_t b_lo = a_lo + (A_STAGE_BYTES >> 4);
+          if (!skip_mma) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t adesc = make_smem_desc_sw128(a_addr + k * UMMA_K * 2, 1024, 16);
-            const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * UMMA_K * 2, 1024, 16);
-            if (!(p.dbg & 4)) umma_16_2sm(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_16_2sm_lh(d_tmem, a_lo + ((k * UMMA_K * 2) >> 4), D_HI, b_lo + ((k * UMMA_K * 2) >> 4), D_HI, idesc,
+                             k != 0 ? 1u : (kb != 0 ? 1u : 0u));
           }
           umma_commit_2sm(&empty_bar[stage], 3);  // stage free in both CTAs once these MMAs have read it
           if (++stage == C::STAGES) {
