@@ -3,6 +3,7 @@
 // iSTFT (inverse FFT, window, overlap-add, window-sum-square normalisation).
 // Reference arithmetic: inference/enhancer.py:55-135, models/components.py:15-99,160-167, models/hybrid_vit.py:367-389,458-465.
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -581,6 +582,38 @@ __device__ __forceinline__ void ld8<__half>(const __half* p, float* v) {
   }
 }
 
+// 16-bit variant of skip_sample_kernel with 8 channels (one 16-byte load per tap, one 16-byte store) per thread
+template <typename T>
+__global__ void skip_sample8_kernel(const T* __restrict__ src, int Hs, int HsPitch, int Ws, int C, int Hd, int Wd,
+                                    T* __restrict__ dst, long long total) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = C / 8;
+  const int c = static_cast<int>(idx % cv) * 8;
+  long long r = idx / cv;
+  const int wd = static_cast<int>(r % Wd);
+  r /= Wd;
+  const int hd = static_cast<int>(r % Hd);
+  const int b = static_cast<int>(r / Hd);
+  const Lerp ly = make_lerp(hd, Hs, Hd), lx = make_lerp(wd, Ws, Wd);
+  const T* base = src + static_cast<long long>(b) * HsPitch * Ws * C + c;
+  float v00[8], v01[8], v10[8], v11[8], o[8];
+  ld8<T>(base + (static_cast<long long>(ly.i0) * Ws + lx.i0) * C, v00);
+  ld8<T>(base + (static_cast<long long>(ly.i0) * Ws + lx.i1) * C, v01);
+  ld8<T>(base + (static_cast<long long>(ly.i1) * Ws + lx.i0) * C, v10);
+  ld8<T>(base + (static_cast<long long>(ly.i1) * Ws + lx.i1) * C, v11);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    o[j] = ly.l0 * (lx.l0 * v00[j] + lx.l1 * v01[j]) + ly.l1 * (lx.l0 * v10[j] + lx.l1 * v11[j]);
+  constexpr int f16 = sizeof(T) == 2 && !std::is_same<T, bf16>::value ? 1 : 0;
+  uint4 pk;
+  pk.x = pack_16x2(o[0], o[1], f16); pk.y = pack_16x2(o[2], o[3], f16);
+  pk.z = pack_16x2(o[4], o[5], f16); pk.w = pack_16x2(o[6], o[7], f16);
+  *reinterpret_cast<uint4*>(dst + ((static_cast<long long>(b) * Hd + hd) * Wd + wd) * C + c) = pk;
+}
+
 // 8 lanes per output pixel, each lane owns 8 channels (one 16-byte load per tap): a warp instruction reads 4 whole
 // 128-byte pixel vectors (4 L1 wavefronts instead of 32 with a pixel-per-lane mapping - ncu showed that version
 // L1-bound at 84 %).  The lane's 72 weights live in registers; the partial sums meet with three shuffles.
@@ -848,6 +881,17 @@ int launch_layernorm(const float* x, const float* g, const float* b, void* out, 
 
 int launch_skip_sample(const void* src, int dt, int B, int Hs, int HsPitch, int Ws, int C, int Hd, int Wd,
                        void* dst, cudaStream_t s) {
+  if (dt != DT_F32 && C % 8 == 0) {
+    const long long total8 = static_cast<long long>(B) * Hd * Wd * (C / 8);
+    const unsigned grid8 = static_cast<unsigned>((total8 + 255) / 256);
+    if (dt == DT_BF16)
+      launch_pdl(skip_sample8_kernel<bf16>, dim3(grid8), dim3(256), 0, s, reinterpret_cast<const bf16*>(src), Hs, HsPitch, Ws, C, Hd,
+                 Wd, reinterpret_cast<bf16*>(dst), total8);
+    else
+      launch_pdl(skip_sample8_kernel<__half>, dim3(grid8), dim3(256), 0, s, reinterpret_cast<const __half*>(src), Hs, HsPitch, Ws,
+                 C, Hd, Wd, reinterpret_cast<__half*>(dst), total8);
+    return check_launch("skip_sample");
+  }
   const long long total = static_cast<long long>(B) * Hd * Wd * (C / 4);
   const unsigned grid = static_cast<unsigned>((total + 255) / 256);
   if (dt == DT_BF16)
