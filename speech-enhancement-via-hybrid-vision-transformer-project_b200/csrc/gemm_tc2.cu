@@ -51,18 +51,25 @@ struct Cfg2 {
   static constexpr int B_HALF_ROWS = BLOCK_N / 2;
   static constexpr int B_STAGE_BYTES = B_HALF_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  // The GEMM main loops are sensitive to the ring depth (3 -> 4 stages: +10 %, 4 -> 5: +5 % on qkv).  Where the
-  // epilogue is far from critical - the plain 16-bit one (EPI_LIN16: qkv, to_feature_map, skip projections) and the
-  // fp32 one of long-K GEMMs (EPI_F32D: fc2) - each epilogue group gives up its second staging buffer (it waits for
-  // the previous TMA store to release the buffer) and the ring gets a fifth stage.
+  // The K = 512 GEMM main loops are bound by the ring's round trip (MMA done -> empty -> TMA issue -> L2 -> full:
+  // ~2 200 cycles against 512 MMA cycles per stage), i.e. by the bytes in flight, not by L2 bandwidth (a variant with
+  // the weights resident in shared memory - half the L2 traffic, 4 A stages - was no faster).  Measured: 3 -> 4
+  // stages +10 %, 4 -> 5 +5 %.  So shared memory goes to stages: the per-channel constants live in shared memory only
+  // for the CURRENT tile (two small buffers, by accumulator parity), and where the epilogue is far from critical -
+  // the plain 16-bit one (EPI_LIN16: qkv, to_feature_map, skip projections) and the fp32 one of long-K GEMMs
+  // (EPI_F32D: fc2) - each epilogue group gives up its second staging buffer (it waits for the previous TMA store
+  // to release the buffer).
   static constexpr bool DEEP = BLOCK_N == 256 && (EPI == 1 || EPI == 8);
   static constexpr int NBUF = DEEP ? 1 : 2;                   // staging buffers per epilogue group
-  static constexpr int STAGES = BLOCK_N == 256 ? (DEEP ? 5 : 4) : (BLOCK_N == 128 ? 6 : 7);
+  static constexpr bool HAS_SCALE = EPI == 0 || EPI == 3 || EPI == 4;  // epilogues with a per-channel multiplier
+  static constexpr int STAGES = BLOCK_N == 256 ? (HAS_SCALE ? 4 : (DEEP ? 6 : 5)) : (BLOCK_N == 128 ? 6 : 7);
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
   static constexpr int STAGING_BYTES = 2 * NBUF * STG_BUF_BYTES;    // [group][buffer]
-  static constexpr int CONST_N = DEEP ? 3072 : (BLOCK_N == 256 ? 4096 : 2048);  // scale[N] | shift[N] of the whole problem fit up to here
-  static constexpr int CONST_BYTES = 2 * CONST_N * 4;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + CONST_BYTES + 1024 + 512;
+  static constexpr int CONST_N = BLOCK_N;                           // shift (| scale) of one tile, x 2 buffers
+  static constexpr int CONST_BUF = (HAS_SCALE ? 2 : 1) * CONST_N;   // floats per buffer
+  static constexpr int CONST_BYTES = 2 * CONST_BUF * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + CONST_BYTES + 512;
+  static_assert(SMEM_BYTES <= 232448, "igemm_tc2: shared memory budget");
 };
 
 struct TileCoord {
@@ -279,6 +286,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, int num_ctiles, int n_tiles_n,
                  int pairs_per_group) {
   using C = Cfg2<BLOCK_N, EPI>;
+  const long long k_t0 = clock64();
   // (declared aligned instead of rounding the pointer up by hand: integer arithmetic on the address loses the
   // shared-memory address space and turns every staging store / constant load of the epilogue into a generic LD/ST)
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -328,6 +336,7 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
   const uint32_t tmem_base = *tmem_slot;
   griddep_launch_dependents();  // PDL: the next kernel's prologue may overlap this kernel ...
   griddep_wait();               // ... and everything above overlapped the previous kernel's tail
+  const long long k_t1 = clock64();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
@@ -477,18 +486,9 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
     const int sw = srow & 7;
     const float relu_lo = p.act == ACT_RELU ? 0.0f : -INFINITY;
 
-    // Per-channel constants of the whole problem -> shared memory once per CTA: cscale[n] | cshift[n], n < N.
-    // (N <= C::CONST_N; larger N reloads the tile's BLOCK_N constants per tile.)
-    float* cscale = reinterpret_cast<float*>(consts);
-    float* cshift = cscale + C::CONST_N;
-    const bool preload = p.N <= C::CONST_N;
-    if (preload) {
-      for (int e = ew * 32 + lane; e < p.N; e += NUM_EPI_WARPS * 32) {
-        cscale[e] = p.scale != nullptr ? __ldg(p.scale + e) : 1.0f;
-        cshift[e] = p.shift != nullptr ? __ldg(p.shift + e) : 0.0f;
-      }
-      named_bar_sync(3, NUM_EPI_WARPS * 32);
-    }
+    // Per-channel constants of the CURRENT tile in shared memory: [acc parity][scale BLOCK_N | shift BLOCK_N].  Every
+    // epilogue thread loads one channel of the tile before it waits for the accumulator; one named barrier per tile.
+    float* cbuf = reinterpret_cast<float*>(consts);
 
     uint32_t it = 0;  // running column-block counter of this group: buffer = it & 1, residual phase = (it >> 1) & 1
     int acc = 0;
@@ -503,16 +503,13 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
       tile_out_coords(p, c, pool, o1, o2, o3);
       const CUtensorMap* omap = &maps.out[c.par];
       const int r3 = p.res_mod > 0 ? 0 : o3;  // positional table: same rows for every clip
-      int cbase = c.n0;
-      if (!preload) {  // rare: N > C::CONST_N
-        named_bar_sync(3, NUM_EPI_WARPS * 32);  // everyone is done with the previous tile's constants
-        for (int e = ew * 32 + lane; e < BLOCK_N; e += NUM_EPI_WARPS * 32) {
-          cscale[e] = p.scale != nullptr ? __ldg(p.scale + c.n0 + e) : 1.0f;
-          cshift[e] = p.shift != nullptr ? __ldg(p.shift + c.n0 + e) : 0.0f;
-        }
-        named_bar_sync(3, NUM_EPI_WARPS * 32);
-        cbase = 0;
+      float* cshift = cbuf + acc * C::CONST_BUF;
+      float* cscale = C::HAS_SCALE ? cshift + C::CONST_N : cshift;  // (never read by the shift-only epilogues)
+      for (int e = ew * 32 + lane; e < BLOCK_N; e += NUM_EPI_WARPS * 32) {
+        if (C::HAS_SCALE) cscale[e] = p.scale != nullptr ? __ldg(p.scale + c.n0 + e) : 1.0f;
+        cshift[e] = p.shift != nullptr ? __ldg(p.shift + c.n0 + e) : 0.0f;
       }
+      constexpr int cbase = 0;
       if (has_res && issuer && J > 0) {
         // residual tile of the first block -> staging buffer; the NEXT tile's residual blocks -> L2, so that the
         // per-block TMA loads of the next tile are L2 hits instead of exposed HBM latency
@@ -532,6 +529,7 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
       const long long tB = clock64();
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      named_bar_sync(3, NUM_EPI_WARPS * 32);  // this tile's constants are in place (and the buffer of two tiles ago is free)
       const long long tC = clock64();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BLOCK_N;
 
@@ -617,9 +615,15 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
     if (issuer) tma_store_wait_all();  // global writes complete before the kernel (and its smem) goes away
   }
 
+  const long long k_t2 = clock64();
   tc_fence_before();
   cluster_sync_all();  // nobody exits (or frees TMEM) while the peer can still touch this CTA's smem / barriers
   if (warp == 2) tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
+  if (p.prof && threadIdx.x == 64) {
+    p.prof[blockIdx.x * 16 + 10] = k_t1 - k_t0;
+    p.prof[blockIdx.x * 16 + 11] = k_t2 - k_t1;
+    p.prof[blockIdx.x * 16 + 12] = clock64() - k_t2;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1153,8 +1157,10 @@ int launch_igemm_tc2(const IgemmParams& p, const IgemmMaps& maps, int block_n, i
     }
     fprintf(stderr,
             "[igemm prof mode=%d M=%d N=%d K=%d bn=%d epi=%d] tiles/cta %.1f | producer wait_empty %.0f total %.0f | mma "
-            "wait_tmem_empty %.0f wait_full %.0f total %.0f | epi cst %.0f wait_full %.0f blocks %.0f total %.0f (cycles)\n",
-            p.mode, p.M, p.N, p.K, block_n, pick_epi(pp), s[9], s[0], s[1], s[2], s[3], s[4], s[6], s[5], s[7], s[8]);
+            "wait_tmem_empty %.0f wait_full %.0f total %.0f | epi cst %.0f wait_full %.0f blocks %.0f total %.0f | kernel: prologue "
+            "%.0f roles %.0f exit %.0f (cycles)\n",
+            p.mode, p.M, p.N, p.K, block_n, pick_epi(pp), s[9], s[0], s[1], s[2], s[3], s[4], s[6], s[5], s[7], s[8], s[10],
+            s[11], s[12]);
     return r;
   }
   if (pp.halo) {
