@@ -129,6 +129,22 @@ __device__ __forceinline__ float gelu_erfc5(float v) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));
   return fmaf(-0.5f * u, e, fmaxf(v, 0.0f));
 }
+// The same on a pair of elements with packed fp32 arithmetic (FFMA2 / FMUL2: one issue slot for two elements; the
+// fc1 epilogue competes with the MMA and TMA threads for issue slots): 6.5 instead of 10 instructions per element,
+// bit-identical results (same operations, same order).
+__device__ __forceinline__ float2 gelu_erfc5_x2(float2 v) {
+  const float2 u = make_float2(fminf(fabsf(v.x), 6.0f), fminf(fabsf(v.y), 6.0f));
+  float2 q = make_float2(-4.837184678763151e-4f, -4.837184678763151e-4f);
+  q = __ffma2_rn(q, u, make_float2(7.163475267589092e-3f, 7.163475267589092e-3f));
+  q = __ffma2_rn(q, u, make_float2(-5.204327404499054e-2f, -5.204327404499054e-2f));
+  q = __ffma2_rn(q, u, make_float2(-4.5973172783851624e-1f, -4.5973172783851624e-1f));
+  q = __ffma2_rn(q, u, make_float2(-1.150922417640686f, -1.150922417640686f));
+  q = __ffma2_rn(q, u, make_float2(-1.5133146916923579e-5f, -1.5133146916923579e-5f));
+  float2 e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(q.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(q.y));
+  return __ffma2_rn(__fmul2_rn(u, make_float2(-0.5f, -0.5f)), e, make_float2(fmaxf(v.x, 0.0f), fmaxf(v.y, 0.0f)));
+}
 
 __device__ __forceinline__ void tile_out_coords(const IgemmParams& p, const TileCoord& c, bool pool, int& o1, int& o2,
                                                 int& o3) {
@@ -161,10 +177,11 @@ __device__ __forceinline__ void emit16(const uint32_t (&cur)[32], const float* s
   for (int q = 0; q < 8; ++q) {
     const float4 b = *reinterpret_cast<const float4*>(sh + 4 * q);
     if (EPI == EPI_LIN16 || EPI == EPI_GELU16 || EPI == EPI_SH16 || EPI == EPI_SHPOOL16) {
-      v[4 * q + 0] = __uint_as_float(cur[4 * q + 0]) + b.x;
-      v[4 * q + 1] = __uint_as_float(cur[4 * q + 1]) + b.y;
-      v[4 * q + 2] = __uint_as_float(cur[4 * q + 2]) + b.z;
-      v[4 * q + 3] = __uint_as_float(cur[4 * q + 3]) + b.w;
+      const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(cur[4 * q + 0]), __uint_as_float(cur[4 * q + 1])),
+                                   make_float2(b.x, b.y));
+      const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(cur[4 * q + 2]), __uint_as_float(cur[4 * q + 3])),
+                                   make_float2(b.z, b.w));
+      v[4 * q + 0] = s0.x; v[4 * q + 1] = s0.y; v[4 * q + 2] = s1.x; v[4 * q + 3] = s1.y;
     } else {
       const float4 a = *reinterpret_cast<const float4*>(sc + 4 * q);
       v[4 * q + 0] = fmaf(__uint_as_float(cur[4 * q + 0]), a.x, b.x);
@@ -199,7 +216,11 @@ __device__ __forceinline__ void emit16(const uint32_t (&cur)[32], const float* s
   }
   if (EPI == EPI_GELU16) {
 #pragma unroll
-    for (int e = 0; e < 32; ++e) v[e] = gelu_erfc5(v[e]);
+    for (int e = 0; e < 32; e += 2) {
+      const float2 g = gelu_erfc5_x2(make_float2(v[e], v[e + 1]));
+      v[e] = g.x;
+      v[e + 1] = g.y;
+    }
   } else if (EPI == EPI_BN16 || EPI == EPI_BNPOOL16 || EPI == EPI_SH16 || EPI == EPI_SHPOOL16) {
 #pragma unroll
     for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], relu_lo);
@@ -245,10 +266,11 @@ __device__ __forceinline__ void emit32(const uint32_t (&cur)[32], const float* s
   for (int q = 0; q < 8; ++q) {
     const float4 b = *reinterpret_cast<const float4*>(sh + 4 * q);
     if (EPI == EPI_F32 || EPI == EPI_F32D) {
-      v[4 * q + 0] = __uint_as_float(cur[4 * q + 0]) + b.x;
-      v[4 * q + 1] = __uint_as_float(cur[4 * q + 1]) + b.y;
-      v[4 * q + 2] = __uint_as_float(cur[4 * q + 2]) + b.z;
-      v[4 * q + 3] = __uint_as_float(cur[4 * q + 3]) + b.w;
+      const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(cur[4 * q + 0]), __uint_as_float(cur[4 * q + 1])),
+                                   make_float2(b.x, b.y));
+      const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(cur[4 * q + 2]), __uint_as_float(cur[4 * q + 3])),
+                                   make_float2(b.z, b.w));
+      v[4 * q + 0] = s0.x; v[4 * q + 1] = s0.y; v[4 * q + 2] = s1.x; v[4 * q + 3] = s1.y;
     } else {
       const float4 a = *reinterpret_cast<const float4*>(sc + 4 * q);
       v[4 * q + 0] = fmaf(__uint_as_float(cur[4 * q + 0]), a.x, b.x);
