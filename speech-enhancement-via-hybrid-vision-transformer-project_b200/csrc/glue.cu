@@ -50,8 +50,13 @@ __global__ void fft_tables_kernel() {
 __device__ __forceinline__ float hann512(int i) { return __ldg(&g_hann512[i]); }
 __device__ __forceinline__ int brev9(int i) { return static_cast<int>(__brev(static_cast<unsigned>(i)) >> 23); }
 
+// Complex arithmetic on the packed fp32 pipes (FADD2 / FMUL2 / FFMA2: one issue slot per complex add) - the FFT
+// kernels are bound by instruction issue.
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+  // (a.x b.x - a.y b.y, a.x b.y + a.y b.x)
+  return __ffma2_rn(make_float2(a.y, a.y), make_float2(-b.y, b.x), __fmul2_rn(make_float2(a.x, a.x), b));
 }
 
 // 8-point DFT in registers (three radix-2 levels).  INV selects the conjugate twiddles.
@@ -59,25 +64,23 @@ template <bool INV>
 __device__ __forceinline__ void dft8(float2 (&v)[8]) {
   constexpr float S = INV ? 1.0f : -1.0f;   // exp(S * i * theta)
   constexpr float H = 0.70710678118654752440f;
-  float2 a[8];
-  a[0] = make_float2(v[0].x + v[4].x, v[0].y + v[4].y); a[1] = make_float2(v[0].x - v[4].x, v[0].y - v[4].y);
-  a[2] = make_float2(v[2].x + v[6].x, v[2].y + v[6].y); a[3] = make_float2(v[2].x - v[6].x, v[2].y - v[6].y);
-  a[4] = make_float2(v[1].x + v[5].x, v[1].y + v[5].y); a[5] = make_float2(v[1].x - v[5].x, v[1].y - v[5].y);
-  a[6] = make_float2(v[3].x + v[7].x, v[3].y + v[7].y); a[7] = make_float2(v[3].x - v[7].x, v[3].y - v[7].y);
-  // (S*i) * z = (-S*z.y, S*z.x)
-  const float2 ja3 = make_float2(-S * a[3].y, S * a[3].x), ja7 = make_float2(-S * a[7].y, S * a[7].x);
-  const float2 b0 = make_float2(a[0].x + a[2].x, a[0].y + a[2].y), b2 = make_float2(a[0].x - a[2].x, a[0].y - a[2].y);
-  const float2 b1 = make_float2(a[1].x + ja3.x, a[1].y + ja3.y), b3 = make_float2(a[1].x - ja3.x, a[1].y - ja3.y);
-  const float2 c0 = make_float2(a[4].x + a[6].x, a[4].y + a[6].y);
-  float2 c2 = make_float2(a[4].x - a[6].x, a[4].y - a[6].y);
-  float2 c1 = make_float2(a[5].x + ja7.x, a[5].y + ja7.y), c3 = make_float2(a[5].x - ja7.x, a[5].y - ja7.y);
-  c1 = make_float2(H * (c1.x - S * c1.y), H * (S * c1.x + c1.y));     // * exp(S*i*pi/4)
-  c2 = make_float2(-S * c2.y, S * c2.x);                                // * exp(S*i*pi/2)
-  c3 = make_float2(H * (-c3.x - S * c3.y), H * (S * c3.x - c3.y));    // * exp(S*i*3pi/4)
-  v[0] = make_float2(b0.x + c0.x, b0.y + c0.y); v[4] = make_float2(b0.x - c0.x, b0.y - c0.y);
-  v[1] = make_float2(b1.x + c1.x, b1.y + c1.y); v[5] = make_float2(b1.x - c1.x, b1.y - c1.y);
-  v[2] = make_float2(b2.x + c2.x, b2.y + c2.y); v[6] = make_float2(b2.x - c2.x, b2.y - c2.y);
-  v[3] = make_float2(b3.x + c3.x, b3.y + c3.y); v[7] = make_float2(b3.x - c3.x, b3.y - c3.y);
+  // a + (S*i) z = (a.x - S z.y, a.y + S z.x);  a - (S*i) z = (a.x + S z.y, a.y - S z.x)
+  auto add_jz = [](float2 a, float2 z) { return __ffma2_rn(make_float2(z.y, z.x), make_float2(-S, S), a); };
+  auto sub_jz = [](float2 a, float2 z) { return __ffma2_rn(make_float2(z.y, z.x), make_float2(S, -S), a); };
+  const float2 a0 = cadd(v[0], v[4]), a1 = csub(v[0], v[4]);
+  const float2 a2 = cadd(v[2], v[6]), a3 = csub(v[2], v[6]);
+  const float2 a4 = cadd(v[1], v[5]), a5 = csub(v[1], v[5]);
+  const float2 a6 = cadd(v[3], v[7]), a7 = csub(v[3], v[7]);
+  const float2 b0 = cadd(a0, a2), b2 = csub(a0, a2);
+  const float2 b1 = add_jz(a1, a3), b3 = sub_jz(a1, a3);
+  const float2 c0 = cadd(a4, a6), c2 = csub(a4, a6);
+  float2 c1 = add_jz(a5, a7), c3 = sub_jz(a5, a7);
+  c1 = __fmul2_rn(add_jz(c1, c1), make_float2(H, H));      // * exp(S*i*pi/4)  = H (1 + S i)
+  c3 = __fmul2_rn(sub_jz(c3, c3), make_float2(-H, -H));    // * exp(S*i*3pi/4) = H (-1 + S i)
+  v[0] = cadd(b0, c0); v[4] = csub(b0, c0);
+  v[1] = cadd(b1, c1); v[5] = csub(b1, c1);
+  v[2] = add_jz(b2, c2); v[6] = sub_jz(b2, c2);            // c2 * exp(S*i*pi/2) = (S i) c2
+  v[3] = cadd(b3, c3); v[7] = csub(b3, c3);
 }
 
 // 512-point complex FFT of one frame in shared memory by ONE warp: radix-8 Stockham, 3 passes, natural order in and
@@ -156,7 +159,7 @@ __global__ void fill_u32_kernel(unsigned* p, int n, unsigned v) {
 // ------------------------------------------------------------------ STFT + |.| + per-clip max (enhancer.py:82-101)
 // Every warp transforms TWO real frames with one complex FFT (frame a in the real parts, frame b in the imaginary
 // parts): A[k] = (Z[k] + conj Z[N-k]) / 2, B[k] = (Z[k] - conj Z[N-k]) / 2i.  Half the butterflies per frame.
-__global__ void __launch_bounds__(FR * 32, 5) stft_kernel(const float* __restrict__ wave, int n, int T,
+__global__ void __launch_bounds__(FR * 32, 4) stft_kernel(const float* __restrict__ wave, int n, int T,
                                                        const unsigned* __restrict__ max_bits,
                                                        float2* __restrict__ spec, float* __restrict__ mag,
                                                        unsigned* __restrict__ mag_max_bits) {
@@ -225,7 +228,7 @@ __device__ __forceinline__ Lerp make_lerp(int dst, int in_size, int out_size) {
 // E = (model_out * mag_max) * S/|S|  (== mag * exp(1j*angle(S)), enhancer.py:115-119), irfft-512, * Hann.
 // When `lowres` is given the model output is bilinearly sampled from the decoder's [B,Hs,Ws] tanh map on the fly
 // (HybridViT's final F.interpolate, hybrid_vit.py:458-465, fused here) and also written to model_out.
-__global__ void __launch_bounds__(FR * 32, 5) istft_frames_kernel(float* __restrict__ model_out,
+__global__ void __launch_bounds__(FR * 32, 4) istft_frames_kernel(float* __restrict__ model_out,
                                                                const float* __restrict__ lowres, int Hs, int Ws,
                                                                const float2* __restrict__ spec,
                                                                const unsigned* __restrict__ mag_max_bits, int T,
