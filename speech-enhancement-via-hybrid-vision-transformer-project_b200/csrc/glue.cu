@@ -175,31 +175,49 @@ __global__ void __launch_bounds__(FR * 32, 4) stft_kernel(const float* __restric
   if (ta < T) {
     const float* w = wave + static_cast<long long>(b) * n;
     const bool has_b = ta + 1 < T;
-    for (int i = lane; i < NFFT; i += 32) {
-      const int sa = ta * HOP - NFFT / 2 + i, sb = sa + HOP;  // centred frames, zero padding
-      const float h = hann512(i);
-      float va = 0.f, vb = 0.f;
-      if (sa >= 0 && sa < n) va = (w[sa] * inv_mv) * h;
-      if (has_b && sb >= 0 && sb < n) vb = (w[sb] * inv_mv) * h;
-      x[fpad(i)] = make_float2(va, vb);
+    const int s0 = ta * HOP - NFFT / 2;  // first sample of frame a (frame b starts HOP later); centred, zero padded
+    if (s0 >= 0 && s0 + HOP + NFFT <= n && has_b) {
+      // interior pair (all but the first / last frames of a clip): no range checks
+      const float* wa = w + s0;
+#pragma unroll 4
+      for (int i = lane; i < NFFT; i += 32) {
+        const float h = hann512(i);
+        x[fpad(i)] = make_float2((wa[i] * inv_mv) * h, (wa[i + HOP] * inv_mv) * h);
+      }
+    } else {
+      for (int i = lane; i < NFFT; i += 32) {
+        const int sa = s0 + i, sb = sa + HOP;
+        const float h = hann512(i);
+        float va = 0.f, vb = 0.f;
+        if (sa >= 0 && sa < n) va = (w[sa] * inv_mv) * h;
+        if (has_b && sb >= 0 && sb < n) vb = (w[sb] * inv_mv) * h;
+        x[fpad(i)] = make_float2(va, vb);
+      }
     }
   }
   __syncwarp();
   if (ta < T) fft512_warp<false>(x, lane);
   __syncthreads();
+  // output: thread -> (frame tl, bins fq, fq + 16, ...); 16 consecutive frames of a bin are one 128-byte store
   float lmax = 0.f;
-  for (int idx = threadIdx.x; idx < NBIN * FRAMES; idx += blockDim.x) {
-    const int tl = idx & (FRAMES - 1), f = idx / FRAMES;
+  {
+    const int tl = threadIdx.x & (FRAMES - 1), fq = threadIdx.x / FRAMES;
     if (t0 + tl < T) {
       const float2* xw = xs + (tl >> 1) * XS;
-      const float2 z1 = xw[fpad(f)], z2 = xw[fpad((NFFT - f) & (NFFT - 1))];
-      const float2 z = (tl & 1) ? make_float2(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x))
+      const bool second = (tl & 1) != 0;
+      const long long o0 = (static_cast<long long>(b) * NBIN + fq) * T + t0 + tl;
+      float2* sp = spec + o0;
+      float* mp = mag + o0;
+      const long long step = static_cast<long long>(FR * 32 / FRAMES) * T;
+      for (int f = fq; f < NBIN; f += FR * 32 / FRAMES, sp += step, mp += step) {
+        const float2 z1 = xw[fpad(f)], z2 = xw[fpad((NFFT - f) & (NFFT - 1))];
+        const float2 z = second ? make_float2(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x))
                                 : make_float2(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
-      const long long o = (static_cast<long long>(b) * NBIN + f) * T + t0 + tl;
-      spec[o] = z;
-      const float m = sqrtf(z.x * z.x + z.y * z.y);
-      mag[o] = m;
-      lmax = fmaxf(lmax, m);
+        *sp = z;
+        const float m = sqrtf(z.x * z.x + z.y * z.y);
+        *mp = m;
+        lmax = fmaxf(lmax, m);
+      }
     }
   }
   lmax = warp_max(lmax);
@@ -240,39 +258,53 @@ __global__ void __launch_bounds__(FR * 32, 4) istft_frames_kernel(float* __restr
   const int b = blockIdx.y, t0 = blockIdx.x * FRAMES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float mm = guard_scalar(mag_max_bits[b]);
-  // E(f, t) of one time-frequency bin
-  auto bin = [&](int f, int t) -> float2 {
-    const long long o = (static_cast<long long>(b) * NBIN + f) * T + t;
-    const float2 z = spec[o];
-    const float a = sqrtf(z.x * z.x + z.y * z.y);
-    float mo;
-    if (lowres != nullptr) {
-      const Lerp ly = make_lerp(f, Hs, NBIN), lx = make_lerp(t, Ws, T);
-      const float* src = lowres + static_cast<long long>(b) * Hs * Ws;
-      const float v00 = src[ly.i0 * Ws + lx.i0], v01 = src[ly.i0 * Ws + lx.i1];
-      const float v10 = src[ly.i1 * Ws + lx.i0], v11 = src[ly.i1 * Ws + lx.i1];
-      mo = ly.l0 * (lx.l0 * v00 + lx.l1 * v01) + ly.l1 * (lx.l0 * v10 + lx.l1 * v11);
-      model_out[o] = mo;
-    } else {
-      mo = model_out[o];
-    }
-    const float e = mo * mm;
-    const float ea = a > 0.f ? e / a : 0.f;
-    float2 E = a > 0.f ? make_float2(ea * z.x, ea * z.y) : make_float2(e, 0.f);
-    if (f == 0 || f == NFFT / 2) E.y = 0.f;  // c2r transforms ignore the imaginary part of DC / Nyquist
-    return E;
-  };
   // Two frames per inverse FFT: Z = Ea + i Eb over the full (Hermitian-filled) spectrum; the real part of the
-  // transform is frame a, the imaginary part frame b.
-  for (int idx = threadIdx.x; idx < NBIN * FR; idx += blockDim.x) {
-    const int q = idx & (FR - 1), f = idx / FR;
-    const int ta = t0 + 2 * q;
-    if (ta < T) {
-      const float2 Ea = bin(f, ta);
-      const float2 Eb = ta + 1 < T ? bin(f, ta + 1) : make_float2(0.f, 0.f);
+  // transform is frame a, the imaginary part frame b.  Thread -> (frame pair q, bins fq, fq + 32, ...): the time
+  // interpolation weights are per thread, the frequency ones per iteration (shared by both frames).
+  {
+    const int q = threadIdx.x & (FR - 1), fq = threadIdx.x / FR;
+    const int qa = t0 + 2 * q;
+    if (qa < T) {
+      const bool has_b = qa + 1 < T;
+      const Lerp lxa = make_lerp(qa, Ws > 0 ? Ws : 1, T), lxb = make_lerp(has_b ? qa + 1 : qa, Ws > 0 ? Ws : 1, T);
+      const float* src = lowres != nullptr ? lowres + static_cast<long long>(b) * Hs * Ws : nullptr;
       float2* x = xs + q * XS;
-      x[fpad(f)] = make_float2(Ea.x - Eb.y, Ea.y + Eb.x);
-      if (f > 0 && f < NFFT / 2) x[fpad(NFFT - f)] = make_float2(Ea.x + Eb.y, Eb.x - Ea.y);
+      const long long o0 = (static_cast<long long>(b) * NBIN + fq) * T + qa;
+      const float2* sp = spec + o0;
+      float* mp = model_out + o0;
+      const long long step = static_cast<long long>(FR * 32 / FR) * T;
+      // E = (model_out * mag_max) * S / |S| of one bin (z = S, mo = model output)
+      auto bin = [&](float2 z, float mo, int f) -> float2 {
+        const float a = sqrtf(z.x * z.x + z.y * z.y);
+        const float e = mo * mm;
+        const float ea = a > 0.f ? e / a : 0.f;
+        float2 E = a > 0.f ? make_float2(ea * z.x, ea * z.y) : make_float2(e, 0.f);
+        if (f == 0 || f == NFFT / 2) E.y = 0.f;  // c2r transforms ignore the imaginary part of DC / Nyquist
+        return E;
+      };
+      for (int f = fq; f < NBIN; f += 32, sp += step, mp += step) {
+        const float2 za = sp[0];
+        const float2 zb = has_b ? sp[1] : make_float2(0.f, 0.f);
+        float moa, mob = 0.f;
+        if (src != nullptr) {
+          const Lerp ly = make_lerp(f, Hs, NBIN);
+          const float* r0 = src + ly.i0 * Ws;
+          const float* r1 = src + ly.i1 * Ws;
+          moa = ly.l0 * (lxa.l0 * r0[lxa.i0] + lxa.l1 * r0[lxa.i1]) + ly.l1 * (lxa.l0 * r1[lxa.i0] + lxa.l1 * r1[lxa.i1]);
+          mp[0] = moa;
+          if (has_b) {
+            mob = ly.l0 * (lxb.l0 * r0[lxb.i0] + lxb.l1 * r0[lxb.i1]) + ly.l1 * (lxb.l0 * r1[lxb.i0] + lxb.l1 * r1[lxb.i1]);
+            mp[1] = mob;
+          }
+        } else {
+          moa = mp[0];
+          if (has_b) mob = mp[1];
+        }
+        const float2 Ea = bin(za, moa, f);
+        const float2 Eb = has_b ? bin(zb, mob, f) : make_float2(0.f, 0.f);
+        x[fpad(f)] = make_float2(Ea.x - Eb.y, Ea.y + Eb.x);
+        if (f > 0 && f < NFFT / 2) x[fpad(NFFT - f)] = make_float2(Ea.x + Eb.y, Eb.x - Ea.y);
+      }
     }
   }
   __syncthreads();
