@@ -275,10 +275,17 @@ __global__ void __launch_bounds__(FR * 32, 4) istft_frames_kernel(float* __restr
       const long long step = static_cast<long long>(FR * 32 / FR) * T;
       // E = (model_out * mag_max) * S / |S| of one bin (z = S, mo = model output)
       auto bin = [&](float2 z, float mo, int f) -> float2 {
-        const float a = sqrtf(z.x * z.x + z.y * z.y);
+        const float zz = z.x * z.x + z.y * z.y;
         const float e = mo * mm;
-        const float ea = a > 0.f ? e / a : 0.f;
-        float2 E = a > 0.f ? make_float2(ea * z.x, ea * z.y) : make_float2(e, 0.f);
+        float2 E;
+        if (zz >= 1.17549435e-38f) {  // e * S / |S| with one MUFU.RSQ (2^-22 relative) instead of sqrt + divide
+          const float ea = e * rsqrtf(zz);
+          E = make_float2(ea * z.x, ea * z.y);
+        } else {                       // |S|^2 underflows or S == 0 (angle 0): exact path
+          const float a = sqrtf(zz);
+          const float ea = a > 0.f ? e / a : 0.f;
+          E = a > 0.f ? make_float2(ea * z.x, ea * z.y) : make_float2(e, 0.f);
+        }
         if (f == 0 || f == NFFT / 2) E.y = 0.f;  // c2r transforms ignore the imaginary part of DC / Nyquist
         return E;
       };
