@@ -33,6 +33,43 @@ bool pdl_enabled() {
   return v == 1;
 }
 
+static thread_local L2Window g_l2_window = {nullptr, 0, 0.f};
+const L2Window& l2_window() { return g_l2_window; }
+void l2_window_set(void* base, size_t bytes, float hit_ratio) { g_l2_window = L2Window{base, bytes, hit_ratio}; }
+
+// Persisting-L2 carve-out for the residual stream (once per process): returns the usable window hit ratio for a
+// buffer of `bytes` (0 = feature unavailable or disabled with HVIT_NO_L2PIN=1).
+static float l2_pin_ratio(size_t bytes) {
+  static int max_persist = -1;
+  static size_t carve = 0;
+  if (max_persist < 0) {
+    max_persist = 0;
+    const char* e = getenv("HVIT_NO_L2PIN");
+    if (!(e != nullptr && e[0] == '1')) {
+      int dev = 0, v = 0;
+      cudaGetDevice(&dev);
+      if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, dev) == cudaSuccess && v > 0) max_persist = v;
+      cudaGetLastError();
+    }
+  }
+  if (max_persist <= 0 || bytes == 0) return 0.f;
+  size_t want = bytes < static_cast<size_t>(max_persist) ? bytes : static_cast<size_t>(max_persist);
+  if (const char* e = getenv("HVIT_L2PIN_MB")) {  // tuning knob: carve-out size in MB (<= the device maximum)
+    const size_t mb = static_cast<size_t>(atoi(e)) << 20;
+    if (mb > 0 && mb < want) want = mb;
+  }
+  if (want > carve) {
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) {
+      cudaGetLastError();
+      max_persist = 0;
+      return 0.f;
+    }
+    carve = want;
+  }
+  const float r = static_cast<float>(static_cast<double>(carve) / static_cast<double>(bytes));
+  return r > 1.f ? 1.f : r;
+}
+
 int check_launch(const char* what) {
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -282,6 +319,9 @@ struct hvit_plan {
   std::vector<hvit::Step> pre, post;  // enhance: peak/STFT before, iSTFT after
   std::vector<hvit::StepMeta> pre_meta, post_meta;
   int launches_forward;
+  void* l2_pin_base = nullptr;        // residual stream kept in persisting L2 lines during the forward steps
+  size_t l2_pin_bytes = 0;
+  float l2_pin_ratio = 0.f;
   // tag the most recently pushed step(s)
   void tag(const std::string& name, const char* kernel, double aflops, double eflops, double bytes, int launches = 1) {
     while (meta.size() < steps.size()) meta.push_back(hvit::StepMeta{name, kernel, 0.0, 0.0, 0.0, 1});
@@ -664,6 +704,11 @@ static int build_steps(hvit_plan* p) {
   }
   // 4. transformer blocks (pre-norm), residual stream fp32
   float* tok = at<float>(p, "tokens");
+  if (bf && c.num_layers > 0) {
+    p->l2_pin_base = tok;
+    p->l2_pin_bytes = static_cast<size_t>(g.M) * D * sizeof(float);
+    p->l2_pin_ratio = l2_pin_ratio(p->l2_pin_bytes);
+  }
   void* ln = at<void>(p, "ln");
   void* qkv = at<void>(p, "qkv");
   void* att = at<void>(p, "attn");
@@ -869,11 +914,12 @@ static Ctx enhance_ctx(hvit_plan* plan, const float* wave_in, float* wave_out, i
 }
 
 static int run_steps(hvit_plan* p, const Ctx& c) {
-  for (size_t i = 0; i < p->steps.size(); ++i) {
-    const int r = p->steps[i](c);
-    if (r != HVIT_OK) return r;
-  }
-  return HVIT_OK;
+  // the fp32 residual stream ("tokens") stays in L2 across the transformer blocks when the device allows it
+  if (p->l2_pin_bytes > 0 && p->l2_pin_ratio > 0.f) l2_window_set(p->l2_pin_base, p->l2_pin_bytes, p->l2_pin_ratio);
+  int r = HVIT_OK;
+  for (size_t i = 0; i < p->steps.size() && r == HVIT_OK; ++i) r = p->steps[i](c);
+  l2_window_set(nullptr, 0, 0.f);
+  return r;
 }
 
 int hvit_forward(hvit_plan* plan, const float* x_dev, float* y_dev, float* attn_probs_dev, void* stream) {
@@ -965,7 +1011,9 @@ int hvit_enhance_profiled(hvit_plan* plan, const float* wave_in_dev, float* wave
     }
   };
   run(plan->pre);
+  if (plan->l2_pin_bytes > 0 && plan->l2_pin_ratio > 0.f) l2_window_set(plan->l2_pin_base, plan->l2_pin_bytes, plan->l2_pin_ratio);
   run(plan->steps);
+  l2_window_set(nullptr, 0, 0.f);
   run(plan->post);
   if (cudaStreamSynchronize(c.stream) != cudaSuccess && r == HVIT_OK) r = check_launch("hvit_enhance_profiled");
   for (int k = 0; k < n_steps; ++k) {

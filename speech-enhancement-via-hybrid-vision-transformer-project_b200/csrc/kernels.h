@@ -142,7 +142,17 @@ int launch_resize(const float* src, int B, int Hs, int Ws, float* dst, int Hd, i
 int launch_maxpool2(const float* src, float* dst, int B, int H, int W, int C, cudaStream_t s);
 
 // Kernel launch with programmatic stream serialization (PDL); HVIT_NO_PDL=1 falls back to plain stream order.
+// While an L2 window is set (l2_window_set: the transformer's fp32 residual stream, re-read and updated in place by
+// every LayerNorm / proj / fc2 of a step) each launch carries it as an access-policy-window attribute: lines of the
+// window are kept as persisting L2 lines, everything else stays normal.
 bool pdl_enabled();
+struct L2Window {
+  void* base;
+  size_t bytes;
+  float hit_ratio;
+};
+const L2Window& l2_window();
+void l2_window_set(void* base, size_t bytes, float hit_ratio);  // bytes == 0 clears it
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                               Args... args) {
@@ -151,11 +161,25 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (pdl_enabled()) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  const L2Window& w = l2_window();
+  if (w.bytes > 0) {
+    at[na].id = cudaLaunchAttributeAccessPolicyWindow;
+    at[na].val.accessPolicyWindow.base_ptr = w.base;
+    at[na].val.accessPolicyWindow.num_bytes = w.bytes;
+    at[na].val.accessPolicyWindow.hitRatio = w.hit_ratio;
+    at[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    at[na].val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    ++na;
+  }
   cfg.attrs = at;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
