@@ -62,7 +62,7 @@ def ncu_traffic(args, family):
     `ncu --set full` capture of this very workload (profiles/); None for any other workload."""
     if args.widened or args.batch != 64 or args.seconds != 4.0 or args.precision != "fp16" or family != "igemm_tc":
         return None
-    path = os.path.join(ROOT, "profiles", "r1z_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r1f_traffic.json")
     if not os.path.exists(path):
         return None
     with open(path) as f:
