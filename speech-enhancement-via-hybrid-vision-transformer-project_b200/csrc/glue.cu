@@ -746,7 +746,9 @@ __global__ void __launch_bounds__(256) head_rows_kernel(const T* __restrict__ x,
     __syncthreads();                                       // ... and everybody else's
     for (int w0 = threadIdx.x >> 3; w0 - (static_cast<int>(threadIdx.x) >> 3) < W; w0 += 32) {
       const bool live = w0 < W;
-      float acc = 0.f;
+      // four independent packed accumulators (a single one is a 72-deep FFMA dependency chain: with one CTA of 8
+      // warps per SM the kernel was bound by FMA latency, 288 cycles per 4 pixels and warp)
+      float2 acc2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
       if (live) {
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
@@ -755,9 +757,11 @@ __global__ void __launch_bounds__(256) head_rows_kernel(const T* __restrict__ x,
           float v[8];
           ld8<T>(reinterpret_cast<const T*>(hsm + ((h + tap / 3) & 3) * row_bytes) + ix * C + lane8 * 8, v);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc = fmaf(v[e], wr[tap][e], acc);
+          for (int e = 0; e < 4; ++e)
+            acc2[e] = __ffma2_rn(make_float2(v[2 * e], v[2 * e + 1]), make_float2(wr[tap][2 * e], wr[tap][2 * e + 1]), acc2[e]);
         }
       }
+      float acc = ((acc2[0].x + acc2[0].y) + (acc2[1].x + acc2[1].y)) + ((acc2[2].x + acc2[2].y) + (acc2[3].x + acc2[3].y));
       acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
       acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
       acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 4);
