@@ -705,16 +705,16 @@ __global__ void __launch_bounds__(256) head_kernel(const T* __restrict__ x, cons
 // computed.  8 lanes per output pixel (8 channels = one conflict-free 16-byte shared-memory load per tap) accumulate
 // in fp32 against register-resident weights.  (The per-pixel global-load kernel above was latency / L1 bound:
 // 116 us for 65 MB of input.)
-constexpr int HEAD_STRIP = 8;
+constexpr int HEAD_STRIP = 8;  // default strip height; the launcher shortens it when that balances the grid better
 template <typename T>
 __global__ void __launch_bounds__(256) head_rows_kernel(const T* __restrict__ x, const float* __restrict__ w9c, int H, int W,
-                                                        float* __restrict__ logits, float* __restrict__ out_tanh) {
+                                                        float* __restrict__ logits, float* __restrict__ out_tanh, int strip) {
   griddep_launch_dependents();
   griddep_wait();
   constexpr int C = 64;
   extern __shared__ __align__(16) uint8_t hsm[];
-  const int h0 = blockIdx.x * HEAD_STRIP, b = blockIdx.y;
-  const int h1 = min(h0 + HEAD_STRIP, H);
+  const int h0 = blockIdx.x * strip, b = blockIdx.y;
+  const int h1 = min(h0 + strip, H);
   const int row_bytes = W * C * 2;
   // input row ih -> ring slot (ih + 1) & 3; rows outside the image are zero (conv padding)
   auto load_row = [&](int ih) {
@@ -744,31 +744,63 @@ __global__ void __launch_bounds__(256) head_rows_kernel(const T* __restrict__ x,
     load_row(h + 2);  // slot of row h-2, whose last readers passed the barrier at the end of the previous iteration
     asm volatile("cp.async.wait_group 1;" ::: "memory");  // rows <= h+1 have landed (this thread's copies)
     __syncthreads();                                       // ... and everybody else's
-    for (int w0 = threadIdx.x >> 3; w0 - (static_cast<int>(threadIdx.x) >> 3) < W; w0 += 32) {
-      const bool live = w0 < W;
-      // four independent packed accumulators (a single one is a 72-deep FFMA dependency chain: with one CTA of 8
-      // warps per SM the kernel was bound by FMA latency, 288 cycles per 4 pixels and warp)
-      float2 acc2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-      if (live) {
+    // Each 8-lane group walks a run of 4 consecutive pixels with a 3-column window of fp32 values in registers:
+    // every input vector is loaded and converted once per output row and group (1.5 instead of 9 loads + converts
+    // per pixel and lane).  The lanes' partial sums of the 4 pixels meet in a butterfly (4 shuffles instead of 12).
+    for (int wb0 = (threadIdx.x >> 5) * 16; wb0 < W; wb0 += 128) {  // (warp-uniform trip count: full-mask shuffles below)
+      const int wb = wb0 + ((threadIdx.x >> 3) & 3) * 4;
+      const T* r0 = reinterpret_cast<const T*>(hsm + ((h + 0) & 3) * row_bytes) + lane8 * 8;
+      const T* r1 = reinterpret_cast<const T*>(hsm + ((h + 1) & 3) * row_bytes) + lane8 * 8;
+      const T* r2 = reinterpret_cast<const T*>(hsm + ((h + 2) & 3) * row_bytes) + lane8 * 8;
+      float win[3][3][8];  // [column slot][row][channel]
+      auto load_col = [&](int slot, int ix) {
+        if (ix >= 0 && ix < W) {
+          ld8<T>(r0 + ix * C, win[slot][0]);
+          ld8<T>(r1 + ix * C, win[slot][1]);
+          ld8<T>(r2 + ix * C, win[slot][2]);
+        } else {
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) win[slot][r][e] = 0.f;
+        }
+      };
+      load_col(0, wb - 1);
+      load_col(1, wb);
+      float part[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        load_col((i + 2) % 3, wb + i + 1);
+        float2 acc2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
-          const int ix = w0 + tap % 3 - 1;
-          if (ix < 0 || ix >= W) continue;
-          float v[8];
-          ld8<T>(reinterpret_cast<const T*>(hsm + ((h + tap / 3) & 3) * row_bytes) + ix * C + lane8 * 8, v);
+          const float(&v)[8] = win[(i + tap % 3) % 3][tap / 3];
 #pragma unroll
           for (int e = 0; e < 4; ++e)
             acc2[e] = __ffma2_rn(make_float2(v[2 * e], v[2 * e + 1]), make_float2(wr[tap][2 * e], wr[tap][2 * e + 1]), acc2[e]);
         }
+        part[i] = ((acc2[0].x + acc2[0].y) + (acc2[1].x + acc2[1].y)) + ((acc2[2].x + acc2[2].y) + (acc2[3].x + acc2[3].y));
       }
-      float acc = ((acc2[0].x + acc2[0].y) + (acc2[1].x + acc2[1].y)) + ((acc2[2].x + acc2[2].y) + (acc2[3].x + acc2[3].y));
-      acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
-      acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
-      acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 4);
-      if (live && lane8 == 0) {
+      // butterfly over the 8 lanes: afterwards every lane holds the finished pixel wb + (lane8 >> 1)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const bool up = (lane8 & 4) != 0;
+        const float send = up ? part[i] : part[i + 2];
+        const float keep = up ? part[i + 2] : part[i];
+        part[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 4);
+      }
+      {
+        const bool up = (lane8 & 2) != 0;
+        const float send = up ? part[0] : part[1];
+        const float keep = up ? part[1] : part[0];
+        part[0] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 2);
+      }
+      part[0] += __shfl_xor_sync(0xFFFFFFFFu, part[0], 1);
+      const int w0 = wb + (lane8 >> 1);
+      if (w0 < W && (lane8 & 1) == 0) {
         const long long pix = (static_cast<long long>(b) * H + h) * W + w0;
-        if (logits != nullptr) logits[pix] = acc;
-        out_tanh[pix] = tanhf(acc);
+        if (logits != nullptr) logits[pix] = part[0];
+        out_tanh[pix] = tanhf(part[0]);
       }
     }
     __syncthreads();  // row h-1's slot may be overwritten by the next iteration's copy
@@ -967,12 +999,35 @@ int launch_head(const void* x, int dt, const float* w, int B, int H, int W, int 
       cudaFuncSetAttribute(head_rows_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
       configured = true;
     }
+    // strip height: the row ring needs 63 KB per block (3 blocks per SM), so the grid is only a few blocks per slot;
+    // pick the strip (8, 4 or 2 rows) whose last wave wastes the least time (shorter strips re-read more halo rows)
+    static int sms = 0;
+    if (sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (sms <= 0) sms = 148;
+    }
+    const int per_sm = rows_smem > 0 ? static_cast<int>((200 * 1024) / rows_smem) : 1;
+    const int slots = sms * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
+    int strip = HEAD_STRIP;
+    double best = 1e30;
+    for (int st = HEAD_STRIP; st >= 2; st /= 2) {
+      const long long blocks = static_cast<long long>((H + st - 1) / st) * B;
+      const double waves = static_cast<double>((blocks + slots - 1) / slots);
+      const double cost = waves * (st + 2);  // rows streamed per block
+      if (cost < best) {
+        best = cost;
+        strip = st;
+      }
+    }
+    if (const char* e = getenv("HVIT_HEAD_STRIP")) strip = atoi(e) > 0 ? atoi(e) : strip;
     if (dt == DT_BF16)
-      launch_pdl(head_rows_kernel<bf16>, dim3((H + HEAD_STRIP - 1) / HEAD_STRIP, B), dim3(256), rows_smem, s, reinterpret_cast<const bf16*>(x), w, H, W,
-                 logits, out_tanh);
+      launch_pdl(head_rows_kernel<bf16>, dim3((H + strip - 1) / strip, B), dim3(256), rows_smem, s, reinterpret_cast<const bf16*>(x), w, H, W,
+                 logits, out_tanh, strip);
     else
-      launch_pdl(head_rows_kernel<__half>, dim3((H + HEAD_STRIP - 1) / HEAD_STRIP, B), dim3(256), rows_smem, s, reinterpret_cast<const __half*>(x), w, H,
-                 W, logits, out_tanh);
+      launch_pdl(head_rows_kernel<__half>, dim3((H + strip - 1) / strip, B), dim3(256), rows_smem, s, reinterpret_cast<const __half*>(x), w, H,
+                 W, logits, out_tanh, strip);
     return check_launch("head_rows");
   }
   long long blocks = (npix + 31) / 32;
