@@ -278,7 +278,7 @@ def test_stem_16(B, H, W, use_tc, kind):
     assert U.rel_err(out.float(), ref) < OUT_TOL[kind]
 
 
-@pytest.mark.parametrize("B,H,W", [(2, 64, 124), (1, 5, 7), (3, 17, 33)])
+@pytest.mark.parametrize("B,H,W", [(2, 64, 124), (1, 5, 7), (3, 17, 33), (1, 9, 140), (1, 6, 150)])
 @pytest.mark.parametrize("kind", ["fp16", "bf16"])
 def test_head_16(B, H, W, kind):
     """Last decoder block: conv3x3(64->1) + tanh with fp32 accumulation (row-streaming kernel) against torch."""
