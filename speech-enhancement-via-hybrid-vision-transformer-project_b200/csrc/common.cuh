@@ -63,12 +63,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// same with a suspend-time hint: the hardware may park the thread for up to that long (it is woken when the phase
+// completes), so a long wait costs a handful of instructions instead of a tight polling loop - in a power-capped
+// step the polling warps' issue slots and energy are not free
+__device__ __forceinline__ bool mbar_try_wait_parked(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug becomes a trapped launch (reported through the C-ABI) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_parked(bar, parity)) {
     if (((++spins) & 0x3FF) == 0 && (clock64() - t0) > 6000000000LL) __trap();
   }
 }
