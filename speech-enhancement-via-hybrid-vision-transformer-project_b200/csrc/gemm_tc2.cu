@@ -322,6 +322,7 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
   uint64_t* tmem_empty = tmem_full + 2;         // [2]        (used in the leader)
   uint64_t* res_bar = tmem_empty + 2;           // [group][buffer]: residual tile landed in the staging buffer
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4);
+  volatile long long* t_issue = reinterpret_cast<volatile long long*>(bars + 32);  // [STAGES] diagnostics: TMA issue time per stage
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -381,6 +382,7 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
           }
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
+          if (p.prof) t_issue[stage] = clock64();
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
           if (p.mode == IG_PLAIN) {
             tma_load_2d_2sm(sa, &maps.a, &full_bar[stage], kb * BLOCK_K, c.m0);
@@ -437,7 +439,7 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      long long mw_e = 0, mw_f = 0;
+      long long mw_e = 0, mw_f = 0, lat_sum = 0, lat_n = 0;
       const long long mt0 = clock64();
       for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters) {
         if (prof) {
@@ -453,7 +455,12 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
           if (prof) {
             const long long t = clock64();
             mbar_wait(&full_bar[stage], phase);
-            mw_f += clock64() - t;
+            const long long t2 = clock64();
+            mw_f += t2 - t;
+            if (t2 - t > 100) {  // the load was still in flight: issue -> landed (an upper bound of the TMA round trip)
+              lat_sum += t2 - t_issue[stage];
+              ++lat_n;
+            }
           } else {
             mbar_wait(&full_bar[stage], phase);
           }
@@ -482,6 +489,8 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
         p.prof[blockIdx.x * 16 + 2] = mw_e;
         p.prof[blockIdx.x * 16 + 3] = mw_f;
         p.prof[blockIdx.x * 16 + 4] = clock64() - mt0;
+        p.prof[blockIdx.x * 16 + 13] = lat_sum;
+        p.prof[blockIdx.x * 16 + 14] = lat_n;
       }
     }
   } else {
@@ -1180,9 +1189,9 @@ int launch_igemm_tc2(const IgemmParams& p, const IgemmMaps& maps, int block_n, i
     fprintf(stderr,
             "[igemm prof mode=%d M=%d N=%d K=%d bn=%d epi=%d] tiles/cta %.1f | producer wait_empty %.0f total %.0f | mma "
             "wait_tmem_empty %.0f wait_full %.0f total %.0f | epi cst %.0f wait_full %.0f blocks %.0f total %.0f | kernel: prologue "
-            "%.0f roles %.0f exit %.0f (cycles)\n",
+            "%.0f roles %.0f exit %.0f | TMA issue -> landed when the MMA thread was waiting: %.0f cycles (%.0f samples/CTA)\n",
             p.mode, p.M, p.N, p.K, block_n, pick_epi(pp), s[9], s[0], s[1], s[2], s[3], s[4], s[6], s[5], s[7], s[8], s[10],
-            s[11], s[12]);
+            s[11], s[12], s[14] > 0 ? s[13] / s[14] : 0.0, s[14]);
     return r;
   }
   if (pp.halo) {
