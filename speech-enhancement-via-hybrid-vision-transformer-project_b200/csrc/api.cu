@@ -899,7 +899,14 @@ int hvit_plan_create(const hvit_model_cfg* cfg, const hvit_weights* weights, int
   return HVIT_OK;
 }
 
-void hvit_plan_destroy(hvit_plan* plan) { delete plan; }
+void hvit_plan_destroy(hvit_plan* plan) {
+  if (plan != nullptr && plan->l2_pin_bytes > 0 && plan->l2_pin_ratio > 0.f) {
+    // give the residual stream's persisting L2 lines back (the carve-out limit itself stays: other plans may use it)
+    cudaCtxResetPersistingL2Cache();
+    cudaGetLastError();
+  }
+  delete plan;
+}
 
 static Ctx enhance_ctx(hvit_plan* plan, const float* wave_in, float* wave_out, int normalize, void* stream) {
   Ctx c;
