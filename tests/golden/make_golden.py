@@ -3,7 +3,8 @@
 Run in the build container only (it needs /root/reference, which does not exist
 on the GPU box):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py          # golden_v1 (tiny / 1 s / 2 s cases, literal-init forward)
+    python tests/golden/make_golden.py --v2     # golden_v2 (4 s / 10 s, seeds 0-2, SNR 0/5/10 dB, W % 4 == 0, literal init)
 
 What runs here is the reference's own code, unmodified:
   * ``models.HybridViT`` imported from /root/reference (models/hybrid_vit.py),
@@ -76,22 +77,40 @@ CASES = {
     "default_1s": ({}, 0, 1.0, 0, None),
     "default_2s": ({}, 1, 2.0, 1, None),
 }
+# golden_v2: the headline clip length (4 s), the longest latency-sweep length (10 s, N = 1248 tokens), three weight
+# seeds, SNR 0 / 5 / 10 dB, a clip whose last encoder map is a multiple of the patch size (T = 512 -> W = 128 = 4 * 32;
+# the other cases leave a remainder of 1..3 columns), and the reference's LITERAL initialisation (BatchNorm 0/1
+# statistics, saturated tanh) through the whole enhance path.
+#   name: (cfg overrides, weight seed | "literal", clip seconds, clip seed, n_samples override, snr_db)
+CASES_V2 = {
+    "default_4s_s0_snr0": ({}, 0, 4.0, 10, None, 0.0),
+    "default_4s_s1_snr10": ({}, 1, 4.0, 11, None, 10.0),
+    "default_4s_s2_snr5": ({}, 2, 4.0, 12, None, 5.0),
+    "default_10s": ({}, 0, 10.0, 13, None, 5.0),
+    "default_w128": ({}, 1, None, 14, 511 * 128, 5.0),
+    "literal_1s": ({}, "literal", 1.0, 15, None, 5.0),
+}
 STAGE_SAMPLES = 1024
+MODEL_OUT_SAMPLES = 65536   # v2 stores the model output at seeded random positions (+ its max |.|), not the full map
 
 
-def main():
-    _install_shims()
-    from models import HybridViT  # reference
-    enh_mod = _load_by_path("ref_enhancer", os.path.join(REF, "inference", "enhancer.py"))
+def run_cases(HybridViT, enh_mod, cases, v2):
     out = {}
     meta = {}
-    for name, (over, wseed, secs, cseed, nsamp) in CASES.items():
+    for name, spec in cases.items():
+        over, wseed, secs, cseed, nsamp = spec[:5]
+        snr_db = spec[5] if v2 else 5.0
         cfg = O.full_cfg(over)
-        sd = O.make_state_dict(cfg, seed=wseed)
         kwargs = {k: cfg[k] for k in ("encoder_channels", "embed_dim", "num_heads", "num_layers", "decoder_channels")}
-        model = HybridViT(**kwargs).eval()
-        model.load_state_dict(sd, strict=True)
-        clean, noisy = O.synth_clip(seconds=secs or 1.0, seed=cseed, n_samples=nsamp)
+        if wseed == "literal":      # the reference's own _init_weights under torch.manual_seed(0)
+            torch.manual_seed(0)
+            model = HybridViT(**kwargs).eval()
+            sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        else:
+            sd = O.make_state_dict(cfg, seed=wseed)
+            model = HybridViT(**kwargs).eval()
+            model.load_state_dict(sd, strict=True)
+        clean, noisy = O.synth_clip(seconds=secs or 1.0, seed=cseed, n_samples=nsamp, snr_db=snr_db)
         enhancer = enh_mod.AudioEnhancer(model, device="cpu")
         y = enhancer.enhance(noisy, normalize=True)
         # forward-only golden on the normalised magnitude the enhancer feeds the model
@@ -117,7 +136,14 @@ def main():
             fwd2, attns = model(x, return_attentions=True)
         assert torch.equal(fwd, fwd2)
         out[f"{name}/waveform"] = np.asarray(y, dtype=np.float32)
-        out[f"{name}/model_out"] = fwd.squeeze().numpy()
+        if v2:
+            flat = fwd.reshape(-1).numpy()
+            idx = np.random.default_rng(4321).integers(0, flat.size, size=MODEL_OUT_SAMPLES)
+            # (positions are default_rng(4321).integers(0, size, MODEL_OUT_SAMPLES): regenerated by the tests)
+            out[f"{name}/model_out_val"] = flat[idx]
+            out[f"{name}/model_out_absmax"] = np.float32(np.abs(flat).max())
+        else:
+            out[f"{name}/model_out"] = fwd.squeeze().numpy()
         out[f"{name}/attn0_head0_row0"] = attns[0][0, 0, 0].numpy()
         rng = np.random.default_rng(1234)
         for sn, t in stages.items():
@@ -129,7 +155,24 @@ def main():
         meta[name] = dict(cfg=over, weight_seed=wseed, seconds=secs, clip_seed=cseed, n_samples=nsamp,
                           weights_sha256=O.state_dict_digest(sd), T=int(x.shape[-1]),
                           out_std=float(fwd.std()), sisdr_clean_vs_ref=O.si_sdr(clean, y))
+        if v2:
+            meta[name]["snr_db"] = snr_db
         print(name, meta[name])
+    return out, meta
+
+
+def main():
+    _install_shims()
+    from models import HybridViT  # reference
+    enh_mod = _load_by_path("ref_enhancer", os.path.join(REF, "inference", "enhancer.py"))
+    if "--v2" in sys.argv:
+        out, meta = run_cases(HybridViT, enh_mod, CASES_V2, v2=True)
+        np.savez_compressed(os.path.join(HERE, "golden_v2.npz"), **out)
+        with open(os.path.join(HERE, "golden_v2.json"), "w") as f:
+            json.dump(meta, f, indent=1, sort_keys=True)
+        print("wrote", os.path.getsize(os.path.join(HERE, "golden_v2.npz")), "bytes")
+        return
+    out, meta = run_cases(HybridViT, enh_mod, CASES, v2=False)
     # literal reference init: digest only (28M params are not stored)
     torch.manual_seed(0)
     ref0 = HybridViT().eval()

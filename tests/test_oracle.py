@@ -64,6 +64,43 @@ def test_oracle_stages_match_reference(oracle, golden, name):
     np.testing.assert_allclose(attns[0][0, 0, 0].numpy(), arrays[f"{name}/attn0_head0_row0"], rtol=1e-4, atol=1e-7)
 
 
+CASES_V2 = ["default_4s_s0_snr0", "default_4s_s1_snr10", "default_4s_s2_snr5", "default_10s", "default_w128", "literal_1s"]
+
+
+@pytest.mark.parametrize("name", CASES_V2)
+def test_oracle_matches_reference_v2(oracle, golden2, name):
+    """golden_v2: headline 4 s clips (three weight seeds, SNR 0/5/10 dB), 10 s (N = 1248 tokens), a W % 4 == 0 length
+    and the reference's literal initialisation - waveform, model output (seeded sample), SI-SDR and per-stage samples."""
+    from conftest import golden_case, golden_model_out_err
+    arrays, meta = golden2
+    m = meta[name]
+    cfg, sd, clean, noisy = golden_case(oracle, m)
+    assert oracle.state_dict_digest(sd) == m["weights_sha256"]
+    dbg = {}
+    y = oracle.enhance(sd, noisy, cfg, debug=dbg)
+    ref_y = arrays[f"{name}/waveform"]
+    assert y.shape == ref_y.shape and dbg["model_out"].shape[1] == m["T"]
+    assert oracle.max_rel_err(y, ref_y) <= 1e-4
+    assert golden_model_out_err(oracle, arrays, name, dbg["model_out"]) <= 1e-4
+    assert abs(oracle.si_sdr(clean, y) - m["sisdr_clean_vs_ref"]) <= 0.05
+    if name in ("default_4s_s0_snr0", "default_w128"):   # per-stage samples (one remainder-1 and one W % 4 == 0 case)
+        x = torch.from_numpy(dbg["noisy_mag_norm"]).float()[None, None]
+        stages = {}
+        with torch.no_grad():
+            oracle.hybrid_vit_forward(sd, x, cfg, stages=stages)
+        B, C, H, W = stages["to_feature_map"].shape
+        stages["to_feature_map"] = stages["to_feature_map"].reshape(B, C, H * W).transpose(1, 2)
+        checked = 0
+        for key in arrays.files:
+            if key.startswith(f"{name}/stage/") and key.endswith("/idx"):
+                sn = key.split("/")[2]
+                val = arrays[key[:-3] + "val"]
+                ours = stages[sn].reshape(-1).numpy()[arrays[key]]
+                assert np.abs(ours - val).max() / max(np.abs(val).max(), 1e-6) <= 2e-5, sn
+                checked += 1
+        assert checked >= 9
+
+
 def test_stft_against_torch(oracle):
     _, noisy = oracle.synth_clip(seconds=1.3, seed=7, n_samples=20777)
     s = oracle.stft(noisy)
