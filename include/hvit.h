@@ -93,6 +93,45 @@ typedef struct hvit_weights {
   const float* head_w;      /* [3][3][C] fp32, last decoder block */
 } hvit_weights;
 
+/* The reference state_dict (models/hybrid_vit.py:172-284) as fp32 DEVICE pointers in the
+ * layouts torch stores them: conv weights [Cout][Cin][kh][kw], linear weights [out][in], BatchNorm weight / bias /
+ * running_mean / running_var [C].  Input of hvit_pack_weights.  Index i of enc_* = encoder block i (0 = stem), of
+ * dec_* = decoder block i (n_dec - 1 = the 1-channel head, no BatchNorm), of skip_* = skip_projections[i]. */
+typedef struct hvit_ref_weights {
+  const float* enc_conv_w[HVIT_MAX_STAGES];
+  const float* enc_bn_w[HVIT_MAX_STAGES];
+  const float* enc_bn_b[HVIT_MAX_STAGES];
+  const float* enc_bn_mean[HVIT_MAX_STAGES];
+  const float* enc_bn_var[HVIT_MAX_STAGES];
+  const float* patch_w;   /* patch_embed.projection.weight [D][C][p][p] */
+  const float* patch_b;
+  const float* pos_embed; /* pos_encoding.pos_embed [1][pos_len][D] */
+  int pos_len;
+  const float* ln1_w[HVIT_MAX_LAYERS];
+  const float* ln1_b[HVIT_MAX_LAYERS];
+  const float* ln2_w[HVIT_MAX_LAYERS];
+  const float* ln2_b[HVIT_MAX_LAYERS];
+  const float* qkv_w[HVIT_MAX_LAYERS];
+  const float* qkv_b[HVIT_MAX_LAYERS];
+  const float* proj_w[HVIT_MAX_LAYERS];
+  const float* proj_b[HVIT_MAX_LAYERS];
+  const float* fc1_w[HVIT_MAX_LAYERS];
+  const float* fc1_b[HVIT_MAX_LAYERS];
+  const float* fc2_w[HVIT_MAX_LAYERS];
+  const float* fc2_b[HVIT_MAX_LAYERS];
+  const float* lnf_w;     /* transformer.norm */
+  const float* lnf_b;
+  const float* tofm_w;    /* to_feature_map */
+  const float* tofm_b;
+  const float* dec_conv_w[HVIT_MAX_STAGES];
+  const float* dec_bn_w[HVIT_MAX_STAGES];
+  const float* dec_bn_b[HVIT_MAX_STAGES];
+  const float* dec_bn_mean[HVIT_MAX_STAGES];
+  const float* dec_bn_var[HVIT_MAX_STAGES];
+  const float* skip_w[HVIT_MAX_STAGES];  /* [Cdec_i][Cenc_rev_i][1][1] */
+  const float* skip_b[HVIT_MAX_STAGES];
+} hvit_ref_weights;
+
 typedef struct hvit_plan hvit_plan;
 
 const char* hvit_last_error(void);
@@ -100,16 +139,33 @@ int hvit_version(void);
 /* 1 when the current CUDA device is compute capability 10.x, 0 otherwise, negative on CUDA error. */
 int hvit_device_ok(void);
 
+/* Weight packing on the device (replaces the parameter half of HybridViT.__init__ / load_state_dict for this path,
+ * models/hybrid_vit.py:172-284, utils/checkpoint.py:127-161): BatchNorm(eval, eps 1e-5) folded to scale / shift (into
+ * the conv weights in the 16-bit modes), conv kernels re-laid out K-major [Cout][ky][kx][Cin], "nearest x2 + 3x3"
+ * decoder kernels pre-summed into four 2x2 parity kernels, conversion to the plan's operand type.  Everything the plan
+ * reads is written into `packed_dev` (hvit_packed_weights_bytes(cfg) bytes, 256-byte aligned, caller-owned), so the
+ * reference tensors may be freed once the stream has passed this call; `out` receives pointers into `packed_dev`. */
+size_t hvit_packed_weights_bytes(const hvit_model_cfg* cfg, int pos_len);
+int hvit_pack_weights(const hvit_model_cfg* cfg, const hvit_ref_weights* ref, void* packed_dev, size_t packed_bytes,
+                      hvit_weights* out, void* stream);
+
 /* Bytes of device workspace a plan needs.  n_samples > 0 adds the STFT/iSTFT buffers (enhance path) and
  * requires F == 257, T == 1 + n_samples / 128.  Returns 0 and sets the error string on bad input. */
 size_t hvit_workspace_bytes(const hvit_model_cfg* cfg, int B, int F, int T, int n_samples);
 
 /* Builds the launch plan (layer geometry, TMA tensor maps over `workspace_dev` and the weight buffers).
  * Replaces the module-construction half of HybridViT.__init__ / AudioEnhancer.__init__
- * (models/hybrid_vit.py:36-170, inference/enhancer.py:25-53). */
+ * (models/hybrid_vit.py:36-170, inference/enhancer.py:25-53).
+ * `stream`: the one-time setup kernels (stem position matrices, FFT tables) are enqueued on it, after whatever
+ * produced `weights` on that stream; the plan can be used on the same stream immediately, on another stream once
+ * the caller has ordered it after this call.  No device-wide synchronisation. */
 int hvit_plan_create(const hvit_model_cfg* cfg, const hvit_weights* weights, int B, int F, int T, int n_samples,
-                     void* workspace_dev, size_t workspace_bytes, hvit_plan** plan_out);
+                     void* workspace_dev, size_t workspace_bytes, void* stream, hvit_plan** plan_out);
 void hvit_plan_destroy(hvit_plan* plan);
+/* Debug mode (tests): the plan additionally stores intermediates nothing downstream reads - the pre-tanh "logits" of the
+ * head and, on the enhance path, the resized model output "model_out" [B,257,T].  Off by default (they cost HBM
+ * traffic: 33 MB + 2 MB per 64 x 4 s batch). */
+int hvit_plan_set_debug(hvit_plan* plan, int on);
 
 /* HybridViT.forward (models/hybrid_vit.py:396-469), eval mode.
  *   x_dev: fp32 [B,1,F,T]   y_dev: fp32 [B,1,F,T]
@@ -124,8 +180,9 @@ int hvit_forward(hvit_plan* plan, const float* x_dev, float* y_dev, float* attn_
 int hvit_enhance(hvit_plan* plan, const float* wave_in_dev, float* wave_out_dev, int normalize, void* stream);
 
 /* Introspection for tests: byte offset (into the workspace), and dims of a named internal buffer.
- * Names: "enc<i>", "tokens", "ln", "qkv", "attn", "mlp", "cat<i>", "dec_last", "logits", "tanh", "model_out",
- * "mag", "spec", "max_val", "mag_max", "frames".  dims receives up to 4 ints; returns the rank or negative. */
+ * Names: "enc<i>", "tokens", "ln", "qkv", "attn", "mlp", "cat<i>", "logits" (debug mode), "tanh", and for enhance
+ * plans "model_out" (debug mode), "mag", "max_val", "mag_max".  dims receives up to 4 ints; returns the rank or
+ * negative. */
 int hvit_plan_buffer(const hvit_plan* plan, const char* name, size_t* offset, int* dims, int* elem_bytes);
 /* Number of kernels one hvit_forward / hvit_enhance call launches. */
 int hvit_plan_launch_count(const hvit_plan* plan, int enhance);
@@ -171,6 +228,19 @@ int hvit_stem_16(const float* x_dev, const void* mag_max_dev, const float* w_dev
  * accumulation; logits_dev (nullable) receives the pre-activation, tanh_dev the tanh.  w_dev fp32 [3][3][C]. */
 int hvit_head_16(const void* x_dev, const float* w_dev, float* logits_dev, float* tanh_dev, int B, int H, int W, int C,
                  int f16, void* stream);
+/* PatchEmbedding + PositionalEncoding (models/components.py:282-307,310-386): p x p / stride p convolution with bias on
+ * NHWC bf16/fp16 x [B,H,W,C] (H % p == 0; trailing W % p columns are dropped like the reference's conv does), plus
+ * pos[:N] -> fp32 tokens [B*N, D], N = (H/p)*(W/p), token n = h'*(W/p) + w'.  w_dev [D][p][p][C] 16-bit, pos_dev fp32
+ * [>= N][D]. */
+int hvit_patch_embed_16(const void* x_dev, int B, int H, int W, int C, const void* w_dev, const float* bias_dev,
+                        const float* pos_dev, int patch, int D, float* tokens_dev, int f16, void* stream);
+/* Skip path of forward_decoder for one decoder block (models/hybrid_vit.py:367-389): 1x1 projection with bias of the
+ * encoder feature src [B,Hs,Ws,Cs], bilinear resize (align_corners=False) to [Hd,Wd], written into channels
+ * [c_off, c_off + Cdec) of the NHWC concat buffer cat [B,Hd,Wd,Ccat] (torch.cat never exists).  Evaluated as
+ * sample-then-project, which is exact.  w_dev [Cdec][Cs] 16-bit; scratch_dev: B*Hd*Wd*Cs 16-bit elements. */
+int hvit_skip_concat_16(const void* src_dev, int B, int Hs, int Ws, int Cs, const void* w_dev, const float* bias_dev,
+                        int Cdec, void* cat_dev, int Hd, int Wd, int Ccat, int c_off, void* scratch_dev, int f16,
+                        void* stream);
 /* Multi-head self-attention core, head_dim 64 (attention.py:86-105). qkv: [B*N, 3D]; out: [B*N, D]. */
 int hvit_attention_16(const void* qkv_dev, void* out_dev, int B, int N, int heads, int f16, void* stream);
 int hvit_attention_f32(const float* qkv_dev, float* out_dev, float* probs_dev, int B, int N, int heads, void* stream);

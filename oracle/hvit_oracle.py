@@ -302,6 +302,38 @@ def enhance(sd: Dict[str, torch.Tensor], noisy_audio: np.ndarray, cfg: Optional[
     return y.astype(np.float32)
 
 
+def enhance_batch(sd: Dict[str, torch.Tensor], noisy_batch: np.ndarray, cfg: Optional[dict] = None,
+                  normalize: bool = True, chunk: int = 16) -> np.ndarray:
+    """Equal-length clips [B, n] -> [B, n]: the same per-clip arithmetic as ``enhance`` (reference enhancer.py:55-135
+    applied clip by clip), with the model forward batched over ``chunk`` clips at a time (the reference's forward
+    accepts a batch, hybrid_vit.py:396-411; chunking only bounds the CPU memory of the fp32 activations).  Used by
+    bench.py as the same-configuration CPU arm (batch 64)."""
+    x = np.asarray(noisy_batch, dtype=np.float32)
+    B, n = x.shape
+    out = np.zeros_like(x)
+    for c0 in range(0, B, chunk):
+        xs = x[c0:c0 + chunk]
+        max_vals, specs, mags, mag_maxs = [], [], [], []
+        for xi in xs:
+            mv = np.abs(xi).max() if (normalize and xi.size) else np.float32(1.0)
+            if not (normalize and mv > 1e-8):
+                mv = 1.0
+            sp = stft(xi / mv if mv != 1.0 else xi)
+            mg = np.abs(sp)
+            mm = mg.max()
+            if not mm > 1e-8:
+                mm = 1.0
+            max_vals.append(mv); specs.append(sp); mags.append(mg / mm if mm != 1.0 else mg); mag_maxs.append(mm)
+        t = torch.from_numpy(np.stack(mags)).float()[:, None]
+        with torch.no_grad():
+            y = hybrid_vit_forward(sd, t, cfg)[:, 0].numpy()
+        for i, (mv, sp, mm) in enumerate(zip(max_vals, specs, mag_maxs)):
+            enh_spec = (y[i] * mm) * np.exp(1j * np.angle(sp))
+            w = istft(enh_spec.astype(np.complex64), length=n)
+            out[c0 + i] = w * mv if normalize else w
+    return out
+
+
 # ----------------------------------------------------------------------------
 # Parity metrics (SI-SDR follows reference evaluation/metrics.py:100-145)
 # ----------------------------------------------------------------------------

@@ -45,15 +45,37 @@ class Weights(C.Structure):
     ]
 
 
+class RefWeights(C.Structure):
+    """struct hvit_ref_weights: the reference state_dict as fp32 device pointers (input of hvit_pack_weights)."""
+    _fields_ = [
+        ("enc_conv_w", _VP * MAX_STAGES), ("enc_bn_w", _VP * MAX_STAGES), ("enc_bn_b", _VP * MAX_STAGES),
+        ("enc_bn_mean", _VP * MAX_STAGES), ("enc_bn_var", _VP * MAX_STAGES),
+        ("patch_w", _VP), ("patch_b", _VP), ("pos_embed", _VP), ("pos_len", C.c_int),
+        ("ln1_w", _VP * MAX_LAYERS), ("ln1_b", _VP * MAX_LAYERS), ("ln2_w", _VP * MAX_LAYERS),
+        ("ln2_b", _VP * MAX_LAYERS),
+        ("qkv_w", _VP * MAX_LAYERS), ("qkv_b", _VP * MAX_LAYERS), ("proj_w", _VP * MAX_LAYERS),
+        ("proj_b", _VP * MAX_LAYERS),
+        ("fc1_w", _VP * MAX_LAYERS), ("fc1_b", _VP * MAX_LAYERS), ("fc2_w", _VP * MAX_LAYERS),
+        ("fc2_b", _VP * MAX_LAYERS),
+        ("lnf_w", _VP), ("lnf_b", _VP), ("tofm_w", _VP), ("tofm_b", _VP),
+        ("dec_conv_w", _VP * MAX_STAGES), ("dec_bn_w", _VP * MAX_STAGES), ("dec_bn_b", _VP * MAX_STAGES),
+        ("dec_bn_mean", _VP * MAX_STAGES), ("dec_bn_var", _VP * MAX_STAGES),
+        ("skip_w", _VP * MAX_STAGES), ("skip_b", _VP * MAX_STAGES),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/hvit.h declares
 _I, _F, _SZ = C.c_int, C.c_float, C.c_size_t
 SYMBOLS = {
     "hvit_last_error": (C.c_char_p, []),
     "hvit_version": (_I, []),
     "hvit_device_ok": (_I, []),
+    "hvit_packed_weights_bytes": (_SZ, [C.POINTER(ModelCfg), _I]),
+    "hvit_pack_weights": (_I, [C.POINTER(ModelCfg), C.POINTER(RefWeights), _VP, _SZ, C.POINTER(Weights), _VP]),
     "hvit_workspace_bytes": (_SZ, [C.POINTER(ModelCfg), _I, _I, _I, _I]),
-    "hvit_plan_create": (_I, [C.POINTER(ModelCfg), C.POINTER(Weights), _I, _I, _I, _I, _VP, _SZ, C.POINTER(_VP)]),
+    "hvit_plan_create": (_I, [C.POINTER(ModelCfg), C.POINTER(Weights), _I, _I, _I, _I, _VP, _SZ, _VP, C.POINTER(_VP)]),
     "hvit_plan_destroy": (None, [_VP]),
+    "hvit_plan_set_debug": (_I, [_VP, _I]),
     "hvit_forward": (_I, [_VP, _VP, _VP, _VP, _VP]),
     "hvit_enhance": (_I, [_VP, _VP, _VP, _I, _VP]),
     "hvit_plan_buffer": (_I, [_VP, C.c_char_p, C.POINTER(_SZ), C.POINTER(_I * 4), C.POINTER(_I)]),
@@ -69,6 +91,8 @@ SYMBOLS = {
     "hvit_conv3x3_f32": (_I, [_VP, _VP, _VP, _VP, _I, _I, _VP, _I, _I, _I, _I, _I, _VP]),
     "hvit_stem_16": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "hvit_head_16": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),
+    "hvit_patch_embed_16": (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _VP, _I, _I, _VP, _I, _VP]),
+    "hvit_skip_concat_16": (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _I, _VP, _I, _I, _I, _I, _VP, _I, _VP]),
     "hvit_attention_16": (_I, [_VP, _VP, _I, _I, _I, _I, _VP]),
     "hvit_attention_f32": (_I, [_VP, _VP, _VP, _I, _I, _I, _VP]),
     "hvit_layernorm": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _F, _VP]),

@@ -1,5 +1,6 @@
 // C ABI of libhvit_sm100.so (declared in include/hvit.h): launch plan for HybridViT.forward /
 // AudioEnhancer.enhance, TMA tensor-map construction, per-kernel test entry points, error plumbing.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -37,37 +38,72 @@ static thread_local L2Window g_l2_window = {nullptr, 0, 0.f};
 const L2Window& l2_window() { return g_l2_window; }
 void l2_window_set(void* base, size_t bytes, float hit_ratio) { g_l2_window = L2Window{base, bytes, hit_ratio}; }
 
-// Persisting-L2 carve-out for the residual stream (once per process): returns the usable window hit ratio for a
-// buffer of `bytes` (0 = feature unavailable or disabled with HVIT_NO_L2PIN=1).
-static float l2_pin_ratio(size_t bytes) {
-  static int max_persist = -1;
-  static size_t carve = 0;
-  if (max_persist < 0) {
-    max_persist = 0;
+// ------------------------------------------------------------------------------------------ per-device state
+// One process may drive several GPUs (a model on cuda:1 after one on cuda:0): everything cached below is keyed by the
+// CUDA device that is current when it is asked for.
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    dev = 0;
+  }
+  return dev < 0 ? 0 : (dev >= kMaxDevices ? kMaxDevices - 1 : dev);
+}
+
+struct DeviceState {
+  int sms = 0;                 // multiprocessor count
+  int max_persist = -1;        // cudaDevAttrMaxPersistingL2CacheSize (-1: not queried yet, 0: unavailable / disabled)
+  int max_window = 0;          // cudaDevAttrMaxAccessPolicyWindowSize
+  size_t carve = 0;            // current cudaLimitPersistingL2CacheSize set by this library
+  size_t carve_before = 0;     // the limit found before the library first raised it (restored when the last plan goes)
+  int pinned_plans = 0;        // live plans that use the carve-out
+};
+static DeviceState g_dev[kMaxDevices];
+
+// Persisting-L2 window for the residual stream: returns the window size in bytes (<= the device's maximum access-policy
+// window) and its hit ratio for a buffer of `bytes`; 0 bytes = feature unavailable or disabled with HVIT_NO_L2PIN=1.
+static size_t l2_pin_window(size_t bytes, float* ratio) {
+  *ratio = 0.f;
+  const int dev = current_device();
+  DeviceState& d = g_dev[dev];
+  if (d.max_persist < 0) {
+    d.max_persist = 0;
     const char* e = getenv("HVIT_NO_L2PIN");
     if (!(e != nullptr && e[0] == '1')) {
-      int dev = 0, v = 0;
-      cudaGetDevice(&dev);
-      if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, dev) == cudaSuccess && v > 0) max_persist = v;
+      int v = 0, wv = 0;
+      if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, dev) == cudaSuccess && v > 0 &&
+          cudaDeviceGetAttribute(&wv, cudaDevAttrMaxAccessPolicyWindowSize, dev) == cudaSuccess && wv > 0) {
+        d.max_persist = v;
+        d.max_window = wv;
+      }
       cudaGetLastError();
     }
   }
-  if (max_persist <= 0 || bytes == 0) return 0.f;
-  size_t want = bytes < static_cast<size_t>(max_persist) ? bytes : static_cast<size_t>(max_persist);
+  if (d.max_persist <= 0 || bytes == 0) return 0;
+  // the window itself may not exceed the device limit (a larger num_bytes makes the launch attribute invalid): pin a
+  // prefix of the buffer; the hit ratio then spreads the carve-out over that prefix
+  const size_t window = bytes < static_cast<size_t>(d.max_window) ? bytes : static_cast<size_t>(d.max_window);
+  size_t want = window < static_cast<size_t>(d.max_persist) ? window : static_cast<size_t>(d.max_persist);
   if (const char* e = getenv("HVIT_L2PIN_MB")) {  // tuning knob: carve-out size in MB (<= the device maximum)
     const size_t mb = static_cast<size_t>(atoi(e)) << 20;
     if (mb > 0 && mb < want) want = mb;
   }
-  if (want > carve) {
+  if (want > d.carve) {
+    if (d.carve == 0) {
+      size_t before = 0;
+      if (cudaDeviceGetLimit(&before, cudaLimitPersistingL2CacheSize) == cudaSuccess) d.carve_before = before;
+      cudaGetLastError();
+    }
     if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) {
       cudaGetLastError();
-      max_persist = 0;
-      return 0.f;
+      d.max_persist = 0;
+      return 0;
     }
-    carve = want;
+    d.carve = want;
   }
-  const float r = static_cast<float>(static_cast<double>(carve) / static_cast<double>(bytes));
-  return r > 1.f ? 1.f : r;
+  const float r = static_cast<float>(static_cast<double>(d.carve) / static_cast<double>(window));
+  *ratio = r > 1.f ? 1.f : r;
+  return window;
 }
 
 int check_launch(const char* what) {
@@ -99,12 +135,13 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// element type of the tensor maps being built (set by the plan / entry point before encoding)
-static thread_local int g_tmap_f16 = 0;
+// Element type of a tensor map: the two 16-bit operand types of the tensor-core path, or fp32 (epilogue outputs).
+enum TmapType { TM_BF16 = 0, TM_F16 = 1, TM_F32 = 2 };
+static TmapType tm16(int f16) { return f16 ? TM_F16 : TM_BF16; }
 
-// 16-bit tensor (bf16 or fp16), 128-byte swizzle, zero fill out of bounds. dims/box innermost first; strides (bytes) for dims 1..rank-1.
-static int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                     const uint32_t* box, int f32 = 0, int no_swizzle = 0) {
+// 128-byte swizzle (unless no_swizzle), zero fill out of bounds. dims/box innermost first; strides (bytes) for dims 1..rank-1.
+static int make_tmap(CUtensorMap* m, const void* base, TmapType type, int rank, const uint64_t* dims,
+                     const uint64_t* strides, const uint32_t* box, int no_swizzle = 0) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -119,7 +156,9 @@ static int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t*
     es[i] = 1;
     if (i > 0) gs[i - 1] = strides[i - 1];
   }
-  const CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (g_tmap_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+  const CUtensorMapDataType dt = type == TM_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : (type == TM_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  const CUresult r = fn(m, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
                         gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         no_swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -132,59 +171,56 @@ static int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t*
   return HVIT_OK;
 }
 
-static int tmap_matrix(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+static int tmap_matrix(CUtensorMap* m, const void* base, int f16, long long rows, long long cols, long long ld, int box_rows) {
   const uint64_t dims[2] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(rows)};
   const uint64_t strides[1] = {static_cast<uint64_t>(ld) * 2};
   const uint32_t box[2] = {64, static_cast<uint32_t>(box_rows)};
-  return make_tmap(m, base, 2, dims, strides, box);
+  return make_tmap(m, base, tm16(f16), 2, dims, strides, box);
 }
 
-static int tmap_image(CUtensorMap* m, const void* base, int B, int H, int Hpitch, int W, int C, int Wt, int Ht) {
+static int tmap_image(CUtensorMap* m, const void* base, int f16, int B, int H, int Hpitch, int W, int C, int Wt, int Ht) {
   const uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
                             static_cast<uint64_t>(B)};
   const uint64_t strides[3] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(W) * C * 2,
                                static_cast<uint64_t>(Hpitch) * W * C * 2};
   const uint32_t box[4] = {64, static_cast<uint32_t>(Wt), static_cast<uint32_t>(Ht), 1};
-  return make_tmap(m, base, 4, dims, strides, box);
+  return make_tmap(m, base, tm16(f16), 4, dims, strides, box);
 }
 
-static int tmap_patch(CUtensorMap* m, const void* base, int B, int Hq, int W, int C, int p, int Wp, int Wt, int Ht) {
+static int tmap_patch(CUtensorMap* m, const void* base, int f16, int B, int Hq, int W, int C, int p, int Wp, int Wt, int Ht) {
   const uint64_t dims[5] = {static_cast<uint64_t>(C), static_cast<uint64_t>(p), static_cast<uint64_t>(Wp),
                             static_cast<uint64_t>(p), static_cast<uint64_t>(B) * Hq};
   const uint64_t strides[4] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(p) * C * 2,
                                static_cast<uint64_t>(W) * C * 2, static_cast<uint64_t>(p) * W * C * 2};
   const uint32_t box[5] = {64, 1, static_cast<uint32_t>(Wt), 1, static_cast<uint32_t>(Ht)};
-  return make_tmap(m, base, 5, dims, strides, box);
+  return make_tmap(m, base, tm16(f16), 5, dims, strides, box);
 }
 
-static int tmap_qkv(CUtensorMap* m, const void* base, int B, int N, int D) {
+static int tmap_qkv(CUtensorMap* m, const void* base, int f16, int B, int N, int D) {
   const uint64_t dims[3] = {static_cast<uint64_t>(3) * D, static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
   const uint64_t strides[2] = {static_cast<uint64_t>(3) * D * 2, static_cast<uint64_t>(N) * 3 * D * 2};
   const uint32_t box[3] = {64, 128, 1};
-  return make_tmap(m, base, 3, dims, strides, box);
+  return make_tmap(m, base, tm16(f16), 3, dims, strides, box);
 }
 
 // attention output [B*N, D] 16-bit as a (D, N, B) map: 128-row x 64-column (one head) store boxes, clipped at N
-static int tmap_attn_out(CUtensorMap* m, const void* base, int B, int N, int D) {
+static int tmap_attn_out(CUtensorMap* m, const void* base, int f16, int B, int N, int D) {
   const uint64_t dims[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
   const uint64_t strides[2] = {static_cast<uint64_t>(D) * 2, static_cast<uint64_t>(N) * D * 2};
   const uint32_t box[3] = {64, 128, 1};
-  return make_tmap(m, base, 3, dims, strides, box);
+  return make_tmap(m, base, tm16(f16), 3, dims, strides, box);
 }
 
-// CTA-pair kernel by default; HVIT_IGEMM_1CTA=1 selects the single-CTA kernel (A/B comparison, debugging)
-static bool use_2cta() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("HVIT_IGEMM_1CTA");
-    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+// Number of row panels the MLP (fc1 -> GELU -> fc2) of a transformer block is split into (see build_steps).
+// HVIT_MLP_PANELS overrides; default: as few panels as keep one panel's hidden activation under ~40 MB.
+static int mlp_panels(int M, int hidden, int es, int tensor_core) {
+  if (const char* e = getenv("HVIT_MLP_PANELS")) {
+    const int v = atoi(e);
+    if (v >= 1) return v;
   }
-  return v == 1;
+  (void)M; (void)hidden; (void)es; (void)tensor_core;
+  return 1;
 }
-static int launch_igemm_any(const IgemmParams& q, const IgemmMaps& mp, int bn, int sms, cudaStream_t s) {
-  return use_2cta() ? launch_igemm_tc2(q, mp, bn, sms, s) : launch_igemm_tc(q, mp.a, mp.b, bn, sms, s);
-}
-static int b_box_rows(int bn) { return use_2cta() ? bn / 2 : bn; }
 
 static int pick_block_n(int N) { return N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64); }
 
@@ -203,17 +239,17 @@ static void pick_tile(int H, int W, int* Wt, int* Ht) {
 
 // 4-D output (and residual) maps of the TMA-store epilogue: dim 0 = channel / column (128-byte box), dims 1..3 =
 // the tile's spatial / row coordinates as the kernel passes them (see igemm_tc2_kernel).
-static int tmap_out4(CUtensorMap* m, const void* base, int f32, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
+static int tmap_out4(CUtensorMap* m, const void* base, TmapType type, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
                      uint64_t s1, uint64_t s2, uint64_t s3, uint32_t b1, uint32_t b2) {
   const uint64_t dims[4] = {d0, d1, d2, d3};
   const uint64_t strides[3] = {s1, s2, s3};
-  const uint32_t box[4] = {f32 ? 32u : 64u, b1, b2, 1};
-  return make_tmap(m, base, 4, dims, strides, box, f32);
+  const uint32_t box[4] = {type == TM_F32 ? 32u : 64u, b1, b2, 1};
+  return make_tmap(m, base, type, 4, dims, strides, box);
 }
 
 static int make_out_maps(const IgemmParams& q, IgemmMaps* mp) {
-  const int f32 = q.out_f32;
-  const uint64_t es = f32 ? 4 : 2;
+  const TmapType ot = q.out_f32 ? TM_F32 : tm16(q.f16);
+  const uint64_t es = q.out_f32 ? 4 : 2;
   const uint64_t ld = static_cast<uint64_t>(q.ldc) * es;
   uint8_t* out = reinterpret_cast<uint8_t*>(q.out);
   const uint64_t N = q.N;
@@ -221,43 +257,42 @@ static int make_out_maps(const IgemmParams& q, IgemmMaps* mp) {
   memset(mp->out, 0, sizeof(mp->out));
   memset(&mp->res, 0, sizeof(mp->res));
   if (q.mode == IG_PLAIN) {
-    r = tmap_out4(&mp->out[0], out, f32, N, q.M, 1, 1, ld, ld * q.M, ld * q.M, 128, 1);
+    r = tmap_out4(&mp->out[0], out, ot, N, q.M, 1, 1, ld, ld * q.M, ld * q.M, 128, 1);
     if (r == HVIT_OK && q.residual != nullptr) {
       const uint64_t lr = static_cast<uint64_t>(q.ldr) * 4;
-      r = tmap_out4(&mp->res, q.residual, 1, N, q.M, 1, 1, lr, lr * q.M, lr * q.M, 128, 1);
+      r = tmap_out4(&mp->res, q.residual, TM_F32, N, q.M, 1, 1, lr, lr * q.M, lr * q.M, 128, 1);
     }
   } else if (q.mode == IG_CONV3) {
     const uint64_t img = static_cast<uint64_t>(q.HoPitch) * q.Wo * ld;
     if (q.pool)
-      r = tmap_out4(&mp->out[0], out, f32, N, q.Wo, q.Ho, q.B, ld, ld * q.Wo, img, q.Wt / 2, q.Ht / 2);
+      r = tmap_out4(&mp->out[0], out, ot, N, q.Wo, q.Ho, q.B, ld, ld * q.Wo, img, q.Wt / 2, q.Ht / 2);
     else
-      r = tmap_out4(&mp->out[0], out, f32, N, q.W, q.H, q.B, ld, ld * q.Wo, img, q.Wt, q.Ht);
+      r = tmap_out4(&mp->out[0], out, ot, N, q.W, q.H, q.B, ld, ld * q.Wo, img, q.Wt, q.Ht);
   } else if (q.mode == IG_UP2) {
     const uint64_t img = static_cast<uint64_t>(q.HoPitch) * q.Wo * ld;
     for (int par = 0; par < 4 && r == HVIT_OK; ++par) {
       const uint64_t off = (static_cast<uint64_t>(par >> 1) * q.Wo + (par & 1)) * ld;
-      r = tmap_out4(&mp->out[par], out + off, f32, N, q.W, q.H, q.B, 2 * ld, 2 * ld * q.Wo, img, q.Wt, q.Ht);
+      r = tmap_out4(&mp->out[par], out + off, ot, N, q.W, q.H, q.B, 2 * ld, 2 * ld * q.Wo, img, q.Wt, q.Ht);
     }
   } else {  // IG_PATCH
     const uint64_t np = static_cast<uint64_t>(q.Hp) * q.Wp;
-    r = tmap_out4(&mp->out[0], out, f32, N, q.Wp, q.Hp, q.B, ld, ld * q.Wp, ld * np, q.Wt, q.Ht);
+    r = tmap_out4(&mp->out[0], out, ot, N, q.Wp, q.Hp, q.B, ld, ld * q.Wp, ld * np, q.Wt, q.Ht);
     if (r == HVIT_OK && q.residual != nullptr) {
       const uint64_t lr = static_cast<uint64_t>(q.ldr) * 4;
-      r = tmap_out4(&mp->res, q.residual, 1, N, q.Wp, q.Hp, q.res_mod > 0 ? 1 : q.B, lr, lr * q.Wp, lr * np, q.Wt, q.Ht);
+      r = tmap_out4(&mp->res, q.residual, TM_F32, N, q.Wp, q.Hp, q.res_mod > 0 ? 1 : q.B, lr, lr * q.Wp, lr * np, q.Wt, q.Ht);
     }
   }
   return r;
 }
 
-static int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+int num_sms() {
+  const int dev = current_device();
+  DeviceState& d = g_dev[dev];
+  if (d.sms == 0) {
+    cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+    if (d.sms <= 0) d.sms = 148;
   }
-  return n;
+  return d.sms;
 }
 
 // ------------------------------------------------------------------------------------------ plan
@@ -320,8 +355,11 @@ struct hvit_plan {
   std::vector<hvit::StepMeta> pre_meta, post_meta;
   int launches_forward;
   void* l2_pin_base = nullptr;        // residual stream kept in persisting L2 lines during the forward steps
-  size_t l2_pin_bytes = 0;
+  size_t l2_pin_bytes = 0;            // access-policy window (<= cudaDevAttrMaxAccessPolicyWindowSize), 0 = no pinning
   float l2_pin_ratio = 0.f;
+  cudaStream_t setup_stream = nullptr; // stream of the one-time setup kernels (hvit_plan_create's argument)
+  int device = -1;                    // device whose persisting-L2 carve-out this plan counts against (-1: none)
+  int debug = 0;                      // keep test-only intermediates ("model_out", "logits"), see hvit_plan_set_debug
   // tag the most recently pushed step(s)
   void tag(const std::string& name, const char* kernel, double aflops, double eflops, double bytes, int launches = 1) {
     while (meta.size() < steps.size()) meta.push_back(hvit::StepMeta{name, kernel, 0.0, 0.0, 0.0, 1});
@@ -474,12 +512,10 @@ static int build_geometry(const hvit_model_cfg& c, int B, int F, int T, int n_sa
       set_error("enhance plan needs F=257 and T=1+n/128 (got F=%d T=%d n=%d)", F, T, n_samples);
       return HVIT_E_SHAPE;
     }
-    add("model_out", 4, 3, B, F, T, 0, static_cast<size_t>(B) * F * T);
+    add("model_out", 4, 3, B, F, T, 0, static_cast<size_t>(B) * F * T);  // written only by plans in debug mode (tests)
     add("max_val", 4, 1, B, 0, 0, 0, B);
     add("mag_max", 4, 1, B, 0, 0, 0, B);
-    add("spec", 8, 3, B, F, T, 0, static_cast<size_t>(B) * F * T);
     add("mag", 4, 3, B, F, T, 0, static_cast<size_t>(B) * F * T);
-    add("frames", 4, 3, B, T, 512, 0, static_cast<size_t>(B) * T * 512);
   }
   g.total = off;
   return HVIT_OK;
@@ -513,15 +549,14 @@ static int add_linear(hvit_plan* p, const std::string& name, const void* A, int 
   if (p->cfg.precision != HVIT_PREC_FP32) {
     IgemmMaps mp;
     const int bn = pick_block_n(N);
-    g_tmap_f16 = q.f16;
-    int r = tmap_matrix(&mp.a, A, M, K, lda, 128);
+    int r = tmap_matrix(&mp.a, A, q.f16, M, K, lda, 128);
     if (r) return r;
-    r = tmap_matrix(&mp.b, W, N, K, K, b_box_rows(bn));
+    r = tmap_matrix(&mp.b, W, q.f16, N, K, K, bn / 2);
     if (r) return r;
     r = make_out_maps(q, &mp);
     if (r) return r;
     const int sms = num_sms();
-    p->steps.push_back([=](const Ctx& c) { return launch_igemm_any(q, mp, bn, sms, c.stream); });
+    p->steps.push_back([=](const Ctx& c) { return launch_igemm_tc2(q, mp, bn, sms, c.stream); });
     p->tag(name, "igemm_tc", algo_flops >= 0 ? algo_flops : fl, fl, by);
   } else {
     q.out_f32 = 1;
@@ -551,7 +586,6 @@ static int add_conv(hvit_plan* p, const std::string& name, const void* in, int B
                      9.0 * Cin * Cout) * es_;
   q.f16 = p->cfg.precision == HVIT_PREC_FP16;
   if (p->cfg.precision != HVIT_PREC_FP32) {
-    g_tmap_f16 = q.f16;
     q.K = (up2 ? 4 : 9) * Cin;
     q.pool = pool;
     q.out_f32 = 0;
@@ -561,7 +595,7 @@ static int add_conv(hvit_plan* p, const std::string& name, const void* in, int B
     // 3x3 convs keep the input tile + halo in shared memory (igemm_halo_kernel); HVIT_NO_HALO=1 selects the
     // tap-shifted TMA boxes of igemm_tc2_kernel instead (A/B comparison)
     static const bool no_halo = getenv("HVIT_NO_HALO") != nullptr && getenv("HVIT_NO_HALO")[0] == '1';
-    q.halo = (use_2cta() && !no_halo && Cin % 64 == 0 && Cout <= 512 && (!up2 || pick_block_n(Cout) <= 128)) ? 1 : 0;
+    q.halo = (!no_halo && Cin % 64 == 0 && Cout <= 512 && (!up2 || pick_block_n(Cout) <= 128)) ? 1 : 0;
     if (q.halo) {
       q.Wt = 8; q.Ht = 16;
     } else if (pool) {
@@ -580,17 +614,17 @@ static int add_conv(hvit_plan* p, const std::string& name, const void* in, int B
       const uint64_t strides[4] = {static_cast<uint64_t>(Cin) * 2, static_cast<uint64_t>(W) * Cin * 2, 16,
                                    static_cast<uint64_t>(H) * W * Cin * 2};
       const uint32_t box[5] = {8, 10, 18, 8, 1};
-      r = make_tmap(&mp.a, in, 5, dims, strides, box, 0, 1);
+      r = make_tmap(&mp.a, in, tm16(q.f16), 5, dims, strides, box, 1);
     } else {
-      r = tmap_image(&mp.a, in, B, H, H, W, Cin, q.Wt, q.Ht);
+      r = tmap_image(&mp.a, in, q.f16, B, H, H, W, Cin, q.Wt, q.Ht);
     }
     if (r) return r;
-    r = tmap_matrix(&mp.b, Wt, static_cast<long long>(up2 ? 4 : 1) * Cout, q.K, q.K, b_box_rows(bn));
+    r = tmap_matrix(&mp.b, Wt, q.f16, static_cast<long long>(up2 ? 4 : 1) * Cout, q.K, q.K, bn / 2);
     if (r) return r;
     r = make_out_maps(q, &mp);
     if (r) return r;
     const int sms = num_sms();
-    p->steps.push_back([=](const Ctx& c) { return launch_igemm_any(q, mp, bn, sms, c.stream); });
+    p->steps.push_back([=](const Ctx& c) { return launch_igemm_tc2(q, mp, bn, sms, c.stream); });
     p->tag(name, "igemm_tc", algo_fl, up2 ? algo_fl * 4.0 / 9.0 : algo_fl, by);
   } else {
     q.K = 9 * Cin;
@@ -614,6 +648,46 @@ static int add_conv(hvit_plan* p, const std::string& name, const void* in, int B
   return HVIT_OK;
 }
 
+// patch embedding step: p x p / stride p conv (+bias) + positional table -> fp32 tokens [B * Hp * Wp, D]
+// (PatchEmbedding + PositionalEncoding, models/components.py:282-307,310-386); token n = h' * Wp + w'
+static int add_patch_embed(hvit_plan* p, const void* in, int B, int H, int Hpitch, int W, int C, const void* pw,
+                           const float* pb, const float* pos, int patch, int D, float* tokens) {
+  const int bf = p->cfg.precision != HVIT_PREC_FP32 ? 1 : 0;
+  const int es = bf ? 2 : 4;
+  IgemmParams q = ig_zero();
+  q.mode = IG_PATCH;
+  q.B = B; q.H = H; q.W = W; q.Cin = C;
+  q.patch = patch; q.Hq = Hpitch / patch; q.Hp = H / patch; q.Wp = W / patch;
+  q.N = D; q.K = patch * patch * C;
+  q.shift = pb; q.residual = pos; q.ldr = D; q.res_mod = q.Hp * q.Wp;
+  q.out = tokens; q.ldc = D; q.out_f32 = 1;
+  q.f16 = p->cfg.precision == HVIT_PREC_FP16;
+  const long long M = static_cast<long long>(B) * q.Hp * q.Wp;
+  if (bf) {
+    pick_tile(q.Hp, q.Wp, &q.Wt, &q.Ht);
+    q.tiles_w = (q.Wp + q.Wt - 1) / q.Wt;
+    q.tiles_h = (q.Hp + q.Ht - 1) / q.Ht;
+    IgemmMaps mp;
+    const int bn = pick_block_n(D);
+    int r = tmap_patch(&mp.a, in, q.f16, B, q.Hq, W, C, patch, q.Wp, q.Wt, q.Ht);
+    if (r) return r;
+    r = tmap_matrix(&mp.b, pw, q.f16, D, q.K, q.K, bn / 2);
+    if (r) return r;
+    r = make_out_maps(q, &mp);
+    if (r) return r;
+    const int sms = num_sms();
+    p->steps.push_back([=](const Ctx& k) { return launch_igemm_tc2(q, mp, bn, sms, k.stream); });
+  } else {
+    const float* inf = reinterpret_cast<const float*>(in);
+    const float* wf = reinterpret_cast<const float*>(pw);
+    p->steps.push_back([=](const Ctx& k) { return launch_igemm_f32(q, inf, C, wf, k.stream); });
+  }
+  const double fl = 2.0 * M * D * q.K;
+  p->tag("patch_embed", bf ? "igemm_tc" : "igemm_f32", fl, fl,
+         (static_cast<double>(M) * q.K + static_cast<double>(D) * q.K) * es + 2.0 * M * D * 4);
+  return HVIT_OK;
+}
+
 static int build_steps(hvit_plan* p) {
   const hvit_model_cfg& c = p->cfg;
   const hvit_weights& w = p->w;
@@ -621,7 +695,6 @@ static int build_steps(hvit_plan* p) {
   const int bf = c.precision != HVIT_PREC_FP32 ? 1 : 0;  // 16-bit tensor-core path
   const int f16 = c.precision == HVIT_PREC_FP16 ? 1 : 0;
   const int dt = c.precision == HVIT_PREC_FP32 ? DT_F32 : (f16 ? DT_F16 : DT_BF16);
-  g_tmap_f16 = f16;
   const int B = g.B, D = c.embed_dim;
   char nm[32], nm2[32];
   int r;
@@ -635,13 +708,14 @@ static int build_steps(hvit_plan* p) {
     if (stem_tc) {
       // tensor-core stem: the position matrices are derived from the weights once, here
       void* apack = at<void>(p, "stem_a");
-      r = launch_stem_pack(sw, ss, apack, f16, nullptr);
+      // (enqueued on the caller's setup stream, after the packing kernels that produced sw / ss on that stream; the plan
+      // may be used on that stream right away - see hvit_plan_create in hvit.h)
+      r = launch_stem_pack(sw, ss, apack, f16, p->setup_stream);
       if (r) return r;
-      if (cudaStreamSynchronize(nullptr) != cudaSuccess) return check_launch("stem_pack(sync)");
       const int sms = num_sms();
       const int Ho = g.enc[0].H, Wo = g.enc[0].W;
       CUtensorMap tmo;  // (64 channels, Wo, Ho, B): one pooled row of a tile = 64 pixels x 128 bytes, 128B-swizzled
-      r = tmap_out4(&tmo, out, 0, 64, Wo, Ho, B, 128, static_cast<uint64_t>(Wo) * 128, static_cast<uint64_t>(Ho) * Wo * 128, 64, 1);
+      r = tmap_out4(&tmo, out, tm16(f16), 64, Wo, Ho, B, 128, static_cast<uint64_t>(Wo) * 128, static_cast<uint64_t>(Ho) * Wo * 128, 64, 1);
       if (r) return r;
       p->steps.push_back([=](const Ctx& k) { return launch_stem_tc(k.x, k.mag_max, apack, sh, tmo, f16, B, F, T, sms, k.stream); });
     } else {
@@ -667,47 +741,21 @@ static int build_steps(hvit_plan* p) {
   {
     const EncGeo& e = g.enc[c.n_enc - 1];
     snprintf(nm, sizeof(nm), "enc%d", c.n_enc - 1);
-    IgemmParams q = ig_zero();
-    q.mode = IG_PATCH;
-    q.B = B; q.H = e.H; q.W = e.W; q.Cin = e.C;
-    q.patch = c.patch_size; q.Hq = e.pitch / c.patch_size; q.Hp = g.Hp; q.Wp = g.Wp;
-    q.N = D; q.K = c.patch_size * c.patch_size * e.C;
-    q.shift = w.patch_b; q.residual = w.pos_embed; q.ldr = D; q.res_mod = g.Np;
-    q.out = at<void>(p, "tokens"); q.ldc = D; q.out_f32 = 1;
-    q.f16 = f16;
-    const void* in = at<void>(p, nm);
-    if (bf) {
-      pick_tile(g.Hp, g.Wp, &q.Wt, &q.Ht);
-      q.tiles_w = (g.Wp + q.Wt - 1) / q.Wt;
-      q.tiles_h = (g.Hp + q.Ht - 1) / q.Ht;
-      IgemmMaps mp;
-      const int bn = pick_block_n(D);
-      r = tmap_patch(&mp.a, in, B, q.Hq, e.W, e.C, c.patch_size, g.Wp, q.Wt, q.Ht);
-      if (r) return r;
-      r = tmap_matrix(&mp.b, w.patch_w, D, q.K, q.K, b_box_rows(bn));
-      if (r) return r;
-      r = make_out_maps(q, &mp);
-      if (r) return r;
-      const int sms = num_sms();
-      p->steps.push_back([=](const Ctx& k) { return launch_igemm_any(q, mp, bn, sms, k.stream); });
-    } else {
-      const float* inf = reinterpret_cast<const float*>(in);
-      const float* wf = reinterpret_cast<const float*>(w.patch_w);
-      const int lda = e.C;
-      p->steps.push_back([=](const Ctx& k) { return launch_igemm_f32(q, inf, lda, wf, k.stream); });
-    }
-    {
-      const double fl = 2.0 * g.M * D * q.K;
-      p->tag("patch_embed", bf ? "igemm_tc" : "igemm_f32", fl, fl,
-             (static_cast<double>(g.M) * q.K + static_cast<double>(D) * q.K) * g.es + 2.0 * g.M * D * 4);
-    }
+    r = add_patch_embed(p, at<void>(p, nm), B, e.H, e.pitch, e.W, e.C, w.patch_w, w.patch_b, w.pos_embed, c.patch_size, D,
+                        at<float>(p, "tokens"));
+    if (r) return r;
   }
   // 4. transformer blocks (pre-norm), residual stream fp32
   float* tok = at<float>(p, "tokens");
   if (bf && c.num_layers > 0) {
     p->l2_pin_base = tok;
-    p->l2_pin_bytes = static_cast<size_t>(g.M) * D * sizeof(float);
-    p->l2_pin_ratio = l2_pin_ratio(p->l2_pin_bytes);
+    p->l2_pin_bytes = l2_pin_window(static_cast<size_t>(g.M) * D * sizeof(float), &p->l2_pin_ratio);
+    if (p->l2_pin_bytes > 0 && p->l2_pin_ratio > 0.f) {
+      p->device = current_device();
+      ++g_dev[p->device].pinned_plans;
+    } else {
+      p->l2_pin_bytes = 0;
+    }
   }
   void* ln = at<void>(p, "ln");
   void* qkv = at<void>(p, "qkv");
@@ -718,9 +766,9 @@ static int build_steps(hvit_plan* p) {
   const float eps = c.ln_eps;
   CUtensorMap tq, to;
   if (bf && c.num_layers > 0) {
-    r = tmap_qkv(&tq, qkv, B, Np, D);
+    r = tmap_qkv(&tq, qkv, f16, B, Np, D);
     if (r) return r;
-    r = tmap_attn_out(&to, att, B, Np, D);
+    r = tmap_attn_out(&to, att, f16, B, Np, D);
     if (r) return r;
   }
   for (int l = 0; l < c.num_layers; ++l) {
@@ -754,10 +802,24 @@ static int build_steps(hvit_plan* p) {
     if (r) return r;
     p->steps.push_back([=](const Ctx& k) { return launch_layernorm(tok, g2, b2, ln, dt, M, D, eps, k.stream); });
     p->tag(L + ".norm2", "layernorm", 0, 0, ln_bytes);
-    r = add_linear(p, L + ".fc1", ln, D, w.fc1_w[l], w.fc1_b[l], ACT_GELU, nullptr, 0, 0, mlp, c.mlp_hidden, !bf, M, c.mlp_hidden, D);
-    if (r) return r;
-    r = add_linear(p, L + ".fc2", mlp, c.mlp_hidden, w.fc2_w[l], w.fc2_b[l], ACT_NONE, tok, D, 0, tok, D, 1, M, D, c.mlp_hidden);
-    if (r) return r;
+    // MLP in row panels: fc1(panel) is followed directly by fc2(panel), so the 16-bit hidden activation of a panel
+    // (M/P x hidden) is still in L2 when fc2 reads it instead of making the round trip through HBM (130 MB per layer at
+    // 64 x 4 s).  Panels are multiples of 256 rows (one CTA-pair tile).
+    {
+      const int es = g.es;
+      int panels = mlp_panels(M, c.mlp_hidden, es, bf);
+      const int rows_per = ((M + panels - 1) / panels + 255) / 256 * 256;
+      for (int r0 = 0; r0 < M; r0 += rows_per) {
+        const int rows = std::min(rows_per, M - r0);
+        const uint8_t* a1 = reinterpret_cast<const uint8_t*>(ln) + static_cast<size_t>(r0) * D * es;
+        uint8_t* h1 = reinterpret_cast<uint8_t*>(mlp) + static_cast<size_t>(r0) * c.mlp_hidden * es;
+        float* x1 = tok + static_cast<size_t>(r0) * D;
+        r = add_linear(p, L + ".fc1", a1, D, w.fc1_w[l], w.fc1_b[l], ACT_GELU, nullptr, 0, 0, h1, c.mlp_hidden, !bf, rows, c.mlp_hidden, D);
+        if (r) return r;
+        r = add_linear(p, L + ".fc2", h1, c.mlp_hidden, w.fc2_w[l], w.fc2_b[l], ACT_NONE, x1, D, 0, x1, D, 1, rows, D, c.mlp_hidden);
+        if (r) return r;
+      }
+    }
   }
   // 5. final LayerNorm + to_feature_map, written straight into the first decoder concat buffer (NHWC == [B,N,C])
   {
@@ -804,9 +866,9 @@ static int build_steps(hvit_plan* p) {
     float* th = at<float>(p, "tanh");
     const float* hw = w.head_w;
     const int H = k.H, W = k.W, C = k.Ccat, F = g.F, T = g.T;
-    p->steps.push_back([=](const Ctx& x) { return launch_head(in, dt, hw, B, H, W, C, logits, th, x.stream); });
+    p->steps.push_back([=](const Ctx& x) { return launch_head(in, dt, hw, B, H, W, C, p->debug ? logits : nullptr, th, x.stream); });
     p->tag("decoder." + std::to_string(c.n_dec - 1), "head", 2.0 * B * H * W * C * 9.0, 2.0 * B * H * W * C * 9.0,
-           static_cast<double>(B) * H * W * (C * g.es + 8));
+           static_cast<double>(B) * H * W * (C * g.es + 4));
     p->steps.push_back([=](const Ctx& x) { return x.fused_resize ? 0 : launch_resize(th, B, H, W, x.y, F, T, x.stream); });
     p->tag("resize", "resize", 0, 0, static_cast<double>(B) * (H * W + F * T) * 4);
   }
@@ -815,22 +877,22 @@ static int build_steps(hvit_plan* p) {
     const int n = g.n_samples, T = g.T;
     float* max_val = at<float>(p, "max_val");
     unsigned* mag_max = at<unsigned>(p, "mag_max");
-    float2* spec = at<float2>(p, "spec");
     float* mag = at<float>(p, "mag");
     float* mo = at<float>(p, "model_out");
-    float* frames = at<float>(p, "frames");
     const double ft = static_cast<double>(B) * 257 * T;
     p->pre.push_back([=](const Ctx& x) { return launch_peak(x.wave_in, B, n, max_val, x.normalize, x.stream); });
     p->pre_meta.push_back(StepMeta{"peak_norm", "peak", 0, 0, static_cast<double>(B) * n * 4, 2});
-    p->pre.push_back([=](const Ctx& x) { return launch_stft(x.wave_in, B, n, T, max_val, spec, mag, mag_max, x.stream); });
-    p->pre_meta.push_back(StepMeta{"stft", "stft", 0, 0, static_cast<double>(B) * n * 4 + ft * 12, 2});
+    // the complex spectrogram is never stored: the back end recomputes the noisy phase from the waveform
+    p->pre.push_back([=](const Ctx& x) { return launch_stft(x.wave_in, B, n, T, max_val, nullptr, mag, mag_max, x.stream); });
+    p->pre_meta.push_back(StepMeta{"stft", "stft", 0, 0, static_cast<double>(B) * n * 4 + ft * 4, 2});
     const CatGeo& hl = g.cat[c.n_dec - 1];
     const float* th = at<float>(p, "tanh");
     const int Hs = hl.H, Ws = hl.W;
-    p->post.push_back([=](const Ctx& x) { return launch_istft_frames(mo, th, Hs, Ws, spec, mag_max, frames, B, T, x.stream); });
-    p->post_meta.push_back(StepMeta{"istft.frames", "istft_frames", 0, 0, ft * 12 + static_cast<double>(B) * T * 512 * 4, 1});
-    p->post.push_back([=](const Ctx& x) { return launch_istft_ola(frames, max_val, x.wave_out, B, n, T, x.stream); });
-    p->post_meta.push_back(StepMeta{"istft.ola", "istft_ola", 0, 0, static_cast<double>(B) * T * 512 * 4 + static_cast<double>(B) * n * 4, 1});
+    p->post.push_back([=](const Ctx& x) {
+      return launch_enhance_istft(x.wave_in, max_val, mag_max, th, Hs, Ws, p->debug ? mo : nullptr, x.wave_out, B, n, T, x.stream);
+    });
+    p->post_meta.push_back(StepMeta{"istft", "enhance_istft", 0, 0,
+                                    2.0 * B * n * 4 + static_cast<double>(B) * Hs * Ws * 4, 1});
   }
   while (p->meta.size() < p->steps.size()) p->meta.push_back(StepMeta{"op", "op", 0, 0, 0, 1});
   p->launches_forward = 0;
@@ -869,7 +931,7 @@ size_t hvit_workspace_bytes(const hvit_model_cfg* cfg, int B, int F, int T, int 
 }
 
 int hvit_plan_create(const hvit_model_cfg* cfg, const hvit_weights* weights, int B, int F, int T, int n_samples,
-                     void* workspace_dev, size_t workspace_bytes, hvit_plan** plan_out) {
+                     void* workspace_dev, size_t workspace_bytes, void* stream, hvit_plan** plan_out) {
   if (cfg == nullptr || weights == nullptr || workspace_dev == nullptr || plan_out == nullptr) {
     set_error("hvit_plan_create: null argument");
     return HVIT_E_ARG;
@@ -880,19 +942,21 @@ int hvit_plan_create(const hvit_model_cfg* cfg, const hvit_weights* weights, int
     set_error("this library only runs on sm_100 (B200); there is no fallback path");
     return HVIT_E_ARCH;
   }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   hvit_plan* p = new hvit_plan();
   p->cfg = *cfg;
   p->w = *weights;
   p->ws = reinterpret_cast<uint8_t*>(workspace_dev);
+  p->setup_stream = st;
   int r = build_geometry(*cfg, B, F, T, n_samples, weights->pos_len, p->g);
   if (r == HVIT_OK && (p->g.total > workspace_bytes || (reinterpret_cast<uintptr_t>(workspace_dev) & 1023) != 0)) {
     set_error("workspace too small or not 1024-byte aligned: need %zu bytes, got %zu", p->g.total, workspace_bytes);
     r = HVIT_E_ALLOC;
   }
-  if (r == HVIT_OK && n_samples > 0) r = ensure_fft_tables(nullptr);
+  if (r == HVIT_OK && n_samples > 0) r = ensure_fft_tables(st);
   if (r == HVIT_OK) r = build_steps(p);
   if (r != HVIT_OK) {
-    delete p;
+    hvit_plan_destroy(p);
     return r;
   }
   *plan_out = p;
@@ -900,12 +964,30 @@ int hvit_plan_create(const hvit_model_cfg* cfg, const hvit_weights* weights, int
 }
 
 void hvit_plan_destroy(hvit_plan* plan) {
-  if (plan != nullptr && plan->l2_pin_bytes > 0 && plan->l2_pin_ratio > 0.f) {
-    // give the residual stream's persisting L2 lines back (the carve-out limit itself stays: other plans may use it)
-    cudaCtxResetPersistingL2Cache();
-    cudaGetLastError();
+  if (plan != nullptr && plan->device >= 0) {
+    // give the residual stream's persisting lines back only when no other live plan on that device pins anything
+    // (cudaCtxResetPersistingL2Cache drops every persisting line of the context), and restore the carve-out limit
+    DeviceState& d = g_dev[plan->device];
+    if (--d.pinned_plans <= 0) {
+      d.pinned_plans = 0;
+      int cur = 0;
+      if (cudaGetDevice(&cur) == cudaSuccess) {
+        if (cur != plan->device) cudaSetDevice(plan->device);
+        cudaCtxResetPersistingL2Cache();
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, d.carve_before);
+        d.carve = 0;
+        if (cur != plan->device) cudaSetDevice(cur);
+      }
+      cudaGetLastError();
+    }
   }
   delete plan;
+}
+
+int hvit_plan_set_debug(hvit_plan* plan, int on) {
+  if (plan == nullptr) return HVIT_E_ARG;
+  plan->debug = on ? 1 : 0;
+  return HVIT_OK;
 }
 
 static Ctx enhance_ctx(hvit_plan* plan, const float* wave_in, float* wave_out, int normalize, void* stream) {
@@ -1079,7 +1161,6 @@ int hvit_gemm_16(const void* a, int lda, const void* w, const float* scale, cons
                  void* stream) {
   int r = require_sm100();
   if (r) return r;
-  g_tmap_f16 = f16 ? 1 : 0;
   IgemmParams q = ig_zero();
   q.f16 = f16 ? 1 : 0;
   if (const char* e = getenv("HVIT_DBG")) q.dbg = atoi(e);
@@ -1089,13 +1170,13 @@ int hvit_gemm_16(const void* a, int lda, const void* w, const float* scale, cons
   q.out = out; q.ldc = ldc; q.out_f32 = out_f32;
   IgemmMaps mp;
   const int bn = pick_block_n(N);
-  r = tmap_matrix(&mp.a, a, M, K, lda, 128);
+  r = tmap_matrix(&mp.a, a, q.f16, M, K, lda, 128);
   if (r) return r;
-  r = tmap_matrix(&mp.b, w, N, K, K, b_box_rows(bn));
+  r = tmap_matrix(&mp.b, w, q.f16, N, K, K, bn / 2);
   if (r) return r;
   r = make_out_maps(q, &mp);
   if (r) return r;
-  return launch_igemm_any(q, mp, bn, num_sms(), reinterpret_cast<cudaStream_t>(stream));
+  return launch_igemm_tc2(q, mp, bn, num_sms(), reinterpret_cast<cudaStream_t>(stream));
 }
 
 int hvit_gemm_f32(const float* a, int lda, const float* w, const float* scale, const float* shift, int act,
@@ -1150,12 +1231,11 @@ int hvit_stem_16(const float* x, const void* mag_max, const float* w, const floa
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const unsigned* mm = reinterpret_cast<const unsigned*>(mag_max);
   if (use_tc && C == 64 && pool == 2 && scratch != nullptr) {
-    g_tmap_f16 = f16 ? 1 : 0;
     r = launch_stem_pack(w, scale, scratch, f16 ? 1 : 0, s);
     if (r) return r;
     const int Ho = H / 2, Wo = W / 2;
     CUtensorMap tmo;
-    r = tmap_out4(&tmo, out, 0, 64, Wo, Ho, B, 128, static_cast<uint64_t>(Wo) * 128, static_cast<uint64_t>(Ho) * Wo * 128, 64, 1);
+    r = tmap_out4(&tmo, out, tm16(f16), 64, Wo, Ho, B, 128, static_cast<uint64_t>(Wo) * 128, static_cast<uint64_t>(Ho) * Wo * 128, 64, 1);
     if (r) return r;
     return launch_stem_tc(x, mm, scratch, shift, tmo, f16 ? 1 : 0, B, H, W, num_sms(), s);
   }
@@ -1172,11 +1252,10 @@ int hvit_head_16(const void* x, const float* w, float* logits, float* out_tanh, 
 int hvit_attention_16(const void* qkv, void* out, int B, int N, int heads, int f16, void* stream) {
   int r = require_sm100();
   if (r) return r;
-  g_tmap_f16 = f16 ? 1 : 0;
   CUtensorMap tq, to;
-  r = tmap_qkv(&tq, qkv, B, N, heads * 64);
+  r = tmap_qkv(&tq, qkv, f16, B, N, heads * 64);
   if (r) return r;
-  r = tmap_attn_out(&to, out, B, N, heads * 64);
+  r = tmap_attn_out(&to, out, f16, B, N, heads * 64);
   if (r) return r;
   if (getenv("HVIT_PROF") != nullptr) {  // diagnostics: per-phase cycle counters of the softmax groups
     const int nc = num_sms();
@@ -1239,6 +1318,50 @@ int hvit_istft(const float* mag_norm, const void* spec, const void* mag_max, con
                           reinterpret_cast<const unsigned*>(mag_max), frames, B, 1 + n / 128, st);
   if (r) return r;
   return launch_istft_ola(frames, reinterpret_cast<const float*>(max_val), wave_out, B, n, 1 + n / 128, st);
+}
+
+int hvit_patch_embed_16(const void* x, int B, int H, int W, int C, const void* w, const float* bias, const float* pos,
+                        int patch, int D, float* tokens, int f16, void* stream) {
+  int r = require_sm100();
+  if (r) return r;
+  if (x == nullptr || w == nullptr || tokens == nullptr || patch < 1 || patch > 16 || H % patch != 0 || H / patch < 1 ||
+      W / patch < 1 || C % 64 != 0 || D % 64 != 0) {
+    set_error("hvit_patch_embed_16: bad argument (needs H %% p == 0, C and D multiples of 64)");
+    return HVIT_E_ARG;
+  }
+  hvit_plan tmp;
+  tmp.cfg.precision = f16 ? HVIT_PREC_FP16 : HVIT_PREC_BF16;
+  r = add_patch_embed(&tmp, x, B, H, H, W, C, w, bias, pos, patch, D, tokens);
+  if (r) return r;
+  Ctx c;
+  memset(&c, 0, sizeof(c));
+  c.stream = reinterpret_cast<cudaStream_t>(stream);
+  return tmp.steps[0](c);
+}
+
+int hvit_skip_concat_16(const void* src, int B, int Hs, int Ws, int Cs, const void* w, const float* bias, int Cdec,
+                        void* cat, int Hd, int Wd, int Ccat, int c_off, void* scratch, int f16, void* stream) {
+  int r = require_sm100();
+  if (r) return r;
+  if (src == nullptr || w == nullptr || cat == nullptr || scratch == nullptr || Cs % 64 != 0 || Cdec % 64 != 0 ||
+      c_off % 64 != 0 || c_off + Cdec > Ccat || Ccat % 8 != 0) {
+    set_error("hvit_skip_concat_16: bad argument (channel counts / offset must be multiples of 64 and fit the concat buffer)");
+    return HVIT_E_ARG;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // bilinear sample first (align_corners=False), then the 1x1 projection on the low-resolution grid: exact, because the
+  // interpolation weights sum to 1 and the projection is affine per pixel
+  r = launch_skip_sample(src, f16 ? DT_F16 : DT_BF16, B, Hs, Hs, Ws, Cs, Hd, Wd, scratch, st);
+  if (r) return r;
+  hvit_plan tmp;
+  tmp.cfg.precision = f16 ? HVIT_PREC_FP16 : HVIT_PREC_BF16;
+  r = add_linear(&tmp, "skip", scratch, Cs, w, bias, ACT_NONE, nullptr, 0, 0,
+                 reinterpret_cast<uint8_t*>(cat) + static_cast<size_t>(c_off) * 2, Ccat, 0, B * Hd * Wd, Cdec, Cs);
+  if (r) return r;
+  Ctx c;
+  memset(&c, 0, sizeof(c));
+  c.stream = st;
+  return tmp.steps[0](c);
 }
 
 }  // extern "C"

@@ -446,21 +446,17 @@ int launch_attn_tc(const CUtensorMap& tmap_qkv, const CUtensorMap& tmap_out, int
     set_error("attention: head_dim must be 64 (D=%d heads=%d)", D, heads);
     return -1;
   }
-  static bool configured = false;
-  static int sms = 148;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     if (e != cudaSuccess) {
+      once.retry();
       set_error("attn_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return -4;
     }
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-    configured = true;
   }
+  const int sms = num_sms();
   const long long items = static_cast<long long>((N + 255) / 256) * heads * B;
   if (items <= 0 || items > 0x7FFFFFFF) {
     set_error("attention: bad problem size B=%d N=%d heads=%d", B, N, heads);

@@ -1,6 +1,5 @@
 // CTA-pair (cta_group::2) tcgen05 implicit GEMM - the production kernel for every dense contraction of the
-// HybridViT forward (same problem description and A-operand modes as gemm_tc.cu, which is kept as the single-CTA
-// comparison kernel).
+// HybridViT forward (problem description and A-operand modes: IgemmParams in kernels.h).
 //
 // Why a CTA pair: with cta_group::1 a 128x256x16 MMA reads 12 KB of operands from shared memory in 128 cycles
 // (96 B/clk) while TMA refills the ring at 94 B/clk - together above the 128 B/clk/SM shared-memory port.  Here one
@@ -1009,15 +1008,15 @@ template <int BLOCK_N, int EPI, bool UP2>
 int launch_halo_impl(const IgemmParams& p, const IgemmMaps& maps, int num_ctiles, int n_tiles_n, int pairs_per_group,
                      int num_sms, cudaStream_t stream) {
   using C = CfgH<BLOCK_N, UP2>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaError_t e = cudaFuncSetAttribute(igemm_halo_kernel<BLOCK_N, EPI, UP2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) {
+      once.retry();
       set_error("igemm_halo: cudaFuncSetAttribute(%d B smem) failed: %s", C::SMEM_BYTES, cudaGetErrorString(e));
       return -4;
     }
-    configured = true;
   }
   const int max_clusters = num_sms / 2;
   const int clusters = num_ctiles < max_clusters ? num_ctiles : max_clusters;
@@ -1053,15 +1052,15 @@ template <int BLOCK_N, int EPI>
 int launch_impl2(const IgemmParams& p, const IgemmMaps& maps, int num_ctiles, int n_tiles_n, int pairs_per_group,
                  int num_sms, cudaStream_t stream) {
   using C = Cfg2<BLOCK_N, EPI>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaError_t e = cudaFuncSetAttribute(igemm_tc2_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) {
+      once.retry();
       set_error("igemm_tc2: cudaFuncSetAttribute(%d B smem) failed: %s", C::SMEM_BYTES, cudaGetErrorString(e));
       return -4;
     }
-    configured = true;
   }
   const int max_clusters = num_sms / 2;
   const int clusters = num_ctiles < max_clusters ? num_ctiles : max_clusters;

@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(FR * 32, 4) stft_kernel(const float* __restric
         const float2 z1 = xw[fpad(f)], z2 = xw[fpad((NFFT - f) & (NFFT - 1))];
         const float2 z = second ? make_float2(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x))
                                 : make_float2(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
-        *sp = z;
+        if (spec != nullptr) *sp = z;   // (the enhance path never stores the complex spectrogram)
         const float m = sqrtf(z.x * z.x + z.y * z.y);
         *mp = m;
         lmax = fmaxf(lmax, m);
@@ -352,6 +352,141 @@ __global__ void istft_ola_kernel(const float* __restrict__ frames, const unsigne
   }
   if (wss > 1.17549435e-38f) acc /= wss;
   wave_out[static_cast<long long>(b) * n + i] = acc * guard_scalar(max_bits[b]);
+}
+
+// ------------------------------------------------------------------ fused back end of AudioEnhancer.enhance
+// enhancer.py:115-133: E = (model_out * mag_max) * exp(1j * angle(S)), librosa.istft (irfft-512, periodic Hann,
+// overlap-add, trim n_fft/2, divide by the window sum-square envelope), * max_val - in ONE kernel that touches HBM only
+// for its algorithmic bytes: the noisy waveform in, the decoder's low-resolution tanh map in, the waveform out.
+//   * the noisy phase is RECOMPUTED here (forward FFT of the same windowed frames as stft_kernel - identical code,
+//     identical bits), so the complex spectrogram [B,257,T] is never written or read (66 MB each way at 64 x 4 s);
+//   * HybridViT's final bilinear resize (hybrid_vit.py:458-465) is sampled per bin from the [B,Hs,Ws] map;
+//   * overlap-add runs out of shared memory: a block transforms FRAMES = 16 consecutive frames and owns the
+//     FRAMES - 3 = 13 hops of output that only those frames touch (every sample is covered by <= 4 frames), so
+//     neighbouring blocks recompute 3 frames instead of exchanging partial sums - no [B,T,512] frame buffer
+//     (66 MB written + read before), no atomics.
+// Per warp: load + window two frames (real / imaginary part of one complex buffer) -> forward FFT -> per bin: untangle
+// the two spectra, E = mo * mag_max * S / |S| for both, re-tangle as Z = Ea + i Eb (in place: bin f and N - f belong to
+// the same lane) -> inverse FFT; then the block overlap-adds its hop range.
+constexpr int OLA_HOPS = FRAMES - 3;
+constexpr int EI_SMEM = FR * XS * sizeof(float2) + NBIN * (sizeof(int2) + sizeof(float));
+
+__global__ void __launch_bounds__(FR * 32, 4) enhance_istft_kernel(const float* __restrict__ wave, int n, int T,
+                                                                const unsigned* __restrict__ max_bits,
+                                                                const unsigned* __restrict__ mag_max_bits,
+                                                                const float* __restrict__ lowres, int Hs, int Ws,
+                                                                float* __restrict__ model_out,
+                                                                float* __restrict__ wave_out) {
+  griddep_launch_dependents();
+  griddep_wait();
+  extern __shared__ float2 sm[];
+  float2* xs = sm;                                            // [FR][XS]
+  int2* lyi = reinterpret_cast<int2*>(xs + FR * XS);          // [NBIN] row offsets (i0 * Ws, i1 * Ws) of the resize
+  float* lyw = reinterpret_cast<float*>(lyi + NBIN);          // [NBIN] weight of row i1
+  const int b = blockIdx.y, t0 = blockIdx.x * OLA_HOPS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float mv = guard_scalar(max_bits[b]);
+  const float inv_mv = 1.0f / mv;
+  const float mm = guard_scalar(mag_max_bits[b]);
+  for (int f = threadIdx.x; f < NBIN; f += FR * 32) {
+    const Lerp ly = make_lerp(f, Hs, NBIN);
+    lyi[f] = make_int2(ly.i0 * Ws, ly.i1 * Ws);
+    lyw[f] = ly.l1;
+  }
+  const int ta = t0 + 2 * warp;
+  const bool live = ta < T, has_b = ta + 1 < T;
+  float2* x = xs + warp * XS;
+  if (live) {
+    // ---- frames ta, ta + 1 of the peak-normalised noisy clip (same arithmetic as stft_kernel)
+    const float* w = wave + static_cast<long long>(b) * n;
+    const int s0 = ta * HOP - NFFT / 2;
+    if (s0 >= 0 && s0 + HOP + NFFT <= n && has_b) {
+      const float* wa = w + s0;
+#pragma unroll 4
+      for (int i = lane; i < NFFT; i += 32) {
+        const float h = hann512(i);
+        x[fpad(i)] = make_float2((wa[i] * inv_mv) * h, (wa[i + HOP] * inv_mv) * h);
+      }
+    } else {
+      for (int i = lane; i < NFFT; i += 32) {
+        const int sa = s0 + i, sb = sa + HOP;
+        const float h = hann512(i);
+        float va = 0.f, vb = 0.f;
+        if (sa >= 0 && sa < n) va = (w[sa] * inv_mv) * h;
+        if (has_b && sb >= 0 && sb < n) vb = (w[sb] * inv_mv) * h;
+        x[fpad(i)] = make_float2(va, vb);
+      }
+    }
+    __syncwarp();
+    fft512_warp<false>(x, lane);
+  }
+  __syncthreads();  // resize table complete
+  if (live) {
+    const Lerp lxa = make_lerp(ta, Ws, T), lxb = make_lerp(has_b ? ta + 1 : ta, Ws, T);
+    const float* src = lowres + static_cast<long long>(b) * Hs * Ws;
+    // E = (model_out * mag_max) * S / |S| of one bin (z = S, mo = model output)
+    auto bin = [&](float2 z, float mo, int f) -> float2 {
+      const float zz = z.x * z.x + z.y * z.y;
+      const float e = mo * mm;
+      float2 E;
+      if (zz >= 1.17549435e-38f) {  // e * S / |S| with one MUFU.RSQ (2^-22 relative) instead of sqrt + divide
+        const float ea = e * rsqrtf(zz);
+        E = make_float2(ea * z.x, ea * z.y);
+      } else {                       // |S|^2 underflows or S == 0 (angle 0): exact path
+        const float a = sqrtf(zz);
+        const float ea = a > 0.f ? e / a : 0.f;
+        E = a > 0.f ? make_float2(ea * z.x, ea * z.y) : make_float2(e, 0.f);
+      }
+      if (f == 0 || f == NFFT / 2) E.y = 0.f;  // c2r transforms ignore the imaginary part of DC / Nyquist
+      return E;
+    };
+    for (int f = lane; f < NBIN; f += 32) {
+      const int fm = (NFFT - f) & (NFFT - 1);
+      const float2 z1 = x[fpad(f)], z2 = x[fpad(fm)];
+      const float2 za = make_float2(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
+      const float2 zb = make_float2(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x));
+      const int2 ro = lyi[f];
+      const float wy1 = lyw[f], wy0 = 1.0f - wy1;
+      const float* r0 = src + ro.x;
+      const float* r1 = src + ro.y;
+      const float moa = wy0 * (lxa.l0 * __ldg(r0 + lxa.i0) + lxa.l1 * __ldg(r0 + lxa.i1)) +
+                        wy1 * (lxa.l0 * __ldg(r1 + lxa.i0) + lxa.l1 * __ldg(r1 + lxa.i1));
+      float mob = 0.f;
+      if (has_b)
+        mob = wy0 * (lxb.l0 * __ldg(r0 + lxb.i0) + lxb.l1 * __ldg(r0 + lxb.i1)) +
+              wy1 * (lxb.l0 * __ldg(r1 + lxb.i0) + lxb.l1 * __ldg(r1 + lxb.i1));
+      if (model_out != nullptr) {  // debug / test builds of the plan only: the resized model output [B,257,T]
+        float* mp = model_out + (static_cast<long long>(b) * NBIN + f) * T + ta;
+        mp[0] = moa;
+        if (has_b) mp[1] = mob;
+      }
+      const float2 Ea = bin(za, moa, f);
+      const float2 Eb = has_b ? bin(zb, mob, f) : make_float2(0.f, 0.f);
+      x[fpad(f)] = make_float2(Ea.x - Eb.y, Ea.y + Eb.x);
+      if (f > 0 && f < NFFT / 2) x[fpad(fm)] = make_float2(Ea.x + Eb.y, Eb.x - Ea.y);
+    }
+    __syncwarp();
+    fft512_warp<true>(x, lane);
+  }
+  __syncthreads();
+  // ---- overlap-add of this block's hop range straight out of shared memory, envelope division, de-normalisation
+  const int j_lo = blockIdx.x == 0 ? NFFT / 2 : HOP * (t0 + 3);
+  const int j_hi = min(HOP * (t0 + FRAMES), NFFT / 2 + n);
+  float* out = wave_out + static_cast<long long>(b) * n - NFFT / 2;
+  for (int j = j_lo + threadIdx.x; j < j_hi; j += FR * 32) {
+    const int h = j >> 7;
+    const int thi = min(h, T - 1), tlo = max(h - 3, 0);
+    float acc = 0.f, wss = 0.f;
+    for (int t = tlo; t <= thi; ++t) {
+      const int k = j - t * HOP, tl = t - t0;
+      const float2 v = xs[(tl >> 1) * XS + fpad(k)];
+      const float w = hann512(k);
+      acc += ((tl & 1) ? v.y : v.x) * (w * (1.0f / NFFT));
+      wss += w * w;
+    }
+    if (wss > 1.17549435e-38f) acc /= wss;
+    out[j] = acc * mv;
+  }
 }
 
 // ------------------------------------------------------------------ stem: Conv3x3(1->C, no bias)+BN+ReLU[+MaxPool2]
@@ -870,13 +1005,24 @@ int launch_peak(const float* wave, int B, int n, float* max_val, int normalize, 
 
 // one-time table fill; called from plan creation / the stand-alone entry points (never inside a graph capture)
 int ensure_fft_tables(cudaStream_t s) {
-  static bool done = false;
-  if (!done) {
+  static PerDeviceOnce once;  // the __device__ tables exist once per device
+  if (once.first()) {
     fft_tables_kernel<<<2, 256, 0, s>>>();
     const int r = check_launch("fft_tables");
-    if (r) return r;
-    if (cudaStreamSynchronize(s) != cudaSuccess) return check_launch("fft_tables(sync)");
-    done = true;
+    if (r) {
+      once.retry();
+      return r;
+    }
+    // later launches on OTHER streams read the tables: order them after the fill (unless `s` is being captured, in which
+    // case the fill is part of the captured work and the caller's stream order covers it)
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone) {
+      if (cudaStreamSynchronize(s) != cudaSuccess) {
+        once.retry();
+        return check_launch("fft_tables(sync)");
+      }
+    }
+    cudaGetLastError();
   }
   return 0;
 }
@@ -891,6 +1037,17 @@ int launch_stft(const float* wave, int B, int n, int T, const float* max_val, fl
 }
 
 static void fft_smem_config() {}
+
+int launch_enhance_istft(const float* wave_in, const float* max_val, const unsigned* mag_max_bits, const float* lowres,
+                         int Hs, int Ws, float* model_out, float* wave_out, int B, int n, int T, cudaStream_t s) {
+  if (n <= 0) return 0;
+  const int hops = (NFFT / 2 - 1 + n) >> 7;                        // index of the last hop that holds output
+  const int blocks = hops >= 3 ? (hops - 3) / OLA_HOPS + 1 : 1;
+  dim3 grid(blocks, B);
+  launch_pdl(enhance_istft_kernel, dim3(grid), dim3(FR * 32), EI_SMEM, s, wave_in, n, T,
+             reinterpret_cast<const unsigned*>(max_val), mag_max_bits, lowres, Hs, Ws, model_out, wave_out);
+  return check_launch("enhance_istft");
+}
 
 int launch_istft_frames(float* model_out, const float* lowres, int Hs, int Ws, const float2* spec,
                         const unsigned* mag_max_bits, float* frames, int B, int T, cudaStream_t s) {
@@ -993,21 +1150,14 @@ int launch_head(const void* x, int dt, const float* w, int B, int H, int W, int 
   const long long npix = static_cast<long long>(B) * H * W;
   const size_t rows_smem = static_cast<size_t>(4) * W * C * 2;
   if (C == 64 && dt != DT_F32 && rows_smem <= 72 * 1024 && B <= 65535 && getenv("HVIT_HEAD_SIMPLE") == nullptr) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.first()) {
       cudaFuncSetAttribute(head_rows_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
       cudaFuncSetAttribute(head_rows_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
-      configured = true;
     }
     // strip height: the row ring needs 63 KB per block (3 blocks per SM), so the grid is only a few blocks per slot;
     // pick the strip (8, 4 or 2 rows) whose last wave wastes the least time (shorter strips re-read more halo rows)
-    static int sms = 0;
-    if (sms == 0) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      if (sms <= 0) sms = 148;
-    }
+    const int sms = num_sms();
     const int per_sm = rows_smem > 0 ? static_cast<int>((200 * 1024) / rows_smem) : 1;
     const int slots = sms * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
     int strip = HEAD_STRIP;

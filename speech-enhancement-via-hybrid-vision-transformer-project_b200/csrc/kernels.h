@@ -84,11 +84,8 @@ struct IgemmParams {
   FastDiv fd_ntn, fd_ppg, fd_tw, fd_th;  // set by launch_igemm_tc2: n tiles, pairs per group, tiles_w, tiles_h
 };
 
-// tcgen05 path. A / Wt are described by TMA tensor maps built on the host (see tmap.cpp).
-int launch_igemm_tc(const IgemmParams& p, const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, int block_n,
-                    int num_sms, cudaStream_t stream);
-
-// CTA-pair (cta_group::2, UMMA M = 256) variant; tmap_b is built with a box of block_n / 2 rows.  The epilogue
+// tcgen05 path. A / Wt are described by TMA tensor maps built on the host (api.cu).
+// CTA-pair (cta_group::2, UMMA M = 256) kernel; tmap_b is built with a box of block_n / 2 rows.  The epilogue
 // writes through shared memory with TMA stores: `out` holds one 4-D map per upsample parity (index 0 otherwise) with a
 // 128-byte-wide box (64 16-bit or 32 fp32 columns); `res` is the fp32 residual map (same box) when p.residual is set.
 struct IgemmMaps {
@@ -116,13 +113,18 @@ int launch_attn_probs_16(const void* qkv16, int f16, float* probs, int B, int N,
 // ---------------------------------------------------------------------------------------------
 int ensure_fft_tables(cudaStream_t s);
 int launch_peak(const float* wave, int B, int n, float* max_val /*[B]*/, int normalize, cudaStream_t s);
-int launch_stft(const float* wave, int B, int n, int T, const float* max_val, float2* spec /*[B,257,T]*/,
+int launch_stft(const float* wave, int B, int n, int T, const float* max_val, float2* spec /*[B,257,T] or null*/,
                 float* mag /*[B,257,T]*/, unsigned* mag_max_bits /*[B]*/, cudaStream_t s);
 // model_out [B,257,T] is read when lowres == nullptr, otherwise it is WRITTEN with the bilinear resize of
 // lowres [B,Hs,Ws] (fused final interpolate of HybridViT.forward).
 int launch_istft_frames(float* model_out, const float* lowres, int Hs, int Ws, const float2* spec,
                         const unsigned* mag_max_bits, float* frames /*[B,T,512]*/, int B, int T, cudaStream_t s);
 int launch_istft_ola(const float* frames, const float* max_val, float* wave_out, int B, int n, int T, cudaStream_t s);
+// Fused back end of the enhance path: phase recomputed from the noisy waveform, final bilinear resize of the decoder's
+// [B,Hs,Ws] tanh map, inverse FFT, overlap-add in shared memory, envelope, de-normalisation.  model_out (nullable)
+// receives the resized model output [B,257,T] for tests.
+int launch_enhance_istft(const float* wave_in, const float* max_val, const unsigned* mag_max_bits, const float* lowres,
+                         int Hs, int Ws, float* model_out, float* wave_out, int B, int n, int T, cudaStream_t s);
 int launch_stem(const float* x /*[B,H,W]*/, const unsigned* mag_max_bits /*nullable*/, const float* w /*[9][C]*/,
                 const float* scale, const float* shift, void* out, int dt, int B, int H, int W, int C, int pool,
                 cudaStream_t s);
@@ -180,8 +182,33 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   }
   cfg.attrs = at;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+  if (e != cudaSuccess && w.bytes > 0) {
+    // a driver that rejects the access-policy window (e.g. a smaller limit than the one queried) must not take the
+    // whole step down: retry this launch once without it
+    cudaGetLastError();
+    cfg.numAttrs = na - 1;
+    e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+  }
+  return e;
 }
+
+// per-device state (api.cu): a process may drive several GPUs, so one-time initialisation (function attributes, FFT
+// tables, SM count, L2 carve-out) is keyed by the current CUDA device
+constexpr int kMaxDevices = 64;
+int current_device();
+int num_sms();
+// true exactly once per (flag array, current device)
+struct PerDeviceOnce {
+  bool done[kMaxDevices] = {};
+  bool first() {
+    const int d = current_device();
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+  void retry() { done[current_device()] = false; }
+};
 
 // error plumbing (api.cu)
 void set_error(const char* fmt, ...);

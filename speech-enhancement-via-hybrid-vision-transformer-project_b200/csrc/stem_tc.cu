@@ -383,16 +383,16 @@ int launch_stem_tc(const float* x, const unsigned* mag_max_bits, const void* apa
     cudaMalloc(&prof, sizeof(long long) * 16 * num_sms);
     cudaMemset(prof, 0, sizeof(long long) * 16 * num_sms);
   }
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(stem_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM);
     if (e != cudaSuccess) {
+      once.retry();
       set_error("stem_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return -4;
     }
-    configured = true;
   }
   const int Ho = H / 2, Wo = W / 2;
   const int tiles_w = (Wo + 63) / 64, row_pairs = (Ho + 1) / 2;

@@ -131,10 +131,19 @@ class AudioEnhancer:
         of ``hvit_enhance`` are replayed as one CUDA graph (the plan only enqueues kernels - no allocation, no sync -
         and is capturable, PDL edges included): single-clip latency is launch-bound otherwise.
         HVIT_NO_GRAPH=1 keeps the eager path."""
-        key = (k, bool(normalize))
+        B, n = pipe["d_in"][k].shape
+        # the graph bakes in raw pointers into the plan's workspace and packed weights: it is keyed by everything that
+        # selects a plan (precision included), holds a strong reference to the plan it captured, and is only replayed
+        # while that very plan is still the model's current one for the shape (weights unchanged, not evicted + rebuilt)
+        plan = self.model.plan_for(B, N_FFT // 2 + 1, 1 + n // HOP, n_samples=n)
+        key = (k, bool(normalize), self.model.precision)
         graphs = pipe.setdefault("graphs", {})
         calls = pipe.setdefault("calls", {})
         g = graphs.get(key)
+        if g is not None and g[1] is not plan:
+            del graphs[key]
+            calls.pop(key, None)
+            g = None
         if g is None:
             calls[key] = calls.get(key, 0) + 1
             # graphs only pay off while the step is launch-bound (measured: batch 1 x 4 s 0.75 -> 0.69 ms p50, but a
@@ -144,7 +153,6 @@ class AudioEnhancer:
                     torch.cuda.is_current_stream_capturing():
                 self.enhance_device(pipe["d_in"][k], normalize=normalize, out=pipe["d_out"][k])
                 return
-            ver = self.model._weights_version() if hasattr(self.model, "_weights_version") else None
             cur = torch.cuda.current_stream()
             cap = torch.cuda.Stream(device=self._dev)
             cap.wait_stream(cur)
@@ -152,14 +160,8 @@ class AudioEnhancer:
             with torch.cuda.graph(graph, stream=cap):
                 self.enhance_device(pipe["d_in"][k], normalize=normalize, out=pipe["d_out"][k])
             cur.wait_stream(cap)
-            g = graphs[key] = (graph, ver)
-        graph, ver = g
-        if ver is not None and ver != self.model._weights_version():   # parameters changed: plans were rebuilt
-            graphs.clear()
-            calls.clear()
-            self.enhance_device(pipe["d_in"][k], normalize=normalize, out=pipe["d_out"][k])
-            return
-        graph.replay()
+            g = graphs[key] = (graph, plan)
+        g[0].replay()
 
     def join(self, block: bool = False) -> None:
         """Order the current stream after every outstanding D2H copy of :meth:`enhance_pinned`

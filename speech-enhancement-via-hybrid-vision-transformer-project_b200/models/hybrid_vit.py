@@ -27,7 +27,7 @@ class _Plan:
     """One hvit_plan (+ its workspace) for a fixed (B, F, T, n_samples, precision)."""
 
     def __init__(self, lib, cfg: _lib.ModelCfg, weights: PackedWeights, B: int, F: int, T: int, n_samples: int,
-                 device: torch.device):
+                 device: torch.device, debug: bool = False):
         self.lib = lib
         nbytes = lib.hvit_workspace_bytes(C.byref(cfg), B, F, T, n_samples)
         if nbytes == 0:
@@ -37,9 +37,14 @@ class _Plan:
         self.workspace = raw[shift:shift + nbytes]
         self.weights = weights  # keeps the packed tensors alive as long as the plan
         handle = C.c_void_p()
+        # setup kernels go on torch's current stream: ordered after the weight packing, and before this stream's forwards
         _lib.check(lib.hvit_plan_create(C.byref(cfg), C.byref(weights.c), B, F, T, n_samples,
-                                        self.workspace.data_ptr(), nbytes, C.byref(handle)), "hvit_plan_create")
+                                        self.workspace.data_ptr(), nbytes, _lib.current_stream_ptr(), C.byref(handle)),
+                   "hvit_plan_create")
         self.handle = handle
+        self.debug = bool(debug)
+        if self.debug:
+            _lib.check(lib.hvit_plan_set_debug(handle, 1), "hvit_plan_set_debug")
         self.B, self.F, self.T, self.n_samples = B, F, T, n_samples
         self.act_dtype = torch.float16 if cfg.precision == _lib.PREC_FP16 else torch.bfloat16
         hp, wp = C.c_int(), C.c_int()
@@ -99,9 +104,13 @@ class HybridViT(nn.Module):
     """CNN encoder -> patch embedding -> ViT -> CNN decoder with U-Net skips (reference hybrid_vit.py:21-170).
 
     Extra keyword (not in the reference): ``precision`` =
-      ``"fp16"`` (default) tcgen05 tensor cores, fp16 operands/activations, fp32 accumulate - meets the 1e-2 bar;
-      ``"bf16"``           same kernels with bf16 operands (wider range, ~1-2e-2 max-rel: the bf16 noise floor);
-      ``"fp32"``           CUDA-core accuracy mode (<= 1e-4).  Supported architecture subset, checked at plan creation:
+      ``"fp16"`` (default) tcgen05 tensor cores, fp16 operands/activations, fp32 accumulate - the 16-bit parity mode
+                           (meets the north star's 1e-2 / 0.05 dB bar);
+      ``"fp32"``           CUDA-core accuracy mode (<= 1e-4);
+      ``"bf16"``           same kernels as fp16 with bf16 operands, kept for dynamic range only - NOT a parity mode
+                           (0.6-2.2e-2 max-rel, the bf16 rounding floor).
+    An explicit ``precision=`` wins over the ``HVIT_PRECISION`` environment default.
+    Supported architecture subset, checked at plan creation:
     1 input / 1 output channel, 3x3 convolutions, pool sizes and upsample factors in {1, 2},
     head_dim 64, channel counts multiples of 64 (bf16) / 16 (fp32), no CLS token.
     """
@@ -113,7 +122,7 @@ class HybridViT(nn.Module):
                  decoder_channels: List[int] = [256, 128, 64, 1], decoder_kernel_sizes: List[int] = [3, 3, 3, 3],
                  decoder_upsample_factors: List[int] = [1, 2, 2, 1], dropout: float = 0.1, attn_dropout: float = 0.1,
                  drop_path_rate: float = 0.1, use_skip_connections: bool = True, use_cls_token: bool = False,
-                 precision: str = "fp16"):
+                 precision: Optional[str] = None):
         super().__init__()
         if use_cls_token:
             raise NotImplementedError("use_cls_token=True is not wired to any reference config and is not supported")
@@ -129,7 +138,9 @@ class HybridViT(nn.Module):
                          patch_size=patch_size, decoder_channels=list(decoder_channels),
                          decoder_upsample_factors=list(decoder_upsample_factors),
                          use_skip_connections=use_skip_connections)
-        self.precision = os.environ.get("HVIT_PRECISION", precision)
+        # an explicit precision= wins; HVIT_PRECISION only supplies the default
+        self.precision = precision if precision is not None else os.environ.get("HVIT_PRECISION", "fp16")
+        self.debug_buffers = False   # True: plans also store the test-only intermediates ("model_out", "logits")
 
         # --- same registration order as the reference so the literal init consumes the RNG identically
         self.encoder = nn.ModuleList()
@@ -165,7 +176,8 @@ class HybridViT(nn.Module):
         self.apply(self._init_weights)
 
         self._packed: Dict[int, tuple] = {}
-        self._plans: Dict[tuple, _Plan] = {}
+        self._plans: Dict[tuple, _Plan] = {}   # LRU: key -> plan, most recently used last
+        self.max_plans = 16
 
     # reference hybrid_vit.py:265-284
     @staticmethod
@@ -245,13 +257,13 @@ class HybridViT(nn.Module):
         prec = _PRECISIONS[self.precision]
         with torch.cuda.device(dev):
             packed = self._get_packed(prec)
-            key = (prec, B, F, T, n_samples)
-            plan = self._plans.get(key)
+            key = (prec, B, F, T, n_samples, bool(self.debug_buffers))
+            plan = self._plans.pop(key, None)
             if plan is None:
-                plan = _Plan(lib, self._c_cfg(prec), packed, B, F, T, n_samples, dev)
-                if len(self._plans) >= 16:
+                plan = _Plan(lib, self._c_cfg(prec), packed, B, F, T, n_samples, dev, debug=self.debug_buffers)
+                while len(self._plans) >= self.max_plans:     # least recently used first (dicts keep insertion order)
                     self._plans.pop(next(iter(self._plans)))
-                self._plans[key] = plan
+            self._plans[key] = plan                           # (re-)insert as most recently used
         return plan
 
     # ------------------------------------------------------------------ forward (reference hybrid_vit.py:396-469)
@@ -300,4 +312,4 @@ def create_hybrid_vit(config: Optional[Dict] = None) -> HybridViT:
         decoder_upsample_factors=dec.get("upsample_factors", [1, 2, 2, 1]),
         dropout=enc.get("dropout", 0.1), attn_dropout=tr.get("attention_dropout", 0.1),
         drop_path_rate=tr.get("drop_path_rate", 0.1), use_skip_connections=dec.get("use_skip_connections", True),
-        precision=m.get("precision", "fp16"))
+        precision=m.get("precision"))

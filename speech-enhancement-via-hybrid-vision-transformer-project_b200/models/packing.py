@@ -1,8 +1,11 @@
-"""Derive the packed, device-resident weight set the CUDA plan consumes (include/hvit.h: hvit_weights)
-from a reference-keyed state_dict: BatchNorm folding, NHWC / K-major re-layout, bf16 conversion, and the
-pre-summed 2x2 parity kernels for "nearest x2 upsample + 3x3 conv" decoder blocks.
+"""The packed, device-resident weight set the CUDA plan consumes (include/hvit.h: hvit_weights), derived from a
+reference-keyed state_dict by ``hvit_pack_weights`` (csrc/pack.cu, C ABI, no torch arithmetic): BatchNorm folding,
+K-major conv re-layout, 16-bit conversion and the pre-summed 2x2 parity kernels for "nearest x2 upsample + 3x3 conv"
+decoder blocks.  ``PackedWeights`` only stages the fp32 state_dict on the device, allocates the packed buffer and keeps
+it alive.  Runs once per weight version.
 
-Runs once per weight version on the device with torch tensor ops (host-side plumbing, not the hot path).
+``fold_bn`` / ``conv_khwc`` / ``up2_parity_kernels`` are the same re-expressions written with torch ops; the tests use
+them (in fp64 on the CPU, and against the CUDA packer's output on the GPU) - the product path does not call them.
 """
 from __future__ import annotations
 
@@ -39,69 +42,58 @@ def up2_parity_kernels(w: torch.Tensor) -> torch.Tensor:
 
 
 class PackedWeights:
-    """Owns the packed tensors and the ctypes view handed to hvit_plan_create."""
+    """Owns the packed device buffer and the ctypes view (``.c``) handed to hvit_plan_create."""
 
-    def __init__(self, model, precision: int):
+    def __init__(self, model, precision: int, c_cfg=None):
+        import ctypes as C
+        lib = _lib.load()
         dev = next(model.parameters()).device
-        sd = {k: v.detach() for k, v in model.state_dict().items()}
-        act = {_lib.PREC_BF16: torch.bfloat16, _lib.PREC_FP16: torch.float16, _lib.PREC_FP32: torch.float32}[precision]
-        self.keep: List[torch.Tensor] = []
-        self.c = _lib.Weights()
-        c = self.c
         cfg = model.arch
-
-        def hold(t: torch.Tensor, dtype=torch.float32) -> int:
-            t = t.to(device=dev, dtype=dtype).contiguous()
-            self.keep.append(t)
-            return t.data_ptr()
-
-        # encoder: block 0 is the stem (fp32 CUDA-core kernel), the rest are implicit GEMMs
+        ccfg = c_cfg if c_cfg is not None else model._c_cfg(precision)
+        sd = {k: v.detach().to(device=dev, dtype=torch.float32).contiguous()
+              for k, v in model.state_dict().items() if v.is_floating_point()}
+        ref = _lib.RefWeights()
         for i in range(len(cfg["encoder_channels"])):
-            w = sd[f"encoder.{i}.block.0.weight"]
-            scale, shift = fold_bn(sd, f"encoder.{i}.block.1")
-            if i == 0:
-                c.stem_w = hold(w[:, 0].permute(1, 2, 0))           # [3,3,C0]
-                c.stem_scale, c.stem_shift = hold(scale), hold(shift)
-            elif precision != _lib.PREC_FP32:
-                # 16-bit modes: the BN scale is folded into the conv weights in fp32 (one rounding to 16 bits), the
-                # epilogue only adds the shift (no per-channel scale loads; scale pointer = NULL means 1.0)
-                c.enc_w[i] = hold(conv_khwc(w.float() * scale.to(w.device)[:, None, None, None]), act)
-                c.enc_shift[i] = hold(shift)
-            else:
-                c.enc_w[i] = hold(conv_khwc(w), act)
-                c.enc_scale[i], c.enc_shift[i] = hold(scale), hold(shift)
-        c.patch_w = hold(conv_khwc(sd["patch_embed.projection.weight"]), act)
-        c.patch_b = hold(sd["patch_embed.projection.bias"])
+            ref.enc_conv_w[i] = sd[f"encoder.{i}.block.0.weight"].data_ptr()
+            bn = f"encoder.{i}.block.1"
+            ref.enc_bn_w[i], ref.enc_bn_b[i] = sd[f"{bn}.weight"].data_ptr(), sd[f"{bn}.bias"].data_ptr()
+            ref.enc_bn_mean[i], ref.enc_bn_var[i] = sd[f"{bn}.running_mean"].data_ptr(), sd[f"{bn}.running_var"].data_ptr()
+        ref.patch_w = sd["patch_embed.projection.weight"].data_ptr()
+        ref.patch_b = sd["patch_embed.projection.bias"].data_ptr()
         pos = sd["pos_encoding.pos_embed"]
-        c.pos_embed = hold(pos.reshape(pos.shape[1], pos.shape[2]))
-        c.pos_len = int(pos.shape[1])
+        ref.pos_embed, ref.pos_len = pos.data_ptr(), int(pos.shape[1])
         for l in range(cfg["num_layers"]):
             p = f"transformer.blocks.{l}"
-            c.ln1_g[l], c.ln1_b[l] = hold(sd[f"{p}.norm1.weight"]), hold(sd[f"{p}.norm1.bias"])
-            c.ln2_g[l], c.ln2_b[l] = hold(sd[f"{p}.norm2.weight"]), hold(sd[f"{p}.norm2.bias"])
-            c.qkv_w[l], c.qkv_b[l] = hold(sd[f"{p}.attn.qkv.weight"], act), hold(sd[f"{p}.attn.qkv.bias"])
-            c.proj_w[l], c.proj_b[l] = hold(sd[f"{p}.attn.proj.weight"], act), hold(sd[f"{p}.attn.proj.bias"])
-            c.fc1_w[l], c.fc1_b[l] = hold(sd[f"{p}.mlp.net.0.weight"], act), hold(sd[f"{p}.mlp.net.0.bias"])
-            c.fc2_w[l], c.fc2_b[l] = hold(sd[f"{p}.mlp.net.3.weight"], act), hold(sd[f"{p}.mlp.net.3.bias"])
-        c.lnf_g, c.lnf_b = hold(sd["transformer.norm.weight"]), hold(sd["transformer.norm.bias"])
-        c.tofm_w, c.tofm_b = hold(sd["to_feature_map.weight"], act), hold(sd["to_feature_map.bias"])
+            ref.ln1_w[l], ref.ln1_b[l] = sd[f"{p}.norm1.weight"].data_ptr(), sd[f"{p}.norm1.bias"].data_ptr()
+            ref.ln2_w[l], ref.ln2_b[l] = sd[f"{p}.norm2.weight"].data_ptr(), sd[f"{p}.norm2.bias"].data_ptr()
+            ref.qkv_w[l], ref.qkv_b[l] = sd[f"{p}.attn.qkv.weight"].data_ptr(), sd[f"{p}.attn.qkv.bias"].data_ptr()
+            ref.proj_w[l], ref.proj_b[l] = sd[f"{p}.attn.proj.weight"].data_ptr(), sd[f"{p}.attn.proj.bias"].data_ptr()
+            ref.fc1_w[l], ref.fc1_b[l] = sd[f"{p}.mlp.net.0.weight"].data_ptr(), sd[f"{p}.mlp.net.0.bias"].data_ptr()
+            ref.fc2_w[l], ref.fc2_b[l] = sd[f"{p}.mlp.net.3.weight"].data_ptr(), sd[f"{p}.mlp.net.3.bias"].data_ptr()
+        ref.lnf_w, ref.lnf_b = sd["transformer.norm.weight"].data_ptr(), sd["transformer.norm.bias"].data_ptr()
+        ref.tofm_w, ref.tofm_b = sd["to_feature_map.weight"].data_ptr(), sd["to_feature_map.bias"].data_ptr()
         n_dec = len(cfg["decoder_channels"])
         for i in range(n_dec):
-            up = cfg["decoder_upsample_factors"][i]
-            ci = 1 if up > 1 else 0
-            w = sd[f"decoder.{i}.block.{ci}.weight"]
+            ci = 1 if cfg["decoder_upsample_factors"][i] > 1 else 0
+            ref.dec_conv_w[i] = sd[f"decoder.{i}.block.{ci}.weight"].data_ptr()
             if i == n_dec - 1:
-                c.head_w = hold(w[0].permute(1, 2, 0))              # [3,3,C]
                 continue
-            scale, shift = fold_bn(sd, f"decoder.{i}.block.{ci + 1}")
-            if precision != _lib.PREC_FP32:  # BN scale folded into the weights (see the encoder above)
-                ws = w.float() * scale.to(w.device)[:, None, None, None]
-                c.dec_w[i] = hold(up2_parity_kernels(ws) if up > 1 else conv_khwc(ws), act)
-                c.dec_shift[i] = hold(shift)
-            else:
-                c.dec_w[i] = hold(conv_khwc(w), act)
-                c.dec_scale[i], c.dec_shift[i] = hold(scale), hold(shift)
+            bn = f"decoder.{i}.block.{ci + 1}"
+            ref.dec_bn_w[i], ref.dec_bn_b[i] = sd[f"{bn}.weight"].data_ptr(), sd[f"{bn}.bias"].data_ptr()
+            ref.dec_bn_mean[i], ref.dec_bn_var[i] = sd[f"{bn}.running_mean"].data_ptr(), sd[f"{bn}.running_var"].data_ptr()
             if cfg["use_skip_connections"] and f"skip_projections.{i}.weight" in sd:
-                sw = sd[f"skip_projections.{i}.weight"]
-                c.skip_w[i] = hold(sw.reshape(sw.shape[0], sw.shape[1]), act)
-                c.skip_b[i] = hold(sd[f"skip_projections.{i}.bias"])
+                ref.skip_w[i] = sd[f"skip_projections.{i}.weight"].data_ptr()
+                ref.skip_b[i] = sd[f"skip_projections.{i}.bias"].data_ptr()
+        nbytes = lib.hvit_packed_weights_bytes(C.byref(ccfg), ref.pos_len)
+        if nbytes == 0:
+            _lib.check(-1, "hvit_packed_weights_bytes")
+        with torch.cuda.device(dev):
+            raw = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+            shift = (-raw.data_ptr()) % 256
+            self.buffer = raw[shift:shift + nbytes]
+            self.c = _lib.Weights()
+            _lib.check(lib.hvit_pack_weights(C.byref(ccfg), C.byref(ref), self.buffer.data_ptr(), nbytes, C.byref(self.c),
+                                             _lib.current_stream_ptr()), "hvit_pack_weights")
+            # the fp32 staging copies (`sd`) are released when this returns: wait for the packing kernels that read them
+            torch.cuda.current_stream().synchronize()
+        self.nbytes = nbytes

