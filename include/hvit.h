@@ -179,6 +179,17 @@ int hvit_forward(hvit_plan* plan, const float* x_dev, float* y_dev, float* attn_
  *   wave_in_dev / wave_out_dev: fp32 [B, n_samples]. */
 int hvit_enhance(hvit_plan* plan, const float* wave_in_dev, float* wave_out_dev, int normalize, void* stream);
 
+/* Variable-length batches (SURVEY.md section 8 f rank 2; the reference has the plumbing - key mask
+ * models/attention.py:94-98, zero-pad collate data/dataset.py:297-347 - but never connects it).  wave_in_dev
+ * [B, n_samples] holds clips zero-padded to the plan's n_samples, n_valid_dev [B] (device int32) their true lengths
+ * (hvit_varlen_min_samples(plan) <= n <= n_samples; values outside are clamped).  Every clip is processed exactly as
+ * AudioEnhancer.enhance (inference/enhancer.py:55-135) would process it alone: its own frame count, right-border zero
+ * padding in every convolution, token order / positional rows / attention keys of its own patch grid, bilinear
+ * resizes between its own widths, iSTFT to its own length.  wave_out_dev [B, n_samples]: samples >= n are zero. */
+int hvit_enhance_varlen(hvit_plan* plan, const float* wave_in_dev, float* wave_out_dev, const int* n_valid_dev,
+                        int normalize, void* stream);
+int hvit_varlen_min_samples(const hvit_plan* plan);
+
 /* Introspection for tests: byte offset (into the workspace), and dims of a named internal buffer.
  * Names: "enc<i>", "tokens", "ln", "qkv", "attn", "mlp", "cat<i>", "logits" (debug mode), "tanh", and for enhance
  * plans "model_out" (debug mode), "mag", "max_val", "mag_max".  dims receives up to 4 ints; returns the rank or

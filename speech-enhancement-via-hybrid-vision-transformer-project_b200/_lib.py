@@ -78,6 +78,8 @@ SYMBOLS = {
     "hvit_plan_set_debug": (_I, [_VP, _I]),
     "hvit_forward": (_I, [_VP, _VP, _VP, _VP, _VP]),
     "hvit_enhance": (_I, [_VP, _VP, _VP, _I, _VP]),
+    "hvit_enhance_varlen": (_I, [_VP, _VP, _VP, _VP, _I, _VP]),
+    "hvit_varlen_min_samples": (_I, [_VP]),
     "hvit_plan_buffer": (_I, [_VP, C.c_char_p, C.POINTER(_SZ), C.POINTER(_I * 4), C.POINTER(_I)]),
     "hvit_plan_launch_count": (_I, [_VP, _I]),
     "hvit_plan_tokens": (_I, [_VP, C.POINTER(_I), C.POINTER(_I)]),

@@ -305,6 +305,7 @@ struct Ctx {
   float* wave_out;           // enhance only
   int normalize;             // enhance only
   int fused_resize;          // enhance: the final bilinear resize is fused into the iSTFT frame kernel
+  const int* geo;            // hvit_enhance_varlen: per-clip geometry table (kernels.h), null for equal-length batches
   cudaStream_t stream;
 };
 typedef std::function<int(const Ctx&)> Step;
@@ -516,6 +517,11 @@ static int build_geometry(const hvit_model_cfg& c, int B, int F, int T, int n_sa
     add("max_val", 4, 1, B, 0, 0, 0, B);
     add("mag_max", 4, 1, B, 0, 0, 0, B);
     add("mag", 4, 3, B, F, T, 0, static_cast<size_t>(B) * F * T);
+    // variable-length batches (hvit_enhance_varlen): per-clip geometry table, the patch grid before it is compacted
+    // into each clip's own token order, and to_feature_map's rows before they are scattered back onto the grid
+    add("geo", 4, 2, B, GEO_STRIDE, 0, 0, static_cast<size_t>(B) * GEO_STRIDE);
+    add("tokgrid", 4, 2, g.M, c.embed_dim, 0, 0, M * c.embed_dim);
+    add("tofm_rows", g.es, 2, g.M, g.cat[0].Cx, 0, 0, M * g.cat[0].Cx);
   }
   g.total = off;
   return HVIT_OK;
@@ -648,6 +654,17 @@ static int add_conv(hvit_plan* p, const std::string& name, const void* in, int B
   return HVIT_OK;
 }
 
+// variable-length batches only: zero the pixel columns beyond each clip's own width (no-op for equal-length batches).
+// A zero-padded clip then looks to the next 3x3 conv exactly like the reference's zero padding at the right border.
+static void add_mask(hvit_plan* p, const std::string& name, void* buf, int H, int Hpitch, int Wmax, int pix_bytes,
+                     int geo_idx) {
+  const int B = p->g.B;
+  p->steps.push_back([=](const Ctx& k) {
+    return k.geo != nullptr ? launch_zero_cols(buf, B, H, Hpitch, Wmax, pix_bytes, k.geo, geo_idx, k.stream) : 0;
+  });
+  p->tag(name, "zero_cols", 0, 0, 0, 0);
+}
+
 // patch embedding step: p x p / stride p conv (+bias) + positional table -> fp32 tokens [B * Hp * Wp, D]
 // (PatchEmbedding + PositionalEncoding, models/components.py:282-307,310-386); token n = h' * Wp + w'
 static int add_patch_embed(hvit_plan* p, const void* in, int B, int H, int Hpitch, int W, int C, const void* pw,
@@ -725,6 +742,7 @@ static int build_steps(hvit_plan* p) {
       const double fl = 2.0 * B * F * T * C0 * 9.0;
       p->tag("encoder.0", stem_tc ? "stem_tc" : "stem", fl, fl, static_cast<double>(B) * F * T * 4 + static_cast<double>(B) * g.enc[0].H * g.enc[0].W * C0 * g.es);
     }
+    add_mask(p, "encoder.0.mask", out, g.enc[0].H, g.enc[0].pitch, g.enc[0].W, C0 * g.es, GEO_ENC + 0);
   }
   // 2. encoder blocks 1.. : implicit-GEMM 3x3 conv + folded BN + ReLU (+ fused 2x2 max-pool)
   float* conv_tmp = g.bufs.count("conv_tmp") ? at<float>(p, "conv_tmp") : nullptr;
@@ -736,6 +754,7 @@ static int build_steps(hvit_plan* p) {
     r = add_conv(p, std::string("encoder.") + std::to_string(i), at<void>(p, nm), B, s.H, s.W, s.C, w.enc_w[i], w.enc_scale[i], w.enc_shift[i], 1,
                  c.enc_pool[i] == 2, 0, at<void>(p, nm2), d.C, d.pitch, d.C, conv_tmp);
     if (r) return r;
+    add_mask(p, std::string("encoder.") + std::to_string(i) + ".mask", at<void>(p, nm2), d.H, d.pitch, d.W, d.C * g.es, GEO_ENC + i);
   }
   // 3. patch embedding (+bias +positional embedding) -> fp32 residual stream
   {
@@ -744,6 +763,26 @@ static int build_steps(hvit_plan* p) {
     r = add_patch_embed(p, at<void>(p, nm), B, e.H, e.pitch, e.W, e.C, w.patch_w, w.patch_b, w.pos_embed, c.patch_size, D,
                         at<float>(p, "tokens"));
     if (r) return r;
+    if (g.n_samples > 0) {
+      // variable-length batch: the GEMM writes the bare patch grid (bias, no positional rows), then every clip's valid
+      // columns are compacted into ITS token order n = h' * Wp_b + w' and get ITS positional rows pos[n]
+      // (components.py:282-307,384: the reference flattens and indexes per clip)
+      hvit_plan tmp;
+      tmp.cfg = p->cfg;
+      float* grid = at<float>(p, "tokgrid");
+      r = add_patch_embed(&tmp, at<void>(p, nm), B, e.H, e.pitch, e.W, e.C, w.patch_w, w.patch_b, nullptr, c.patch_size, D, grid);
+      if (r) return r;
+      const Step fixed = p->steps.back(), var = tmp.steps[0];
+      float* tokens = at<float>(p, "tokens");
+      const float* pos = w.pos_embed;
+      const int Hp = g.Hp, Wp = g.Wp;
+      p->steps.back() = [=](const Ctx& k) {
+        if (k.geo == nullptr) return fixed(k);
+        const int e2 = var(k);
+        if (e2) return e2;
+        return launch_tokens_compact(grid, pos, tokens, B, Hp, Wp, D, k.geo, k.stream);
+      };
+    }
   }
   // 4. transformer blocks (pre-norm), residual stream fp32
   float* tok = at<float>(p, "tokens");
@@ -786,14 +825,14 @@ static int build_steps(hvit_plan* p) {
           const int e = launch_attn_probs_16(qkv, f16, k.probs + probs_off, B, Np, heads, D, scale, k.stream);
           if (e) return e;
         }
-        return launch_attn_tc(tq, to, f16, B, Np, heads, D, scale, k.stream);
+        return launch_attn_tc(tq, to, f16, B, Np, heads, D, scale, k.stream, nullptr, k.geo);
       });
       p->tag(L + ".attn", "attn_tc", 4.0 * B * heads * Np * Np * 64.0, 4.0 * B * heads * Np * Np * 64.0,
              static_cast<double>(M) * 4 * D * g.es);
     } else {
       p->steps.push_back([=](const Ctx& k) {
         return launch_attn_f32(reinterpret_cast<const float*>(qkv), reinterpret_cast<float*>(att),
-                               k.probs != nullptr ? k.probs + probs_off : nullptr, B, Np, heads, D, scale, k.stream);
+                               k.probs != nullptr ? k.probs + probs_off : nullptr, B, Np, heads, D, scale, k.stream, k.geo);
       });
       p->tag(L + ".attn", "attn_f32", 4.0 * B * heads * Np * Np * 64.0, 4.0 * B * heads * Np * Np * 64.0,
              static_cast<double>(M) * 4 * D * g.es);
@@ -829,6 +868,23 @@ static int build_steps(hvit_plan* p) {
     const CatGeo& k0 = g.cat[0];
     r = add_linear(p, "to_feature_map", ln, D, w.tofm_w, w.tofm_b, ACT_NONE, nullptr, 0, 0, at<void>(p, "cat0"), k0.Ccat, !bf, M, k0.Cx, D);
     if (r) return r;
+    if (g.n_samples > 0) {
+      // variable-length batch: rows are in each clip's own token order -> scatter them back onto the [Hp, Wp] grid
+      hvit_plan tmp;
+      tmp.cfg = p->cfg;
+      void* rows = at<void>(p, "tofm_rows");
+      void* cat0 = at<void>(p, "cat0");
+      r = add_linear(&tmp, "to_feature_map", ln, D, w.tofm_w, w.tofm_b, ACT_NONE, nullptr, 0, 0, rows, k0.Cx, !bf, M, k0.Cx, D);
+      if (r) return r;
+      const Step fixed = p->steps.back(), var = tmp.steps[0];
+      const int Hp = g.Hp, Wp = g.Wp, Cx = k0.Cx, Ccat = k0.Ccat;
+      p->steps.back() = [=](const Ctx& k) {
+        if (k.geo == nullptr) return fixed(k);
+        const int e2 = var(k);
+        if (e2) return e2;
+        return launch_tofm_expand(rows, dt, cat0, B, Hp, Wp, Cx, Ccat, k.geo, k.stream);
+      };
+    }
   }
   // 6. decoder blocks with skip connections
   for (int i = 0; i + 1 < c.n_dec; ++i) {
@@ -845,7 +901,9 @@ static int build_steps(hvit_plan* p) {
       const void* src = at<void>(p, en);
       void* samp = at<void>(p, "samp");
       const int Hs = e.H, Hpit = e.pitch, Ws = e.W, Cs = e.C, Hd = k.H, Wd = k.W;
-      p->steps.push_back([=](const Ctx& x) { return launch_skip_sample(src, dt, B, Hs, Hpit, Ws, Cs, Hd, Wd, samp, x.stream); });
+      p->steps.push_back([=](const Ctx& x) {
+        return launch_skip_sample(src, dt, B, Hs, Hpit, Ws, Cs, Hd, Wd, samp, x.stream, x.geo, GEO_ENC + ei, GEO_CAT + i);
+      });
       p->tag("skip." + std::to_string(i) + ".sample", "skip_sample", 0, 0, 5.0 * B * Hd * Wd * Cs * g.es);
       // reference graph: 1x1 conv on the full-resolution skip feature, then bilinear resize (hybrid_vit.py:377-386)
       r = add_linear(p, "skip." + std::to_string(i) + ".proj", samp, Cs, w.skip_w[i], w.skip_b[i], ACT_NONE, nullptr, 0,
@@ -853,6 +911,8 @@ static int build_steps(hvit_plan* p) {
                      2.0 * B * Hs * Ws * c.dec_channels[i] * Cs);
       if (r) return r;
     }
+    // (variable-length batch: both halves of the concat buffer are zero beyond the clip's own width before the conv reads it)
+    add_mask(p, std::string("decoder.") + std::to_string(i) + ".mask", cat, k.H, k.H, k.W, k.Ccat * g.es, GEO_CAT + i);
     r = add_conv(p, std::string("decoder.") + std::to_string(i), cat, B, k.H, k.W, k.Ccat, w.dec_w[i], w.dec_scale[i], w.dec_shift[i], 1, 0, c.dec_up[i] == 2,
                  at<void>(p, nm2), kn.Ccat, kn.H, c.dec_channels[i], nullptr);
     if (r) return r;
@@ -866,6 +926,7 @@ static int build_steps(hvit_plan* p) {
     float* th = at<float>(p, "tanh");
     const float* hw = w.head_w;
     const int H = k.H, W = k.W, C = k.Ccat, F = g.F, T = g.T;
+    add_mask(p, "decoder." + std::to_string(c.n_dec - 1) + ".mask", at<void>(p, nm), H, H, W, C * g.es, GEO_CAT + c.n_dec - 1);
     p->steps.push_back([=](const Ctx& x) { return launch_head(in, dt, hw, B, H, W, C, p->debug ? logits : nullptr, th, x.stream); });
     p->tag("decoder." + std::to_string(c.n_dec - 1), "head", 2.0 * B * H * W * C * 9.0, 2.0 * B * H * W * C * 9.0,
            static_cast<double>(B) * H * W * (C * g.es + 4));
@@ -883,13 +944,15 @@ static int build_steps(hvit_plan* p) {
     p->pre.push_back([=](const Ctx& x) { return launch_peak(x.wave_in, B, n, max_val, x.normalize, x.stream); });
     p->pre_meta.push_back(StepMeta{"peak_norm", "peak", 0, 0, static_cast<double>(B) * n * 4, 2});
     // the complex spectrogram is never stored: the back end recomputes the noisy phase from the waveform
-    p->pre.push_back([=](const Ctx& x) { return launch_stft(x.wave_in, B, n, T, max_val, nullptr, mag, mag_max, x.stream); });
+    p->pre.push_back([=](const Ctx& x) { return launch_stft(x.wave_in, B, n, T, max_val, nullptr, mag, mag_max, x.stream, x.geo); });
     p->pre_meta.push_back(StepMeta{"stft", "stft", 0, 0, static_cast<double>(B) * n * 4 + ft * 4, 2});
     const CatGeo& hl = g.cat[c.n_dec - 1];
     const float* th = at<float>(p, "tanh");
     const int Hs = hl.H, Ws = hl.W;
+    const int geo_ws = GEO_CAT + c.n_dec - 1;
     p->post.push_back([=](const Ctx& x) {
-      return launch_enhance_istft(x.wave_in, max_val, mag_max, th, Hs, Ws, p->debug ? mo : nullptr, x.wave_out, B, n, T, x.stream);
+      return launch_enhance_istft(x.wave_in, max_val, mag_max, th, Hs, Ws, p->debug ? mo : nullptr, x.wave_out, B, n, T, x.stream,
+                                  x.geo, geo_ws);
     });
     p->post_meta.push_back(StepMeta{"istft", "enhance_istft", 0, 0,
                                     2.0 * B * n * 4 + static_cast<double>(B) * Hs * Ws * 4, 1});
@@ -1038,6 +1101,58 @@ int hvit_enhance(hvit_plan* plan, const float* wave_in_dev, float* wave_out_dev,
     if (r) return r;
   }
   int r = run_steps(plan, c);
+  if (r) return r;
+  for (const Step& st : plan->post) {
+    r = st(c);
+    if (r) return r;
+  }
+  return HVIT_OK;
+}
+
+// smallest clip (samples) that still yields one patch column after the encoder's pooling
+static int varlen_min_samples(const hvit_model_cfg& c) {
+  int down = c.patch_size;
+  for (int i = 0; i < c.n_enc; ++i) down *= c.enc_pool[i];
+  return (down - 1) * 128;   // T = 1 + n / 128 >= down
+}
+
+int hvit_varlen_min_samples(const hvit_plan* plan) {
+  if (plan == nullptr) return HVIT_E_ARG;
+  return varlen_min_samples(plan->cfg);
+}
+
+int hvit_enhance_varlen(hvit_plan* plan, const float* wave_in_dev, float* wave_out_dev, const int* n_valid_dev,
+                        int normalize, void* stream) {
+  if (plan == nullptr || wave_in_dev == nullptr || wave_out_dev == nullptr || n_valid_dev == nullptr) {
+    set_error("hvit_enhance_varlen: null argument");
+    return HVIT_E_ARG;
+  }
+  if (plan->g.n_samples <= 0) {
+    set_error("hvit_enhance_varlen: plan was created without n_samples");
+    return HVIT_E_ARG;
+  }
+  const hvit_model_cfg& cf = plan->cfg;
+  if (cf.n_enc > 8 || cf.n_dec > 8) {
+    set_error("hvit_enhance_varlen: at most 8 encoder / decoder blocks");
+    return HVIT_E_SHAPE;
+  }
+  Ctx c = enhance_ctx(plan, wave_in_dev, wave_out_dev, normalize, stream);
+  VarlenCfg vc;
+  memset(&vc, 0, sizeof(vc));
+  vc.n_enc = cf.n_enc; vc.n_dec = cf.n_dec; vc.patch = cf.patch_size; vc.Hp = plan->g.Hp;
+  for (int i = 0; i < cf.n_enc; ++i) vc.enc_pool[i] = cf.enc_pool[i];
+  for (int i = 0; i < cf.n_dec; ++i) vc.dec_up[i] = cf.dec_up[i];
+  vc.n_min = varlen_min_samples(cf);
+  vc.n_max = plan->g.n_samples;
+  int* geo = at<int>(plan, "geo");
+  int r = launch_varlen_geometry(n_valid_dev, plan->g.B, vc, geo, c.stream);
+  if (r) return r;
+  c.geo = geo;
+  for (const Step& st : plan->pre) {
+    r = st(c);
+    if (r) return r;
+  }
+  r = run_steps(plan, c);
   if (r) return r;
   for (const Step& st : plan->post) {
     r = st(c);

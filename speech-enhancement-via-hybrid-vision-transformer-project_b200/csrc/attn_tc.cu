@@ -132,7 +132,7 @@ __device__ __forceinline__ float exp_pack_row(uint32_t (&s)[128], float scale_lo
 template <bool PROF>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out, int N,
-               int D, int heads, int n_items, float scale_log2, int f16, long long* prof) {
+               int D, int heads, int n_items, float scale_log2, int f16, long long* prof, const int* __restrict__ geo) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B swizzle needs 1024-byte aligned tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -149,8 +149,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkv = (N + 127) / 128;
   const int qpairs = (N + 255) / 256;
+  // keys of clip b: all N tokens, or - variable-length batch - its own valid prefix N_b (token order is the clip's own,
+  // so validity is a prefix): key blocks beyond N_b are skipped by every role, the tail of the last one is masked.
+  // Every QUERY tile is still computed (rows >= N_b are padding: finite, never read by a valid row).
+  auto clip_tokens = [&](int b) -> int { return geo != nullptr ? __ldg(geo + b * GEO_STRIDE + GEO_NTOK) : N; };
   // persistent work loop: item -> (clip b, head h, query-tile pair); the pairs of one (b, h) are adjacent items, so
   // they run at the same time on neighbouring CTAs and share K / V in L2
   auto decode = [&](int item, int& b, int& h, int& q0) {
@@ -205,6 +208,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
           int b, h, q0;
           decode(item, b, h, q0);
           const bool hasB = q0 + 128 < N;
+          const int nkv = (clip_tokens(b) + 127) / 128;
           mbar_wait(q_empty, (it & 1) ^ 1);
           mbar_expect_tx(q_full, hasB ? 2 * TILE_BYTES : TILE_BYTES);
           tma_load_3d(smem + OFF_Q, &tmap_qkv, q_full, h * 64, q0, b);
@@ -247,6 +251,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
           int b, h, q0;
           decode(item, b, h, q0);
+          const int nkv = (clip_tokens(b) + 127) / 128;
           if (w == 1 && !(q0 + 128 < N)) {  // no second query tile: only keep the shared barriers' counts
             // (each arrival waits for the matching "full" phase first, so it can never land in an earlier phase)
             mbar_wait(q_full, it & 1);
@@ -316,9 +321,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
       decode(item, b, h, q0);
       const bool hasB = q0 + 128 < N;
       if (w == 1 && !hasB) continue;  // this pair has no second query tile
+      const int Nb = clip_tokens(b);
+      const int nkv = (Nb + 127) / 128;
       float m_used = -INFINITY, l_run = 0.f;
       for (int j = 0; j < nkv; ++j, ++blk) {
-        const int nvalid = min(128, N - j * 128);
+        const int nvalid = min(128, Nb - j * 128);
         const long long c0 = tick();
         mbar_wait(&s_full[w], blk & 1);
         tc_fence_after();
@@ -441,7 +448,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
 }  // namespace
 
 int launch_attn_tc(const CUtensorMap& tmap_qkv, const CUtensorMap& tmap_out, int f16, int B, int N, int heads, int D,
-                   float scale, cudaStream_t stream, long long* prof) {
+                   float scale, cudaStream_t stream, long long* prof, const int* geo) {
   if (D != heads * 64) {
     set_error("attention: head_dim must be 64 (D=%d heads=%d)", D, heads);
     return -1;
@@ -465,9 +472,9 @@ int launch_attn_tc(const CUtensorMap& tmap_qkv, const CUtensorMap& tmap_out, int
   const int grid = items < sms ? static_cast<int>(items) : sms;
   const cudaError_t le =
       prof != nullptr ? launch_pdl(attn_tc_kernel<true>, dim3(grid), dim3(AT_THREADS), AT_SMEM, stream, tmap_qkv, tmap_out,
-                                   N, D, heads, static_cast<int>(items), scale * 1.4426950408889634f, f16, prof)
+                                   N, D, heads, static_cast<int>(items), scale * 1.4426950408889634f, f16, prof, geo)
                       : launch_pdl(attn_tc_kernel<false>, dim3(grid), dim3(AT_THREADS), AT_SMEM, stream, tmap_qkv, tmap_out,
-                                   N, D, heads, static_cast<int>(items), scale * 1.4426950408889634f, f16, prof);
+                                   N, D, heads, static_cast<int>(items), scale * 1.4426950408889634f, f16, prof, geo);
   if (le != cudaSuccess) {
     set_error("attn_tc: %s", cudaGetErrorString(le));
     return -4;

@@ -159,10 +159,10 @@ __global__ void fill_u32_kernel(unsigned* p, int n, unsigned v) {
 // ------------------------------------------------------------------ STFT + |.| + per-clip max (enhancer.py:82-101)
 // Every warp transforms TWO real frames with one complex FFT (frame a in the real parts, frame b in the imaginary
 // parts): A[k] = (Z[k] + conj Z[N-k]) / 2, B[k] = (Z[k] - conj Z[N-k]) / 2i.  Half the butterflies per frame.
-__global__ void __launch_bounds__(FR * 32, 4) stft_kernel(const float* __restrict__ wave, int n, int T,
+__global__ void __launch_bounds__(FR * 32, 4) stft_kernel(const float* __restrict__ wave, int n_pitch, int T_pitch,
                                                        const unsigned* __restrict__ max_bits,
                                                        float2* __restrict__ spec, float* __restrict__ mag,
-                                                       unsigned* __restrict__ mag_max_bits) {
+                                                       unsigned* __restrict__ mag_max_bits, const int* __restrict__ geo) {
   griddep_launch_dependents();
   griddep_wait();
   extern __shared__ float2 sm[];
@@ -170,10 +170,14 @@ __global__ void __launch_bounds__(FR * 32, 4) stft_kernel(const float* __restric
   const int b = blockIdx.y, t0 = blockIdx.x * FRAMES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float inv_mv = 1.0f / guard_scalar(max_bits[b]);
+  // variable-length batch: this clip's own sample / frame counts (its frames >= T are written as zero magnitude, so
+  // the padded clip looks to the encoder exactly like the reference's zero padding at the right border)
+  const int n = geo != nullptr ? geo[b * GEO_STRIDE + GEO_N] : n_pitch;
+  const int T = geo != nullptr ? geo[b * GEO_STRIDE + GEO_T] : T_pitch;
   const int ta = t0 + 2 * warp;
   float2* x = xs + warp * XS;
   if (ta < T) {
-    const float* w = wave + static_cast<long long>(b) * n;
+    const float* w = wave + static_cast<long long>(b) * n_pitch;
     const bool has_b = ta + 1 < T;
     const int s0 = ta * HOP - NFFT / 2;  // first sample of frame a (frame b starts HOP later); centred, zero padded
     if (s0 >= 0 && s0 + HOP + NFFT <= n && has_b) {
@@ -202,13 +206,22 @@ __global__ void __launch_bounds__(FR * 32, 4) stft_kernel(const float* __restric
   float lmax = 0.f;
   {
     const int tl = threadIdx.x & (FRAMES - 1), fq = threadIdx.x / FRAMES;
+    if (t0 + tl >= T && t0 + tl < T_pitch) {   // padding frames of a shorter clip in a variable-length batch
+      const long long o0 = (static_cast<long long>(b) * NBIN + fq) * T_pitch + t0 + tl;
+      const long long step = static_cast<long long>(FR * 32 / FRAMES) * T_pitch;
+      long long o = o0;
+      for (int f = fq; f < NBIN; f += FR * 32 / FRAMES, o += step) {
+        if (spec != nullptr) spec[o] = make_float2(0.f, 0.f);
+        mag[o] = 0.f;
+      }
+    }
     if (t0 + tl < T) {
       const float2* xw = xs + (tl >> 1) * XS;
       const bool second = (tl & 1) != 0;
-      const long long o0 = (static_cast<long long>(b) * NBIN + fq) * T + t0 + tl;
+      const long long o0 = (static_cast<long long>(b) * NBIN + fq) * T_pitch + t0 + tl;
       float2* sp = spec + o0;
       float* mp = mag + o0;
-      const long long step = static_cast<long long>(FR * 32 / FRAMES) * T;
+      const long long step = static_cast<long long>(FR * 32 / FRAMES) * T_pitch;
       for (int f = fq; f < NBIN; f += FR * 32 / FRAMES, sp += step, mp += step) {
         const float2 z1 = xw[fpad(f)], z2 = xw[fpad((NFFT - f) & (NFFT - 1))];
         const float2 z = second ? make_float2(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x))
@@ -371,12 +384,13 @@ __global__ void istft_ola_kernel(const float* __restrict__ frames, const unsigne
 constexpr int OLA_HOPS = FRAMES - 3;
 constexpr int EI_SMEM = FR * XS * sizeof(float2) + NBIN * (sizeof(int2) + sizeof(float));
 
-__global__ void __launch_bounds__(FR * 32, 4) enhance_istft_kernel(const float* __restrict__ wave, int n, int T,
+__global__ void __launch_bounds__(FR * 32, 4) enhance_istft_kernel(const float* __restrict__ wave, int n_pitch, int T_pitch,
                                                                 const unsigned* __restrict__ max_bits,
                                                                 const unsigned* __restrict__ mag_max_bits,
-                                                                const float* __restrict__ lowres, int Hs, int Ws,
+                                                                const float* __restrict__ lowres, int Hs, int Ws_pitch,
                                                                 float* __restrict__ model_out,
-                                                                float* __restrict__ wave_out) {
+                                                                float* __restrict__ wave_out,
+                                                                const int* __restrict__ geo, int geo_ws_idx) {
   griddep_launch_dependents();
   griddep_wait();
   extern __shared__ float2 sm[];
@@ -388,9 +402,14 @@ __global__ void __launch_bounds__(FR * 32, 4) enhance_istft_kernel(const float* 
   const float mv = guard_scalar(max_bits[b]);
   const float inv_mv = 1.0f / mv;
   const float mm = guard_scalar(mag_max_bits[b]);
+  // variable-length batch: this clip's own sample count, frame count and decoder-output width (the resize of the
+  // reference maps ITS [Hs, Ws_b] map onto ITS [257, T_b] spectrogram); samples beyond n_b are written as zero
+  const int n = geo != nullptr ? geo[b * GEO_STRIDE + GEO_N] : n_pitch;
+  const int T = geo != nullptr ? geo[b * GEO_STRIDE + GEO_T] : T_pitch;
+  const int Ws = geo != nullptr ? geo[b * GEO_STRIDE + geo_ws_idx] : Ws_pitch;
   for (int f = threadIdx.x; f < NBIN; f += FR * 32) {
     const Lerp ly = make_lerp(f, Hs, NBIN);
-    lyi[f] = make_int2(ly.i0 * Ws, ly.i1 * Ws);
+    lyi[f] = make_int2(ly.i0 * Ws_pitch, ly.i1 * Ws_pitch);
     lyw[f] = ly.l1;
   }
   const int ta = t0 + 2 * warp;
@@ -398,7 +417,7 @@ __global__ void __launch_bounds__(FR * 32, 4) enhance_istft_kernel(const float* 
   float2* x = xs + warp * XS;
   if (live) {
     // ---- frames ta, ta + 1 of the peak-normalised noisy clip (same arithmetic as stft_kernel)
-    const float* w = wave + static_cast<long long>(b) * n;
+    const float* w = wave + static_cast<long long>(b) * n_pitch;
     const int s0 = ta * HOP - NFFT / 2;
     if (s0 >= 0 && s0 + HOP + NFFT <= n && has_b) {
       const float* wa = w + s0;
@@ -423,7 +442,7 @@ __global__ void __launch_bounds__(FR * 32, 4) enhance_istft_kernel(const float* 
   __syncthreads();  // resize table complete
   if (live) {
     const Lerp lxa = make_lerp(ta, Ws, T), lxb = make_lerp(has_b ? ta + 1 : ta, Ws, T);
-    const float* src = lowres + static_cast<long long>(b) * Hs * Ws;
+    const float* src = lowres + static_cast<long long>(b) * Hs * Ws_pitch;
     // E = (model_out * mag_max) * S / |S| of one bin (z = S, mo = model output)
     auto bin = [&](float2 z, float mo, int f) -> float2 {
       const float zz = z.x * z.x + z.y * z.y;
@@ -456,7 +475,7 @@ __global__ void __launch_bounds__(FR * 32, 4) enhance_istft_kernel(const float* 
         mob = wy0 * (lxb.l0 * __ldg(r0 + lxb.i0) + lxb.l1 * __ldg(r0 + lxb.i1)) +
               wy1 * (lxb.l0 * __ldg(r1 + lxb.i0) + lxb.l1 * __ldg(r1 + lxb.i1));
       if (model_out != nullptr) {  // debug / test builds of the plan only: the resized model output [B,257,T]
-        float* mp = model_out + (static_cast<long long>(b) * NBIN + f) * T + ta;
+        float* mp = model_out + (static_cast<long long>(b) * NBIN + f) * T_pitch + ta;
         mp[0] = moa;
         if (has_b) mp[1] = mob;
       }
@@ -471,9 +490,13 @@ __global__ void __launch_bounds__(FR * 32, 4) enhance_istft_kernel(const float* 
   __syncthreads();
   // ---- overlap-add of this block's hop range straight out of shared memory, envelope division, de-normalisation
   const int j_lo = blockIdx.x == 0 ? NFFT / 2 : HOP * (t0 + 3);
-  const int j_hi = min(HOP * (t0 + FRAMES), NFFT / 2 + n);
-  float* out = wave_out + static_cast<long long>(b) * n - NFFT / 2;
+  const int j_hi = min(HOP * (t0 + FRAMES), NFFT / 2 + n_pitch);
+  float* out = wave_out + static_cast<long long>(b) * n_pitch - NFFT / 2;
   for (int j = j_lo + threadIdx.x; j < j_hi; j += FR * 32) {
+    if (j >= NFFT / 2 + n) {  // padding of a shorter clip (variable-length batch)
+      out[j] = 0.f;
+      continue;
+    }
     const int h = j >> 7;
     const int thi = min(h, T - 1), tlo = max(h - 3, 0);
     float acc = 0.f, wss = 0.f;
@@ -703,7 +726,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
 // (the 1x1 projection is applied AFTER sampling; exact because bilinear weights sum to 1 - hybrid_vit.py:377-386)
 template <typename T>
 __global__ void skip_sample_kernel(const T* __restrict__ src, int Hs, int HsPitch, int Ws, int C, int Hd, int Wd,
-                                   T* __restrict__ dst, long long total) {
+                                   T* __restrict__ dst, long long total, const int* __restrict__ geo, int gsrc, int gdst) {
   griddep_launch_dependents();
   griddep_wait();
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -715,7 +738,18 @@ __global__ void skip_sample_kernel(const T* __restrict__ src, int Hs, int HsPitc
   r /= Wd;
   const int hd = static_cast<int>(r % Hd);
   const int b = static_cast<int>(r / Hd);
-  const Lerp ly = make_lerp(hd, Hs, Hd), lx = make_lerp(wd, Ws, Wd);
+  T* out = dst + ((static_cast<long long>(b) * Hd + hd) * Wd + wd) * C + c;
+  int Ws_b = Ws, Wd_b = Wd;
+  if (geo != nullptr) {  // variable-length batch: this clip's own source / destination widths; zero beyond
+    Ws_b = geo[b * GEO_STRIDE + gsrc];
+    Wd_b = geo[b * GEO_STRIDE + gdst];
+    if (wd >= Wd_b) {
+      const float z[4] = {0.f, 0.f, 0.f, 0.f};
+      st4<T>(out, z);
+      return;
+    }
+  }
+  const Lerp ly = make_lerp(hd, Hs, Hd), lx = make_lerp(wd, Ws_b, Wd_b);
   const T* base = src + static_cast<long long>(b) * HsPitch * Ws * C + c;
   float v00[4], v01[4], v10[4], v11[4], o[4];
   ld4<T>(base + (static_cast<long long>(ly.i0) * Ws + lx.i0) * C, v00);
@@ -725,7 +759,7 @@ __global__ void skip_sample_kernel(const T* __restrict__ src, int Hs, int HsPitc
 #pragma unroll
   for (int j = 0; j < 4; ++j)
     o[j] = ly.l0 * (lx.l0 * v00[j] + lx.l1 * v01[j]) + ly.l1 * (lx.l0 * v10[j] + lx.l1 * v11[j]);
-  st4<T>(dst + ((static_cast<long long>(b) * Hd + hd) * Wd + wd) * C + c, o);
+  st4<T>(out, o);
 }
 
 // ------------------------------------------------------------------ head: Conv3x3(C->1, no bias) + tanh, fp32 accumulate
@@ -762,7 +796,7 @@ __device__ __forceinline__ void ld8<__half>(const __half* p, float* v) {
 // 16-bit variant of skip_sample_kernel with 8 channels (one 16-byte load per tap, one 16-byte store) per thread
 template <typename T>
 __global__ void skip_sample8_kernel(const T* __restrict__ src, int Hs, int HsPitch, int Ws, int C, int Hd, int Wd,
-                                    T* __restrict__ dst, long long total) {
+                                    T* __restrict__ dst, long long total, const int* __restrict__ geo, int gsrc, int gdst) {
   griddep_launch_dependents();
   griddep_wait();
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -774,7 +808,17 @@ __global__ void skip_sample8_kernel(const T* __restrict__ src, int Hs, int HsPit
   r /= Wd;
   const int hd = static_cast<int>(r % Hd);
   const int b = static_cast<int>(r / Hd);
-  const Lerp ly = make_lerp(hd, Hs, Hd), lx = make_lerp(wd, Ws, Wd);
+  T* out = dst + ((static_cast<long long>(b) * Hd + hd) * Wd + wd) * C + c;
+  int Ws_b = Ws, Wd_b = Wd;
+  if (geo != nullptr) {  // variable-length batch: this clip's own source / destination widths; zero beyond
+    Ws_b = geo[b * GEO_STRIDE + gsrc];
+    Wd_b = geo[b * GEO_STRIDE + gdst];
+    if (wd >= Wd_b) {
+      *reinterpret_cast<uint4*>(out) = make_uint4(0, 0, 0, 0);
+      return;
+    }
+  }
+  const Lerp ly = make_lerp(hd, Hs, Hd), lx = make_lerp(wd, Ws_b, Wd_b);
   const T* base = src + static_cast<long long>(b) * HsPitch * Ws * C + c;
   float v00[8], v01[8], v10[8], v11[8], o[8];
   ld8<T>(base + (static_cast<long long>(ly.i0) * Ws + lx.i0) * C, v00);
@@ -788,7 +832,7 @@ __global__ void skip_sample8_kernel(const T* __restrict__ src, int Hs, int HsPit
   uint4 pk;
   pk.x = pack_16x2(o[0], o[1], f16); pk.y = pack_16x2(o[2], o[3], f16);
   pk.z = pack_16x2(o[4], o[5], f16); pk.w = pack_16x2(o[6], o[7], f16);
-  *reinterpret_cast<uint4*>(dst + ((static_cast<long long>(b) * Hd + hd) * Wd + wd) * C + c) = pk;
+  *reinterpret_cast<uint4*>(out) = pk;
 }
 
 // 8 lanes per output pixel, each lane owns 8 channels (one 16-byte load per tap): a warp instruction reads 4 whole
@@ -984,6 +1028,85 @@ __global__ void maxpool2_kernel(const float* __restrict__ src, float* __restrict
   *reinterpret_cast<float4*>(dst + ((b * Ho + oh) * Wo + ow) * C + c) = o;
 }
 
+// ------------------------------------------------------------------ variable-length batches (see kernels.h)
+__global__ void varlen_geometry_kernel(const int* __restrict__ n_valid, int B, VarlenCfg c, int* __restrict__ geo) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int n = n_valid[b];
+  n = n < c.n_min ? c.n_min : (n > c.n_max ? c.n_max : n);
+  int* g = geo + b * GEO_STRIDE;
+  const int T = 1 + n / HOP;
+  g[GEO_N] = n;
+  g[GEO_T] = T;
+  int w = T;
+  for (int i = 0; i < c.n_enc; ++i) {
+    w /= c.enc_pool[i];
+    g[GEO_ENC + i] = w;
+  }
+  const int wp = w / c.patch;
+  g[GEO_WP] = wp;
+  g[GEO_NTOK] = wp * c.Hp;
+  int wx = wp;
+  for (int i = 0; i < c.n_dec; ++i) {
+    g[GEO_CAT + i] = wx;
+    wx *= c.dec_up[i];
+  }
+}
+
+// one block per (pixel row, clip): zero the bytes of pixels [W_b, Wmax)
+__global__ void zero_cols_kernel(uint8_t* __restrict__ buf, int Hpitch, int Wmax, int pix_bytes, const int* __restrict__ geo,
+                                 int geo_idx) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int wb = geo[b * GEO_STRIDE + geo_idx];
+  if (wb >= Wmax) return;
+  uint8_t* row = buf + ((static_cast<long long>(b) * Hpitch + h) * Wmax + wb) * pix_bytes;
+  const long long bytes = static_cast<long long>(Wmax - wb) * pix_bytes;   // multiple of 16 (pix_bytes is)
+  for (long long o = static_cast<long long>(threadIdx.x) * 16; o < bytes; o += static_cast<long long>(blockDim.x) * 16)
+    *reinterpret_cast<uint4*>(row + o) = make_uint4(0, 0, 0, 0);
+}
+
+// grid (Np, B), D / 4 threads: x[b][n] = grid[b][n / Wp_b][n % Wp_b] + pos[n]  (n < N_b), 0 otherwise
+__global__ void tokens_compact_kernel(const float* __restrict__ grid, const float* __restrict__ pos, float* __restrict__ x,
+                                      int Hp, int Wp, int D, const int* __restrict__ geo) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const int n = blockIdx.x, b = blockIdx.y;
+  const int wpb = geo[b * GEO_STRIDE + GEO_WP], ntok = geo[b * GEO_STRIDE + GEO_NTOK];
+  float4* dst = reinterpret_cast<float4*>(x + (static_cast<long long>(b) * Hp * Wp + n) * D);
+  if (n >= ntok) {
+    for (int i = threadIdx.x; i < D / 4; i += blockDim.x) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  const int hq = n / wpb, wq = n - hq * wpb;
+  const float4* src = reinterpret_cast<const float4*>(grid + ((static_cast<long long>(b) * Hp + hq) * Wp + wq) * D);
+  const float4* pp = reinterpret_cast<const float4*>(pos + static_cast<long long>(n) * D);
+  for (int i = threadIdx.x; i < D / 4; i += blockDim.x) {
+    const float4 a = src[i], q = __ldg(pp + i);
+    dst[i] = make_float4(a.x + q.x, a.y + q.y, a.z + q.z, a.w + q.w);
+  }
+}
+
+// grid (Hp * Wp, B): cat[b][h][w][0:Cx] = rows[b][h * Wp_b + w][:]  (w < Wp_b), 0 otherwise; 16-byte vectors
+__global__ void tofm_expand_kernel(const uint8_t* __restrict__ rows, uint8_t* __restrict__ cat, int Hp, int Wp, int row_bytes,
+                                   int cat_pix_bytes, const int* __restrict__ geo) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const int pix = blockIdx.x, b = blockIdx.y;
+  const int hq = pix / Wp, wq = pix - hq * Wp;
+  const int wpb = geo[b * GEO_STRIDE + GEO_WP];
+  uint4* dst = reinterpret_cast<uint4*>(cat + (static_cast<long long>(b) * Hp * Wp + pix) * cat_pix_bytes);
+  if (wq >= wpb) {
+    for (int i = threadIdx.x; i < row_bytes / 16; i += blockDim.x) dst[i] = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  const uint4* src = reinterpret_cast<const uint4*>(rows + (static_cast<long long>(b) * Hp * Wp + hq * wpb + wq) * row_bytes);
+  for (int i = threadIdx.x; i < row_bytes / 16; i += blockDim.x) dst[i] = src[i];
+}
+
 constexpr int FFT_SMEM = FR * XS * sizeof(float2);
 
 }  // namespace
@@ -1028,24 +1151,25 @@ int ensure_fft_tables(cudaStream_t s) {
 }
 
 int launch_stft(const float* wave, int B, int n, int T, const float* max_val, float2* spec, float* mag,
-                unsigned* mag_max_bits, cudaStream_t s) {
+                unsigned* mag_max_bits, cudaStream_t s, const int* geo) {
   launch_pdl(fill_u32_kernel, dim3((B + 255) / 256), dim3(256), 0, s, mag_max_bits, B, 0u);
   dim3 grid((T + FRAMES - 1) / FRAMES, B);
   launch_pdl(stft_kernel, dim3(grid), dim3(FR * 32), FFT_SMEM, s, wave, n, T, reinterpret_cast<const unsigned*>(max_val), spec, mag,
-                                               mag_max_bits);
+                                               mag_max_bits, geo);
   return check_launch("stft");
 }
 
 static void fft_smem_config() {}
 
 int launch_enhance_istft(const float* wave_in, const float* max_val, const unsigned* mag_max_bits, const float* lowres,
-                         int Hs, int Ws, float* model_out, float* wave_out, int B, int n, int T, cudaStream_t s) {
+                         int Hs, int Ws, float* model_out, float* wave_out, int B, int n, int T, cudaStream_t s,
+                         const int* geo, int geo_ws_idx) {
   if (n <= 0) return 0;
   const int hops = (NFFT / 2 - 1 + n) >> 7;                        // index of the last hop that holds output
   const int blocks = hops >= 3 ? (hops - 3) / OLA_HOPS + 1 : 1;
   dim3 grid(blocks, B);
   launch_pdl(enhance_istft_kernel, dim3(grid), dim3(FR * 32), EI_SMEM, s, wave_in, n, T,
-             reinterpret_cast<const unsigned*>(max_val), mag_max_bits, lowres, Hs, Ws, model_out, wave_out);
+             reinterpret_cast<const unsigned*>(max_val), mag_max_bits, lowres, Hs, Ws, model_out, wave_out, geo, geo_ws_idx);
   return check_launch("enhance_istft");
 }
 
@@ -1115,29 +1239,29 @@ int launch_layernorm(const float* x, const float* g, const float* b, void* out, 
 }
 
 int launch_skip_sample(const void* src, int dt, int B, int Hs, int HsPitch, int Ws, int C, int Hd, int Wd,
-                       void* dst, cudaStream_t s) {
+                       void* dst, cudaStream_t s, const int* geo, int gsrc, int gdst) {
   if (dt != DT_F32 && C % 8 == 0) {
     const long long total8 = static_cast<long long>(B) * Hd * Wd * (C / 8);
     const unsigned grid8 = static_cast<unsigned>((total8 + 255) / 256);
     if (dt == DT_BF16)
       launch_pdl(skip_sample8_kernel<bf16>, dim3(grid8), dim3(256), 0, s, reinterpret_cast<const bf16*>(src), Hs, HsPitch, Ws, C, Hd,
-                 Wd, reinterpret_cast<bf16*>(dst), total8);
+                 Wd, reinterpret_cast<bf16*>(dst), total8, geo, gsrc, gdst);
     else
       launch_pdl(skip_sample8_kernel<__half>, dim3(grid8), dim3(256), 0, s, reinterpret_cast<const __half*>(src), Hs, HsPitch, Ws,
-                 C, Hd, Wd, reinterpret_cast<__half*>(dst), total8);
+                 C, Hd, Wd, reinterpret_cast<__half*>(dst), total8, geo, gsrc, gdst);
     return check_launch("skip_sample");
   }
   const long long total = static_cast<long long>(B) * Hd * Wd * (C / 4);
   const unsigned grid = static_cast<unsigned>((total + 255) / 256);
   if (dt == DT_BF16)
     launch_pdl(skip_sample_kernel<bf16>, dim3(grid), dim3(256), 0, s, reinterpret_cast<const bf16*>(src), Hs, HsPitch, Ws, C, Hd, Wd,
-                                                  reinterpret_cast<bf16*>(dst), total);
+                                                  reinterpret_cast<bf16*>(dst), total, geo, gsrc, gdst);
   else if (dt == DT_F16)
     launch_pdl(skip_sample_kernel<__half>, dim3(grid), dim3(256), 0, s, reinterpret_cast<const __half*>(src), Hs, HsPitch, Ws, C, Hd, Wd,
-                                                    reinterpret_cast<__half*>(dst), total);
+                                                    reinterpret_cast<__half*>(dst), total, geo, gsrc, gdst);
   else
     launch_pdl(skip_sample_kernel<float>, dim3(grid), dim3(256), 0, s, reinterpret_cast<const float*>(src), Hs, HsPitch, Ws, C, Hd, Wd,
-                                                   reinterpret_cast<float*>(dst), total);
+                                                   reinterpret_cast<float*>(dst), total, geo, gsrc, gdst);
   return check_launch("skip_sample");
 }
 
@@ -1203,6 +1327,39 @@ int launch_maxpool2(const float* src, float* dst, int B, int H, int W, int C, cu
   const long long total = static_cast<long long>(B) * Ho * Wo * (C / 4);
   maxpool2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(src, dst, H, W, C, Ho, Wo, total);
   return check_launch("maxpool2");
+}
+
+int launch_varlen_geometry(const int* n_valid, int B, const VarlenCfg& c, int* geo, cudaStream_t s) {
+  launch_pdl(varlen_geometry_kernel, dim3((B + 127) / 128), dim3(128), 0, s, n_valid, B, c, geo);
+  return check_launch("varlen_geometry");
+}
+
+int launch_zero_cols(void* buf, int B, int H, int Hpitch, int Wmax, int pix_bytes, const int* geo, int geo_idx,
+                     cudaStream_t s) {
+  if (pix_bytes % 16 != 0) {
+    set_error("zero_cols: pixel size must be a multiple of 16 bytes");
+    return -1;
+  }
+  launch_pdl(zero_cols_kernel, dim3(H, B), dim3(128), 0, s, reinterpret_cast<uint8_t*>(buf), Hpitch, Wmax, pix_bytes, geo, geo_idx);
+  return check_launch("zero_cols");
+}
+
+int launch_tokens_compact(const float* grid, const float* pos, float* x, int B, int Hp, int Wp, int D, const int* geo,
+                          cudaStream_t s) {
+  launch_pdl(tokens_compact_kernel, dim3(Hp * Wp, B), dim3(128), 0, s, grid, pos, x, Hp, Wp, D, geo);
+  return check_launch("tokens_compact");
+}
+
+int launch_tofm_expand(const void* rows, int dt, void* cat, int B, int Hp, int Wp, int Cx, int Ccat, const int* geo,
+                       cudaStream_t s) {
+  const int es = dt == DT_F32 ? 4 : 2;
+  if ((Cx * es) % 16 != 0 || (Ccat * es) % 16 != 0) {
+    set_error("tofm_expand: channel counts must be multiples of 16 bytes");
+    return -1;
+  }
+  launch_pdl(tofm_expand_kernel, dim3(Hp * Wp, B), dim3(64), 0, s, reinterpret_cast<const uint8_t*>(rows),
+             reinterpret_cast<uint8_t*>(cat), Hp, Wp, Cx * es, Ccat * es, geo);
+  return check_launch("tofm_expand");
 }
 
 }  // namespace hvit

@@ -100,10 +100,11 @@ int launch_igemm_f32(const IgemmParams& p, const float* A, int lda, const float*
 // ---------------------------------------------------------------------------------------------
 // Attention. qkv: [B*N, 3*D] (q | k | v, head h at columns h*64 .. h*64+63 of each third), out: [B*N, D].
 // ---------------------------------------------------------------------------------------------
+// geo (nullable): per-clip valid token count geo[b][GEO_NTOK] - keys >= N_b are masked, whole key blocks beyond it skipped
 int launch_attn_tc(const CUtensorMap& tmap_qkv, const CUtensorMap& tmap_out /*[B*N, D] 16-bit*/, int f16, int B, int N, int heads, int D, float scale,
-                   cudaStream_t stream, long long* prof = nullptr);
+                   cudaStream_t stream, long long* prof = nullptr, const int* geo = nullptr);
 int launch_attn_f32(const float* qkv, float* out, float* probs /*nullable [B,h,N,N]*/, int B, int N, int heads, int D,
-                    float scale, cudaStream_t stream);
+                    float scale, cudaStream_t stream, const int* geo = nullptr);
 // probabilities only (return_attentions=True slow path) from bf16 qkv
 int launch_attn_probs_16(const void* qkv16, int f16, float* probs, int B, int N, int heads, int D, float scale,
                          cudaStream_t stream);
@@ -114,7 +115,7 @@ int launch_attn_probs_16(const void* qkv16, int f16, float* probs, int B, int N,
 int ensure_fft_tables(cudaStream_t s);
 int launch_peak(const float* wave, int B, int n, float* max_val /*[B]*/, int normalize, cudaStream_t s);
 int launch_stft(const float* wave, int B, int n, int T, const float* max_val, float2* spec /*[B,257,T] or null*/,
-                float* mag /*[B,257,T]*/, unsigned* mag_max_bits /*[B]*/, cudaStream_t s);
+                float* mag /*[B,257,T]*/, unsigned* mag_max_bits /*[B]*/, cudaStream_t s, const int* geo = nullptr);
 // model_out [B,257,T] is read when lowres == nullptr, otherwise it is WRITTEN with the bilinear resize of
 // lowres [B,Hs,Ws] (fused final interpolate of HybridViT.forward).
 int launch_istft_frames(float* model_out, const float* lowres, int Hs, int Ws, const float2* spec,
@@ -124,7 +125,8 @@ int launch_istft_ola(const float* frames, const float* max_val, float* wave_out,
 // [B,Hs,Ws] tanh map, inverse FFT, overlap-add in shared memory, envelope, de-normalisation.  model_out (nullable)
 // receives the resized model output [B,257,T] for tests.
 int launch_enhance_istft(const float* wave_in, const float* max_val, const unsigned* mag_max_bits, const float* lowres,
-                         int Hs, int Ws, float* model_out, float* wave_out, int B, int n, int T, cudaStream_t s);
+                         int Hs, int Ws, float* model_out, float* wave_out, int B, int n, int T, cudaStream_t s,
+                         const int* geo = nullptr, int geo_ws_idx = 0);
 int launch_stem(const float* x /*[B,H,W]*/, const unsigned* mag_max_bits /*nullable*/, const float* w /*[9][C]*/,
                 const float* scale, const float* shift, void* out, int dt, int B, int H, int W, int C, int pool,
                 cudaStream_t s);
@@ -137,11 +139,45 @@ int launch_stem_tc(const float* x, const unsigned* mag_max_bits, const void* apa
 int launch_layernorm(const float* x, const float* g, const float* b, void* out, int dt, int rows, int D,
                      float eps, cudaStream_t s);
 int launch_skip_sample(const void* src, int dt, int B, int Hs, int HsPitch, int Ws, int C, int Hd, int Wd,
-                       void* dst, cudaStream_t s);
+                       void* dst, cudaStream_t s, const int* geo = nullptr, int geo_src_idx = 0, int geo_dst_idx = 0);
 int launch_head(const void* x, int dt, const float* w /*[9][C]*/, int B, int H, int W, int C, float* logits,
                 float* out_tanh, cudaStream_t s);
 int launch_resize(const float* src, int B, int Hs, int Ws, float* dst, int Hd, int Wd, cudaStream_t s);
 int launch_maxpool2(const float* src, float* dst, int B, int H, int W, int C, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// Variable-length batches (hvit_enhance_varlen): clips are zero-padded to the plan's n_samples; every clip is processed
+// exactly as if it were alone (SURVEY.md section 8 f rank 2; reference plumbing: models/attention.py:94-98 key mask,
+// data/dataset.py:297-347 zero-pad collate).  A one-block kernel derives the per-clip geometry table `geo`
+// ([B][GEO_STRIDE] ints, device memory) from the valid sample counts; kernels that take a `geo` pointer use the
+// per-clip sizes when it is non-null and the plan's sizes otherwise.
+// ---------------------------------------------------------------------------------------------
+constexpr int GEO_STRIDE = 32;
+enum {
+  GEO_N = 0,      // valid samples
+  GEO_T = 1,      // STFT frames 1 + n / 128
+  GEO_NTOK = 2,   // tokens Hp * Wp
+  GEO_WP = 3,     // patch-grid width
+  GEO_ENC = 4,    // + i: width of encoder block i's output
+  GEO_CAT = 12    // + i: width of decoder block i's input (concat buffer i)
+};
+struct VarlenCfg {
+  int n_enc, n_dec, patch, Hp;
+  int enc_pool[8];
+  int dec_up[8];
+  int n_min, n_max;  // clamp range of the valid sample counts (n_min: smallest clip that still yields one patch column)
+};
+int launch_varlen_geometry(const int* n_valid, int B, const VarlenCfg& c, int* geo, cudaStream_t s);
+// zero the pixel columns [W_b, Wmax) of an NHWC buffer [B, Hpitch, Wmax, pix_bytes] (rows h < H), W_b = geo[b][geo_idx]
+int launch_zero_cols(void* buf, int B, int H, int Hpitch, int Wmax, int pix_bytes, const int* geo, int geo_idx,
+                     cudaStream_t s);
+// residual stream of a clip from the patch grid: x[b][n] = grid[b][n / Wp_b][n % Wp_b] + pos[n] for n < N_b (the
+// reference's token order and positional rows for THAT clip's width), 0 for N_b <= n < Np
+int launch_tokens_compact(const float* grid, const float* pos, float* x, int B, int Hp, int Wp, int D, const int* geo,
+                          cudaStream_t s);
+// to_feature_map output rows (compact token order) -> channels [0, Cx) of the NHWC concat buffer, zero beyond Wp_b
+int launch_tofm_expand(const void* rows, int dt, void* cat, int B, int Hp, int Wp, int Cx, int Ccat, const int* geo,
+                       cudaStream_t s);
 
 // Kernel launch with programmatic stream serialization (PDL); HVIT_NO_PDL=1 falls back to plain stream order.
 // While an L2 window is set (l2_window_set: the transformer's fp32 residual stream, re-read and updated in place by

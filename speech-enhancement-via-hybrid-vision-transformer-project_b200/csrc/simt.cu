@@ -163,7 +163,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 template <typename T, bool WRITE_O>
 __global__ void __launch_bounds__(256) attn_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out,
                                                         float* __restrict__ probs, int B, int N, int heads, int D,
-                                                        float scale) {
+                                                        float scale, const int* __restrict__ geo) {
   const int lane = threadIdx.x & 31;
   const long long wg = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (wg >= static_cast<long long>(B) * heads * N) return;
@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(256) attn_simt_kernel(const T* __restrict__ qk
   const T* base = qkv + static_cast<long long>(b) * N * ld + h * 64 + 2 * lane;
   const float2 qv = ld2<T>(base + static_cast<long long>(q) * ld);
   float mx = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
-  for (int j = 0; j < N; ++j) {
+  const int Nb = geo != nullptr ? geo[b * GEO_STRIDE + GEO_NTOK] : N;  // variable-length batch: valid key prefix of clip b
+  for (int j = 0; j < Nb; ++j) {
     const float2 kv = ld2<T>(base + static_cast<long long>(j) * ld + D);
     const float s = warp_sum(qv.x * kv.x + qv.y * kv.y) * scale;
     const float mn = fmaxf(mx, s);
@@ -222,14 +223,14 @@ int launch_igemm_f32(const IgemmParams& p, const float* A, int lda, const float*
 }
 
 int launch_attn_f32(const float* qkv, float* out, float* probs, int B, int N, int heads, int D, float scale,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, const int* geo) {
   if (D != heads * 64) {
     set_error("attention: head_dim must be 64 (D=%d heads=%d)", D, heads);
     return -1;
   }
   const long long warps = static_cast<long long>(B) * heads * N;
   attn_simt_kernel<float, true><<<static_cast<unsigned>((warps + 7) / 8), 256, 0, stream>>>(qkv, out, probs, B, N,
-                                                                                            heads, D, scale);
+                                                                                            heads, D, scale, geo);
   return check_launch("attn_f32");
 }
 
@@ -243,10 +244,10 @@ int launch_attn_probs_16(const void* qkv, int f16, float* probs, int B, int N, i
   const unsigned grid = static_cast<unsigned>((warps + 7) / 8);
   if (f16)
     attn_simt_kernel<__half, false><<<grid, 256, 0, stream>>>(reinterpret_cast<const __half*>(qkv), nullptr, probs, B,
-                                                              N, heads, D, scale);
+                                                              N, heads, D, scale, nullptr);
   else
     attn_simt_kernel<bf16, false><<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(qkv), nullptr, probs, B, N,
-                                                            heads, D, scale);
+                                                            heads, D, scale, nullptr);
   return check_launch("attn_probs_16");
 }
 

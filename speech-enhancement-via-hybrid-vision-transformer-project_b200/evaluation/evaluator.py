@@ -2,8 +2,8 @@
 
 ``enhance_audio`` is the same data flow as ``AudioEnhancer.enhance`` (the reference duplicates that code,
 evaluator.py:54-117) and runs through the same CUDA plan; ``evaluate_dataset`` additionally batches the directory:
-all noisy files are enhanced first through the length-bucketed ``enhance_files`` machinery (in memory), then scored
-on the host.  PCM WAV decoding replaces librosa.load / soundfile (neither is a dependency here)."""
+all noisy files are enhanced first in mixed-length batches (``AudioEnhancer.enhance_varlen``, in memory), then scored
+(SI-SDR / SNR / segmental SNR / LSD).  PCM WAV decoding replaces librosa.load / soundfile (neither is a dependency here)."""
 from __future__ import annotations
 
 import json
@@ -47,7 +47,7 @@ class Evaluator:
 
     def evaluate_dataset(self, noisy_dir: Path, clean_dir: Path, output_dir: Optional[Path] = None,
                          save_enhanced: bool = False, batch_size: int = 64) -> Dict[str, object]:
-        """reference evaluator.py:157-231 (same result dictionary), with the enhancement batched by clip length."""
+        """reference evaluator.py:157-231 (same result dictionary), with the enhancement run in mixed-length batches."""
         noisy_files = sorted(Path(noisy_dir).glob("*.wav"))
         if len(noisy_files) == 0:
             raise ValueError(f"No .wav files found in {noisy_dir}")
@@ -65,17 +65,14 @@ class Evaluator:
             clean, _ = load_audio(clean_path, sr=self.sample_rate, mono=True)
             n = min(len(noisy), len(clean))
             pairs.append((noisy_path.name, noisy[:n], clean[:n]))
-        # enhance bucket by bucket (equal-length clips share a batch; results equal the per-file path bit for bit)
+        # enhance in mixed-length batches (clips sorted by length; every clip is processed exactly as if alone)
         enhanced = {}
-        buckets = {}
-        for name, noisy, _ in pairs:
-            buckets.setdefault(len(noisy), []).append((name, noisy))
-        for n, items in buckets.items():
-            for s in range(0, len(items), batch_size):
-                chunk = items[s:s + batch_size]
-                out = self._enh.enhance_batch(np.stack([a for _, a in chunk]))
-                for (name, _), y in zip(chunk, out):
-                    enhanced[name] = y
+        order = sorted(range(len(pairs)), key=lambda i: (len(pairs[i][1]), i))
+        for s in range(0, len(order), batch_size):
+            idx = order[s:s + batch_size]
+            outs = self._enh.enhance_varlen([pairs[i][1] for i in idx])
+            for i, y in zip(idx, outs):
+                enhanced[pairs[i][0]] = y
         all_metrics, per_file = [], {}
         for name, noisy, clean in pairs:
             m = self._score(noisy, clean, enhanced[name])

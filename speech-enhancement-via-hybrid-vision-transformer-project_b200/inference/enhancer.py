@@ -206,50 +206,64 @@ class AudioEnhancer:
         save_audio(out, output_path, self.sample_rate)
         print(f"Enhanced audio saved to {output_path}")
 
+    @torch.no_grad()
+    def enhance_varlen(self, clips: Sequence[np.ndarray], normalize: bool = True, pad_multiple: int = 8000) -> list:
+        """Mixed-length batch: clips of different lengths share ONE batch and every result
+        equals ``enhance(clip)`` of that clip alone.  The clips are zero-padded to a common length (rounded up to
+        ``pad_multiple`` samples so that a stream of batches reuses a small set of plans) and ``hvit_enhance_varlen`` is
+        given their true lengths: per-clip frame counts, right-border zero padding in every convolution, per-clip token
+        order / positional rows / key mask in attention, per-clip bilinear resizes and iSTFT length - all on the device
+        (reference plumbing that this completes: attention.py:94-98 mask, dataset.py:297-347 zero-pad collate)."""
+        xs = [np.ascontiguousarray(np.asarray(c, dtype=np.float32)) for c in clips]
+        if not xs:
+            return []
+        if any(x.ndim != 1 for x in xs):
+            raise ValueError("enhance_varlen expects a sequence of 1-D waveforms")
+        lens = [int(x.shape[0]) for x in xs]
+        B = len(xs)
+        n_max = max(1, -(-max(lens) // pad_multiple) * pad_multiple)
+        plan = self.model.plan_for(B, N_FFT // 2 + 1, 1 + n_max // HOP, n_samples=n_max)
+        n_min = plan.lib.hvit_varlen_min_samples(plan.handle)
+        if min(lens) < n_min:
+            raise ValueError(f"clips must have at least {n_min} samples (one 4x4 patch after the encoder), got {min(lens)}")
+        pin_in, pin_out, d_in, d_out = self._staging(B, n_max)
+        buf = pin_in.numpy()
+        buf[...] = 0.0
+        for i, x in enumerate(xs):
+            buf[i, :lens[i]] = x
+        with torch.cuda.device(self._dev):
+            n_valid = torch.tensor(lens, dtype=torch.int32).to(self._dev, non_blocking=False)
+            d_in.copy_(pin_in, non_blocking=True)
+            _lib.check(plan.lib.hvit_enhance_varlen(plan.handle, d_in.data_ptr(), d_out.data_ptr(), n_valid.data_ptr(),
+                                                    1 if normalize else 0, _lib.current_stream_ptr()), "hvit_enhance_varlen")
+            pin_out.copy_(d_out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        out = pin_out.numpy()
+        return [out[i, :lens[i]].copy() for i in range(B)]
+
     def enhance_files(self, input_paths: Sequence, output_paths: Sequence, normalize: bool = True,
-                      batch_size: int = 64) -> None:
+                      batch_size: int = 64, pad_multiple: int = 8000) -> None:
         """Batched file enhancement.  The reference enhances one file at a time; here the
-        decoded clips are bucketed by EXACT sample count (zero-padding a shorter clip would change its convolution
-        borders, so only equal-length clips share a batch - every output is bit-identical to ``enhance_file``), each
-        bucket runs in batches of up to ``batch_size`` through the copy/compute pipeline of :meth:`enhance_pinned`
-        (two rotating pinned buffer sets: the WAV encode of batch i overlaps the kernels of batch i+1), and the results
-        are written as 16-bit PCM like ``enhance_file``."""
+        decoded clips are sorted by length and consecutive runs of up to ``batch_size`` clips share a batch through
+        :meth:`enhance_varlen` (mixed lengths, each clip processed exactly as if alone), so a directory of arbitrary
+        lengths runs in ceil(files / batch_size) launches of the plan instead of one per file - and the number of
+        distinct plans is bounded by the number of distinct (batch size, padded length) pairs.  Results are written as
+        16-bit PCM like ``enhance_file``."""
         from ..utils.audio_processing import load_audio, save_audio
         if len(input_paths) != len(output_paths):
             raise ValueError("input_paths and output_paths must have the same length")
-        buckets = {}
+        items = []
         for i, path in enumerate(input_paths):
             audio, _ = load_audio(path, sr=self.sample_rate)
             if audio.size == 0:
                 raise ValueError(f"{path}: empty audio")
-            buckets.setdefault(audio.shape[0], []).append((i, audio))
-        for n, items in sorted(buckets.items()):
-            pending = []   # [(pinned set key, pinned_out, [file indices])] of submitted, not yet written batches
-            sets = {}      # (batch size, 0 | 1) -> (pinned_in, pinned_out): two rotating sets per batch size
-            turn = 0
-            for start in range(0, len(items), batch_size):
-                chunk = items[start:start + batch_size]
-                B = len(chunk)
-                key = (B, turn & 1)
-                turn += 1
-                if key not in sets:
-                    sets[key] = (torch.empty((B, n), dtype=torch.float32).pin_memory(),
-                                 torch.empty((B, n), dtype=torch.float32).pin_memory())
-                while any(p[0] == key for p in pending):   # this set is still owned by an earlier batch
-                    self._flush_files(pending, 1, output_paths, save_audio)
-                pin_in, pin_out = sets[key]
-                pin_in.numpy()[...] = np.stack([a for _, a in chunk])
-                self.enhance_pinned(pin_in, pin_out, normalize=normalize, synchronize=False)
-                pending.append((key, pin_out, [i for i, _ in chunk]))
-            self._flush_files(pending, len(pending), output_paths, save_audio)
-
-    def _flush_files(self, pending, count, output_paths, save_audio) -> None:
-        self.join(block=True)  # (waits for every outstanding D2H; batches are written in submission order)
-        for _ in range(min(count, len(pending))):
-            _, pin_out, idxs = pending.pop(0)
-            y = pin_out.numpy()
-            for r, i in enumerate(idxs):
-                save_audio(y[r], output_paths[i], self.sample_rate)
+            items.append((audio.shape[0], i, audio))
+        items.sort(key=lambda t: (t[0], t[1]))
+        for start in range(0, len(items), batch_size):
+            chunk = items[start:start + batch_size]
+            outs = self.enhance_varlen([a for _, _, a in chunk], normalize=normalize, pad_multiple=pad_multiple)
+            for (_, i, _), y in zip(chunk, outs):
+                save_audio(y, output_paths[i], self.sample_rate)
 
     def enhance_directory(self, input_dir, output_dir, extension: str = ".wav", normalize: bool = True,
                           batch_size: int = 64) -> None:
