@@ -1382,11 +1382,18 @@ int hvit_attention_16(const void* qkv, void* out, int B, int N, int heads, int f
     std::vector<long long> hst(32 * nc);
     cudaMemcpy(hst.data(), d, sizeof(long long) * 32 * nc, cudaMemcpyDeviceToHost);
     cudaFree(d);
-    double sa[16] = {0};
+    double sa[32] = {0};
     for (int c = 0; c < nc; ++c)
-      for (int k = 0; k < 16; ++k) sa[k] += static_cast<double>(hst[c * 32 + k]) / nc;
-    fprintf(stderr, "[attn prof B=%d N=%d] group A per CTA (%.1f items): wait_s %.0f ld %.0f max %.0f wait_pv/rescale %.0f exp %.0f arrive %.0f finish %.0f total %.0f cycles\n",
-            B, N, sa[7], sa[0], sa[1], sa[2], sa[3], sa[4], sa[5], sa[8], sa[6]);
+      for (int k = 0; k < 32; ++k) sa[k] += static_cast<double>(hst[c * 32 + k]) / nc;
+    for (int w = 0; w < 2; ++w)
+      fprintf(stderr, "[attn prof B=%d N=%d] group %c per CTA (%.1f items): wait_s %.0f ld %.0f max %.0f wait_pv/rescale %.0f exp %.0f arrive %.0f finish %.0f total %.0f cycles\n",
+              B, N, 'A' + w, sa[w * 16 + 7], sa[w * 16 + 0], sa[w * 16 + 1], sa[w * 16 + 2], sa[w * 16 + 3], sa[w * 16 + 4], sa[w * 16 + 5], sa[w * 16 + 8], sa[w * 16 + 6]);
+    // phase of group B relative to group A: start of the exp phase of blocks 1..6 (CTA 0 and the mean over CTAs)
+    fprintf(stderr, "[attn prof] exp-phase start, B minus A, blocks 1..6: CTA0");
+    for (int k = 10; k <= 15; ++k) fprintf(stderr, " %lld", hst[16 + k] - hst[k]);
+    fprintf(stderr, " | A block-to-block:");
+    for (int k = 11; k <= 15; ++k) fprintf(stderr, " %lld", hst[k] - hst[k - 1]);
+    fprintf(stderr, "\n");
     return r;
   }
   return launch_attn_tc(tq, to, f16 ? 1 : 0, B, N, heads, heads * 64, 0.125f, reinterpret_cast<cudaStream_t>(stream));

@@ -136,9 +136,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B swizzle needs 1024-byte aligned tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* q_full = bars;                      // Q tiles of the current item landed
-  uint64_t* q_empty = bars + 1;                 // every S MMA of the current item has completed (Q may be reloaded)
-  uint64_t* k_full = bars + 2;                  // [KV_STAGES]
+  uint64_t* q_full = bars;                      // [2]  Q tile of group w's current item landed
+  uint64_t* q_empty = bars + 2;                 // [2]  every S MMA of group w's current item has completed (Q_w may be reloaded)
+  uint64_t* k_full = bars + 4;                  // [KV_STAGES]
   uint64_t* v_full = k_full + KV_STAGES;        // [KV_STAGES]
   uint64_t* kv_empty = v_full + KV_STAGES;      // [KV_STAGES]
   uint64_t* s_full = kv_empty + KV_STAGES;      // [2]  S_w(block) complete in TMEM
@@ -146,7 +146,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
   uint64_t* p_full = s_free + 2;                // [2]  P_w(block) in shared memory (and O_w rescaled if needed)
   uint64_t* pv_done = p_full + 2;               // [2]  O_w += P_w(block) V(block) complete
   uint64_t* o_free = pv_done + 2;               // [2]  final O_w of an item copied to registers by all 128 rows
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+  uint64_t* lag_bar = o_free + 2;               // group A has finished the row maximum of its first block (see below)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lag_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qpairs = (N + 255) / 256;
@@ -168,8 +169,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
     tma_prefetch_desc(&tmap_out);
   }
   if (warp == 9 && lane == 0) {
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 2);
+    for (int w = 0; w < 2; ++w) {
+      mbar_init(&q_full[w], 1);
+      mbar_init(&q_empty[w], 1);
+    }
+    mbar_init(lag_bar, 128);
     for (int s = 0; s < KV_STAGES; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&v_full[s], 1);
@@ -202,25 +206,58 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
     asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     if (warp == 8) {
       // ------------------------------------------------------------ TMA producer
+      // Three independent load streams over this CTA's items - Q tiles of group A, Q tiles of group B, K/V blocks -
+      // each issued as soon as ITS buffer is free (non-blocking polls): the two softmax groups run half a key block out
+      // of phase on purpose (see the MMA issuers), and a producer that waited for one group's buffer before serving the
+      // other would pull them back into lock-step at every item boundary.
       if (elect_one()) {
-        uint32_t it = 0, kv = 0;  // items / K-V blocks issued so far by this CTA
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-          int b, h, q0;
-          decode(item, b, h, q0);
-          const bool hasB = q0 + 128 < N;
-          const int nkv = (clip_tokens(b) + 127) / 128;
-          mbar_wait(q_empty, (it & 1) ^ 1);
-          mbar_expect_tx(q_full, hasB ? 2 * TILE_BYTES : TILE_BYTES);
-          tma_load_3d(smem + OFF_Q, &tmap_qkv, q_full, h * 64, q0, b);
-          if (hasB) tma_load_3d(smem + OFF_Q + TILE_BYTES, &tmap_qkv, q_full, h * 64, q0 + 128, b);
-          for (int j = 0; j < nkv; ++j, ++kv) {
+        const int stride = gridDim.x;
+        auto has_b = [&](int item) { return (item % qpairs) * 256 + 128 < N; };
+        int itemA = blockIdx.x, itemB = blockIdx.x, itemK = blockIdx.x;
+        while (itemB < n_items && !has_b(itemB)) itemB += stride;
+        uint32_t nA = 0, nB = 0, kv = 0;
+        int jK = 0, nkvK = 0;
+        if (itemK < n_items) nkvK = (clip_tokens(itemK / qpairs / heads) + 127) / 128;
+        while (itemA < n_items || itemB < n_items || itemK < n_items) {
+          bool progress = false;
+          if (itemK < n_items) {
             const int st = kv % KV_STAGES;
-            mbar_wait(&kv_empty[st], ((kv / KV_STAGES) & 1) ^ 1);
-            mbar_expect_tx(&k_full[st], TILE_BYTES);
-            tma_load_3d(smem + OFF_K + st * TILE_BYTES, &tmap_qkv, &k_full[st], D + h * 64, j * 128, b);
-            mbar_expect_tx(&v_full[st], TILE_BYTES);
-            tma_load_3d(smem + OFF_V + st * TILE_BYTES, &tmap_qkv, &v_full[st], 2 * D + h * 64, j * 128, b);
+            if (mbar_try_wait(&kv_empty[st], ((kv / KV_STAGES) & 1) ^ 1)) {
+              int b, h, q0;
+              decode(itemK, b, h, q0);
+              mbar_expect_tx(&k_full[st], TILE_BYTES);
+              tma_load_3d(smem + OFF_K + st * TILE_BYTES, &tmap_qkv, &k_full[st], D + h * 64, jK * 128, b);
+              mbar_expect_tx(&v_full[st], TILE_BYTES);
+              tma_load_3d(smem + OFF_V + st * TILE_BYTES, &tmap_qkv, &v_full[st], 2 * D + h * 64, jK * 128, b);
+              ++kv;
+              if (++jK == nkvK) {
+                jK = 0;
+                itemK += stride;
+                if (itemK < n_items) nkvK = (clip_tokens(itemK / qpairs / heads) + 127) / 128;
+              }
+              progress = true;
+            }
           }
+          if (itemA < n_items && mbar_try_wait(&q_empty[0], (nA & 1) ^ 1)) {
+            int b, h, q0;
+            decode(itemA, b, h, q0);
+            mbar_expect_tx(&q_full[0], TILE_BYTES);
+            tma_load_3d(smem + OFF_Q, &tmap_qkv, &q_full[0], h * 64, q0, b);
+            ++nA;
+            itemA += stride;
+            progress = true;
+          }
+          if (itemB < n_items && mbar_try_wait(&q_empty[1], (nB & 1) ^ 1)) {
+            int b, h, q0;
+            decode(itemB, b, h, q0);
+            mbar_expect_tx(&q_full[1], TILE_BYTES);
+            tma_load_3d(smem + OFF_Q + TILE_BYTES, &tmap_qkv, &q_full[1], h * 64, q0 + 128, b);
+            ++nB;
+            itemB += stride;
+            while (itemB < n_items && !has_b(itemB)) itemB += stride;
+            progress = true;
+          }
+          if (!progress) __nanosleep(128);  // (a tight poll would take issue slots from the softmax warps on this scheduler)
         }
       }
     } else if (warp == 9 || warp == 10) {
@@ -252,30 +289,36 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
           int b, h, q0;
           decode(item, b, h, q0);
           const int nkv = (clip_tokens(b) + 127) / 128;
-          if (w == 1 && !(q0 + 128 < N)) {  // no second query tile: only keep the shared barriers' counts
+          if (w == 1 && !(q0 + 128 < N)) {  // no second query tile: only keep the shared K/V barriers' counts
             // (each arrival waits for the matching "full" phase first, so it can never land in an earlier phase)
-            mbar_wait(q_full, it & 1);
-            mbar_arrive(q_empty);
             for (int j = 0; j < nkv; ++j, ++kv) {
               mbar_wait(&k_full[kv % KV_STAGES], (kv / KV_STAGES) & 1);
               mbar_arrive(&kv_empty[kv % KV_STAGES]);
             }
             continue;
           }
-          mbar_wait(q_full, it & 1);
+          mbar_wait(&q_full[w], itw & 1);
           if (blk > 0) {  // the group's last score block of its previous item has left TMEM
             mbar_wait(&s_free[w], (blk - 1) & 1);
             tc_fence_after();
+          } else if (w == 1) {
+            // De-phasing: group B's first S is issued only when group A has finished the row maximum of ITS first block
+            // and enters its exp phase.  From then on B runs about half a key block behind A (nothing re-aligns them:
+            // separate Q buffers / barriers, the K/V ring absorbs the skew), so one group's MUFU-bound exp phase overlaps
+            // the other's TMEM loads / row maximum / barrier waits instead of both hitting the MUFU unit together and
+            // both leaving it idle afterwards (measured before: 2 230-cycle exp phases in lock-step, 4 440 cycles per key
+            // block against a 2 048-cycle MUFU floor).
+            mbar_wait(lag_bar, 0);
           }
           issue_s(kv);
-          if (nkv == 1) umma_commit(q_empty);
+          if (nkv == 1) umma_commit(&q_empty[w]);
           for (int j = 0; j < nkv; ++j, ++kv) {
             const int st = kv % KV_STAGES;
             if (j + 1 < nkv) {  // S_w(j+1) as soon as the softmax group has S_w(j) in registers
               mbar_wait(&s_free[w], (blk + j) & 1);
               tc_fence_after();
               issue_s(kv + 1);
-              if (j + 2 == nkv) umma_commit(q_empty);  // last S MMA of this item issued
+              if (j + 2 == nkv) umma_commit(&q_empty[w]);  // last S MMA of this item issued
             }
             mbar_wait(&v_full[st], (kv / KV_STAGES) & 1);
             mbar_wait(&p_full[w], (blk + j) & 1);
@@ -365,6 +408,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
         const float mnew =
             fmaxf(max3(mr[0], mr[1], mr[2]), max3(max3(mr[3], mr[4], mr[5]), mr[6], mr[7])) * scale_log2;
         const long long c3 = tick();
+        if (w == 0 && blk == 0) mbar_arrive(lag_bar);  // group B may start (half a key block behind, see the MMA issuers)
         if (j == 0) {
           m_used = mnew;
         } else {
@@ -388,6 +432,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
           }
         }
         const long long c4 = tick();
+        if (PROF && prof != nullptr && row == 0 && blk >= 1 && blk <= 6) prof[blockIdx.x * 32 + w * 16 + 9 + blk] = c4;
         l_run += exp_pack_row(s, scale_log2, m_used + ebias, emul, p_row, sw);
         const long long c5 = tick();
         fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor-core async proxy

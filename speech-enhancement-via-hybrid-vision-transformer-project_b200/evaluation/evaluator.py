@@ -79,7 +79,7 @@ class Evaluator:
             per_file[name] = m
             all_metrics.append(m)
             if save_enhanced and output_dir:
-                save_audio(enhanced[name], output_dir / name, self.sample_rate)
+                save_audio(output_dir / name, enhanced[name], self.sample_rate)
         average = {}
         if all_metrics:
             for k in all_metrics[0].keys():

@@ -203,7 +203,7 @@ class AudioEnhancer:
         from ..utils.audio_processing import load_audio, save_audio
         audio, _ = load_audio(input_path, sr=self.sample_rate)
         out = self.enhance(audio, normalize=normalize)
-        save_audio(out, output_path, self.sample_rate)
+        save_audio(output_path, out, self.sample_rate)
         print(f"Enhanced audio saved to {output_path}")
 
     @torch.no_grad()
@@ -263,7 +263,7 @@ class AudioEnhancer:
             chunk = items[start:start + batch_size]
             outs = self.enhance_varlen([a for _, _, a in chunk], normalize=normalize, pad_multiple=pad_multiple)
             for (_, i, _), y in zip(chunk, outs):
-                save_audio(y, output_paths[i], self.sample_rate)
+                save_audio(output_paths[i], y, self.sample_rate)
 
     def enhance_directory(self, input_dir, output_dir, extension: str = ".wav", normalize: bool = True,
                           batch_size: int = 64) -> None:

@@ -1,12 +1,13 @@
 """STFT front-end wrappers with the reference's signatures (reference utils/audio_processing.py:67-193), backed by
 the CUDA STFT / iSTFT kernels (hvit_stft / hvit_istft in include/hvit.h).  numpy in, numpy out, float32/complex64.
 
-Also a dependency-free PCM WAV reader/writer standing in for librosa.load / soundfile.write
-(reference audio_processing.py:15-64), which are not installed in this image.
+Also ``load_audio`` / ``save_audio`` with the reference's signatures (reference audio_processing.py:15-64) on a
+dependency-free RIFF/WAVE reader / writer (PCM 8/16/24/32-bit and IEEE float) standing in for librosa.load /
+soundfile.write, which are not installed in this image.
 """
 from __future__ import annotations
 
-import wave as _wave
+import struct
 from pathlib import Path
 from typing import Optional, Tuple
 
@@ -74,33 +75,124 @@ def reconstruct_from_magnitude_phase(magnitude: np.ndarray, phase: np.ndarray) -
     return magnitude * np.exp(1j * phase)
 
 
-def load_audio(file_path, sr: int = 16000, mono: bool = True) -> Tuple[np.ndarray, int]:
-    """PCM WAV -> float32 mono in [-1, 1]; linear resampling when the file rate differs."""
-    with _wave.open(str(file_path), "rb") as f:
-        ch, width, rate, frames = f.getnchannels(), f.getsampwidth(), f.getframerate(), f.getnframes()
-        raw = f.readframes(frames)
-    if width == 2:
-        x = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
-    elif width == 4:
-        x = np.frombuffer(raw, dtype="<i4").astype(np.float32) / 2147483648.0
-    elif width == 1:
-        x = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
+def _read_wav(path) -> Tuple[np.ndarray, int]:
+    """RIFF/WAVE -> (float32 [frames, channels] in [-1, 1), sample rate).  Integer PCM of 8 / 16 / 24 / 32 bits is scaled
+    by 1 / 2^(bits-1) and IEEE float (32 / 64 bits) is taken as is - the conversions libsndfile (behind librosa.load /
+    soundfile) applies; WAVE_FORMAT_EXTENSIBLE is resolved through its sub-format.  (Python's ``wave`` module rejects
+    float files, hence the hand-written chunk walk.)"""
+    with open(path, "rb") as f:
+        data = f.read()
+    if len(data) < 12 or data[:4] != b"RIFF" or data[8:12] != b"WAVE":
+        raise ValueError(f"{path}: not a RIFF/WAVE file")
+    pos, fmt, raw = 12, None, None
+    while pos + 8 <= len(data):
+        cid, size = data[pos:pos + 4], struct.unpack("<I", data[pos + 4:pos + 8])[0]
+        body = data[pos + 8:pos + 8 + size]
+        if cid == b"fmt ":
+            tag, ch, rate, _, _, bits = struct.unpack("<HHIIHH", body[:16])
+            if tag == 0xFFFE and len(body) >= 26:      # WAVE_FORMAT_EXTENSIBLE: the real tag leads the sub-format GUID
+                tag = struct.unpack("<H", body[24:26])[0]
+            fmt = (tag, ch, rate, bits)
+        elif cid == b"data":
+            raw = body
+        pos += 8 + size + (size & 1)
+    if fmt is None or raw is None:
+        raise ValueError(f"{path}: missing fmt / data chunk")
+    tag, ch, rate, bits = fmt
+    if tag == 1:
+        if bits == 8:
+            x = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
+        elif bits == 16:
+            x = np.frombuffer(raw[:len(raw) // 2 * 2], dtype="<i2").astype(np.float32) / 32768.0
+        elif bits == 24:
+            b = np.frombuffer(raw[:len(raw) // 3 * 3], dtype=np.uint8).reshape(-1, 3).astype(np.int32)
+            v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+            x = (v - ((v & 0x800000) << 1)).astype(np.float32) / 8388608.0
+        elif bits == 32:
+            x = (np.frombuffer(raw[:len(raw) // 4 * 4], dtype="<i4").astype(np.float64) / 2147483648.0).astype(np.float32)
+        else:
+            raise ValueError(f"{path}: unsupported PCM width {bits}")
+    elif tag == 3:
+        if bits == 32:
+            x = np.frombuffer(raw[:len(raw) // 4 * 4], dtype="<f4").astype(np.float32)
+        elif bits == 64:
+            x = np.frombuffer(raw[:len(raw) // 8 * 8], dtype="<f8").astype(np.float32)
+        else:
+            raise ValueError(f"{path}: unsupported float width {bits}")
     else:
-        raise ValueError(f"unsupported WAV sample width {width}")
-    x = x.reshape(-1, ch)
-    x = x.mean(axis=1) if mono else x.T
-    if rate != sr:
-        n_out = int(round(x.shape[-1] * sr / rate))
-        x = np.interp(np.arange(n_out) * (rate / sr), np.arange(x.shape[-1]), x).astype(np.float32)
-    return x.astype(np.float32), sr
+        raise ValueError(f"{path}: unsupported WAVE format tag {tag} (PCM and IEEE float are supported)")
+    return x[:len(x) // ch * ch].reshape(-1, ch), rate
 
 
-def save_audio(audio: np.ndarray, file_path, sr: int = 16000, subtype: str = "PCM_16") -> None:
+def load_audio(file_path, sr: int = 16000, mono: bool = True, offset: float = 0.0, duration: Optional[float] = None,
+               res_type: Optional[str] = None) -> Tuple[np.ndarray, int]:
+    """reference audio_processing.py:15-43 (= ``librosa.load(file_path, sr=sr, mono=mono, offset=..., duration=...)``):
+    float32 waveform (mono: channel mean) and the sample rate.  WAV only (PCM 8/16/24/32-bit, IEEE float 32/64-bit).
+
+    Resampling: librosa's default resampler (``soxr_hq``) is a third-party library that is not available here, and a
+    different resampler would silently change the audio.  A file whose rate differs from ``sr`` therefore raises unless
+    ``res_type`` names the resampler to use: ``"polyphase"`` = ``scipy.signal.resample_poly`` with the gcd-reduced ratio
+    (exactly librosa's ``res_type="polyphase"``), ``"linear"`` = linear interpolation."""
+    x, rate = _read_wav(file_path)
+    if offset:
+        x = x[int(round(offset * rate)):]
+    if duration is not None:
+        x = x[:int(round(duration * rate))]
+    x = x.mean(axis=1) if mono else np.ascontiguousarray(x.T)
+    if sr is not None and rate != sr:
+        if res_type == "polyphase":
+            from math import gcd
+            from scipy.signal import resample_poly
+            g = gcd(int(sr), int(rate))
+            x = resample_poly(x, int(sr) // g, int(rate) // g, axis=-1)
+        elif res_type == "linear":
+            n_out = int(np.ceil(x.shape[-1] * sr / rate))
+            t = np.arange(n_out) * (rate / sr)
+            x = np.interp(t, np.arange(x.shape[-1]), x) if x.ndim == 1 else \
+                np.stack([np.interp(t, np.arange(x.shape[-1]), c) for c in x])
+        else:
+            raise NotImplementedError(
+                f"{file_path}: sample rate {rate} != {sr}. librosa's default resampler (soxr_hq) is not available; pass "
+                "res_type='polyphase' (scipy.signal.resample_poly, librosa's 'polyphase') or 'linear', or resample offline")
+        rate = sr
+    return np.ascontiguousarray(x, dtype=np.float32), rate
+
+
+_SUBTYPES = {"PCM_16": (1, 16), "PCM_24": (1, 24), "PCM_32": (1, 32), "FLOAT": (3, 32)}
+
+
+def save_audio(file_path, audio: np.ndarray, sr: int = 16000, subtype: str = "PCM_16") -> None:
+    """reference audio_processing.py:46-64 (= ``soundfile.write(file_path, audio, sr, subtype=subtype)``): mono [n] or
+    [n, channels] float audio -> WAV.  Integer subtypes are scaled by 2^(bits-1) - 1 and rounded to nearest like
+    libsndfile's float -> int conversion; samples outside [-1, 1] are clipped (libsndfile would wrap them)."""
+    if subtype not in _SUBTYPES:
+        raise ValueError(f"unsupported subtype {subtype!r}; supported: {sorted(_SUBTYPES)}")
     path = Path(file_path)
     path.parent.mkdir(parents=True, exist_ok=True)
-    pcm = (np.clip(np.asarray(audio, dtype=np.float32), -1.0, 1.0) * 32767.0).astype("<i2")
-    with _wave.open(str(path), "wb") as f:
-        f.setnchannels(1)
-        f.setsampwidth(2)
-        f.setframerate(sr)
-        f.writeframes(pcm.tobytes())
+    x = np.asarray(audio)
+    if x.ndim == 1:
+        x = x[:, None]
+    ch = x.shape[1]
+    tag, bits = _SUBTYPES[subtype]
+    if tag == 3:
+        payload = np.ascontiguousarray(x, dtype="<f4").tobytes()
+    else:
+        full = float(2 ** (bits - 1) - 1)
+        q = np.rint(np.clip(x.astype(np.float64), -1.0, 1.0) * full)
+        if bits == 16:
+            payload = q.astype("<i2").tobytes()
+        elif bits == 32:
+            payload = q.astype("<i4").tobytes()
+        else:
+            v = q.astype(np.int32).reshape(-1)
+            b = np.empty((v.size, 3), dtype=np.uint8)
+            b[:, 0], b[:, 1], b[:, 2] = v & 0xFF, (v >> 8) & 0xFF, (v >> 16) & 0xFF
+            payload = b.tobytes()
+    block = ch * bits // 8
+    fmt = struct.pack("<HHIIHH", tag, ch, int(sr), int(sr) * block, block, bits)
+    chunks = b"fmt " + struct.pack("<I", len(fmt)) + fmt
+    if tag == 3:
+        chunks += b"fact" + struct.pack("<II", 4, x.shape[0])
+    chunks += b"data" + struct.pack("<I", len(payload)) + payload + (b"\x00" if len(payload) & 1 else b"")
+    with open(path, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", 4 + len(chunks)) + b"WAVE" + chunks)

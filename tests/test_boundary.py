@@ -158,11 +158,37 @@ def test_weight_packing_cpu(oracle):
 
 
 def test_wav_io_roundtrip(tmp_path):
+    """load_audio / save_audio keep the reference's signatures (utils/audio_processing.py:15-64) and cover the subtypes
+    soundfile would write: PCM_16 (default), PCM_24, PCM_32, FLOAT; stereo -> mono is the channel mean; a sample-rate
+    mismatch raises unless a resampler is named (librosa's default soxr_hq is unavailable)."""
+    import wave
     from hvit_b200.utils.audio_processing import load_audio, save_audio
     x = (0.5 * np.sin(np.arange(8000) * 0.05)).astype(np.float32)
-    save_audio(x, tmp_path / "a.wav", 16000)
-    y, sr = load_audio(tmp_path / "a.wav", sr=16000)
-    assert sr == 16000 and y.shape == x.shape and np.abs(x - y).max() < 1e-4
+    for subtype, tol in (("PCM_16", 2.0 ** -15), ("PCM_24", 2.0 ** -23), ("PCM_32", 1e-7), ("FLOAT", 0.0)):
+        save_audio(tmp_path / f"{subtype}.wav", x, 16000, subtype=subtype)
+        y, sr = load_audio(tmp_path / f"{subtype}.wav", sr=16000)
+        assert sr == 16000 and y.shape == x.shape and y.dtype == np.float32
+        assert np.abs(x - y).max() <= tol, subtype
+    with wave.open(str(tmp_path / "PCM_16.wav"), "rb") as f:       # readable by an independent parser, 16-bit mono
+        assert (f.getnchannels(), f.getsampwidth(), f.getframerate(), f.getnframes()) == (1, 2, 16000, 8000)
+        pcm = np.frombuffer(f.readframes(8000), dtype="<i2")
+    assert np.array_equal(pcm, np.rint(x.astype(np.float64) * 32767.0).astype(np.int16))   # libsndfile's float -> short
+    st = np.stack([x, -0.5 * x], axis=1)
+    save_audio(tmp_path / "st.wav", st, 16000, subtype="FLOAT")
+    m, _ = load_audio(tmp_path / "st.wav", sr=16000, mono=True)
+    assert np.allclose(m, 0.25 * x, atol=1e-7)
+    s2, _ = load_audio(tmp_path / "st.wav", sr=16000, mono=False)
+    assert s2.shape == (2, 8000)
+    seg, _ = load_audio(tmp_path / "FLOAT.wav", sr=16000, offset=0.1, duration=0.2)
+    assert np.array_equal(seg, x[1600:4800])
+    save_audio(tmp_path / "r8k.wav", x, 8000, subtype="FLOAT")
+    with pytest.raises(NotImplementedError):
+        load_audio(tmp_path / "r8k.wav", sr=16000)
+    up, sr = load_audio(tmp_path / "r8k.wav", sr=16000, res_type="polyphase")
+    from scipy.signal import resample_poly
+    assert sr == 16000 and np.allclose(up, resample_poly(x, 2, 1).astype(np.float32), atol=1e-6)
+    with pytest.raises(ValueError):
+        save_audio(tmp_path / "bad.wav", x, 16000, subtype="ULAW")
 
 
 def test_shard_range():

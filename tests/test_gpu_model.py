@@ -335,7 +335,7 @@ def test_enhance_directory_batched_equals_per_file(oracle, tmp_path):
     src, dst_b, dst_s = tmp_path / "in", tmp_path / "batched", tmp_path / "single"
     lengths = [8000, 8000, 12345, 8000, 16000, 12345, 8000, 8000]
     for i, n in enumerate(lengths):
-        save_audio(0.5 * oracle.synth_clip(seed=300 + i, n_samples=n)[1], src / f"clip{i:02d}.wav", 16000)
+        save_audio(src / f"clip{i:02d}.wav", 0.5 * oracle.synth_clip(seed=300 + i, n_samples=n)[1], 16000)
     enh.enhance_directory(src, dst_b, batch_size=3)
     dst_s.mkdir()
     for f in sorted(src.glob("*.wav")):
@@ -349,7 +349,7 @@ def test_enhance_directory_batched_equals_per_file(oracle, tmp_path):
         # oracle arm: the CPU restatement of the reference on the same decoded PCM, quantised to 16 bits like the file
         x, _ = load_audio(src / nm)
         ref = oracle.enhance(sd, x, cfg)
-        ref_pcm = (np.clip(ref, -1.0, 1.0) * 32767.0).astype("<i2").astype(np.float32) / 32768.0
+        ref_pcm = np.rint(np.clip(ref, -1.0, 1.0) * 32767.0).astype(np.float32) / 32768.0
         assert np.abs(a - ref_pcm).max() <= TOL["fp16"] * 2 * max(np.abs(ref).max(), 1e-6) + 2.0 / 32768.0, nm
 
 
@@ -364,8 +364,8 @@ def test_evaluator_dataset(oracle, tmp_path):
     noisy_dir, clean_dir = tmp_path / "noisy", tmp_path / "clean"
     for i, n in enumerate([8000, 9000, 8000]):
         clean, noisy = oracle.synth_clip(seed=400 + i, n_samples=n)
-        save_audio(0.5 * clean, clean_dir / f"u{i}.wav", 16000)
-        save_audio(0.5 * noisy, noisy_dir / f"u{i}.wav", 16000)
+        save_audio(clean_dir / f"u{i}.wav", 0.5 * clean, 16000)
+        save_audio(noisy_dir / f"u{i}.wav", 0.5 * noisy, 16000)
     res = ev.evaluate_dataset(noisy_dir, clean_dir, output_dir=tmp_path / "enh", save_enhanced=True)
     assert res["num_files"] == 3 and (tmp_path / "enh" / "u1.wav").exists()
     single = ev.evaluate_pair(noisy_dir / "u1.wav", clean_dir / "u1.wav")
@@ -439,3 +439,39 @@ def test_varlen_equal_lengths_equals_fixed_batch(oracle):
         assert oracle.max_rel_err(yv[i], yb[i]) <= 1e-6, i
     with pytest.raises(ValueError):
         enh.enhance_varlen([clips[0], clips[1][:1000]])     # shorter than one patch column
+
+
+# ------------------------------------------------------------------------------------------------ C host (no Python)
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_c_host_enhances_golden_clip(oracle, golden, precision, tmp_path):
+    """tests/host_c/enhance_host.c links libhvit_sm100.so and uses ONLY the C ABI (hvit_pack_weights -> hvit_plan_create ->
+    hvit_enhance) plus the CUDA runtime: the library is self-sufficient for a C/C++ host.  Checked against the waveform
+    the reference's own AudioEnhancer produced (tests/golden, tiny_0p5s)."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(__file__), "host_c", "enhance_host")
+    assert os.path.exists(exe), "run __graft_entry__.build() first (it compiles tests/host_c/enhance_host.c)"
+    arrays, meta = golden
+    m = meta["tiny_0p5s"]
+    cfg = oracle.full_cfg(m["cfg"])
+    sd = oracle.make_state_dict(cfg, seed=m["weight_seed"])
+    _, noisy = oracle.synth_clip(seconds=m["seconds"], seed=m["clip_seed"])
+    ref_y = arrays["tiny_0p5s/waveform"]
+    prec = {"fp32": 0, "bf16": 1, "fp16": 2}[precision]
+    enc, dec = cfg["encoder_channels"], cfg["decoder_channels"]
+    hdr = [len(enc)] + list(enc) + list(cfg["encoder_pool_sizes"]) + \
+          [cfg["embed_dim"], cfg["num_heads"], cfg["num_layers"], int(cfg["embed_dim"] * cfg["mlp_ratio"]), cfg["patch_size"]] + \
+          [len(dec)] + list(dec) + list(cfg["decoder_upsample_factors"]) + [1, prec, 10000, len(noisy)]
+    blob = tmp_path / "case.bin"
+    with open(blob, "wb") as f:
+        f.write(np.asarray([len(hdr)] + hdr, dtype=np.int32).tobytes())
+        for key, shape, kind in oracle.state_dict_spec(cfg):      # registration order == the order enhance_host.c reads
+            if kind != "count":
+                f.write(sd[key].contiguous().numpy().astype(np.float32).tobytes())
+        f.write(noisy.astype(np.float32).tobytes())
+        f.write(ref_y.astype(np.float32).tobytes())
+    out = subprocess.run([exe, str(blob)], capture_output=True, text=True, timeout=300)
+    print("\n[c host/%s] %s %s" % (precision, out.stdout.strip(), out.stderr.strip()))
+    assert out.returncode == 0, out.stderr
+    err = float(out.stdout.split("max_rel=")[1])
+    assert err <= TOL[precision] * 2
