@@ -190,6 +190,15 @@ int hvit_enhance_varlen(hvit_plan* plan, const float* wave_in_dev, float* wave_o
                         int normalize, void* stream);
 int hvit_varlen_min_samples(const hvit_plan* plan);
 
+/* Objective metrics of the evaluation caller on the device (evaluation/metrics.py:100-296, used by
+ * evaluation/evaluator.py:119-231): SI-SDR, SNR, segmental SNR (512 / 256 frames, clipped to [-10, 35] dB) and
+ * log-spectral distance (|STFT| 512 / 128) between clean_dev and enhanced_dev, both fp32 [B, n_samples] on the device
+ * (n_valid_dev: nullable int32 [B] true lengths of zero-padded clips).  out_dev: [B][4] doubles
+ * {sisdr, snr, segsnr, lsd}.  scratch_dev: hvit_metrics_scratch_bytes(B, n_samples) bytes, 256-byte aligned. */
+size_t hvit_metrics_scratch_bytes(int B, int n_samples);
+int hvit_metrics(const float* clean_dev, const float* enhanced_dev, int B, int n_samples, const int* n_valid_dev,
+                 void* scratch_dev, size_t scratch_bytes, double* out_dev, void* stream);
+
 /* Introspection for tests: byte offset (into the workspace), and dims of a named internal buffer.
  * Names: "enc<i>", "tokens", "ln", "qkv", "attn", "mlp", "cat<i>", "logits" (debug mode), "tanh", and for enhance
  * plans "model_out" (debug mode), "mag", "max_val", "mag_max".  dims receives up to 4 ints; returns the rank or

@@ -80,6 +80,8 @@ SYMBOLS = {
     "hvit_enhance": (_I, [_VP, _VP, _VP, _I, _VP]),
     "hvit_enhance_varlen": (_I, [_VP, _VP, _VP, _VP, _I, _VP]),
     "hvit_varlen_min_samples": (_I, [_VP]),
+    "hvit_metrics_scratch_bytes": (_SZ, [_I, _I]),
+    "hvit_metrics": (_I, [_VP, _VP, _I, _I, _VP, _VP, _SZ, _VP, _VP]),
     "hvit_plan_buffer": (_I, [_VP, C.c_char_p, C.POINTER(_SZ), C.POINTER(_I * 4), C.POINTER(_I)]),
     "hvit_plan_launch_count": (_I, [_VP, _I]),
     "hvit_plan_tokens": (_I, [_VP, C.POINTER(_I), C.POINTER(_I)]),

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB = os.path.join(HERE, "libhvit_sm100.so")
-SOURCES = ["api.cu", "pack.cu", "gemm_tc2.cu", "attn_tc.cu", "stem_tc.cu", "simt.cu", "glue.cu"]
+SOURCES = ["api.cu", "pack.cu", "metrics.cu", "gemm_tc2.cu", "attn_tc.cu", "stem_tc.cu", "simt.cu", "glue.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--use_fast_math=false" if False else "-Xptxas", "-v" if os.environ.get("HVIT_PTXAS_V") else "-O3"]
 

@@ -15,7 +15,7 @@ import torch.nn as nn
 
 from ..inference.enhancer import AudioEnhancer
 from ..utils.audio_processing import load_audio, save_audio
-from .metrics import compute_all_metrics
+from .metrics import compute_metrics_device, compute_pesq, compute_stoi
 
 
 class Evaluator:
@@ -32,10 +32,36 @@ class Evaluator:
         """reference evaluator.py:54-117"""
         return self._enh.enhance(noisy_audio, normalize=True)
 
-    def _score(self, noisy_audio: np.ndarray, clean_audio: np.ndarray, enhanced_audio: np.ndarray) -> Dict[str, float]:
-        n = min(len(noisy_audio), len(clean_audio))
-        return compute_all_metrics(clean=clean_audio[:n], enhanced=enhanced_audio[:n], noisy=noisy_audio[:n],
-                                   sr=self.sample_rate)
+    def _score_batch(self, noisy, clean, enhanced_host, enhanced_dev, lens):
+        """Metric dictionaries (the reference's keys, metrics.py:299-349) for one enhanced batch.  SI-SDR / SNR / segmental
+        SNR / LSD are reduced ON THE DEVICE from the enhancer's output buffer (``hvit_metrics``); only the clean and noisy
+        references are uploaded, and 4 doubles per clip come back.  PESQ / STOI are third-party host packages in the
+        reference too (0.0 when not installed)."""
+        import torch
+        dev = enhanced_dev.device
+        B, n_max = enhanced_dev.shape
+
+        def padded(xs):
+            buf = np.zeros((B, n_max), dtype=np.float32)
+            for i, x in enumerate(xs):
+                buf[i, :lens[i]] = x[:lens[i]]
+            return torch.from_numpy(buf).to(dev)
+
+        d_clean = padded(clean)
+        enh = compute_metrics_device(d_clean, enhanced_dev, lens)
+        noi = compute_metrics_device(d_clean, padded(noisy), lens)
+        out = []
+        for i in range(B):
+            c, e, x = clean[i][:lens[i]], enhanced_host[i][:lens[i]], noisy[i][:lens[i]]
+            m = {"pesq": compute_pesq(c, e, self.sample_rate), "stoi": compute_stoi(c, e, self.sample_rate),
+                 "sisdr": float(enh["sisdr"][i]), "snr": float(enh["snr"][i]), "segsnr": float(enh["segsnr"][i]),
+                 "lsd": float(enh["lsd"][i])}
+            m["pesq_improvement"] = m["pesq"] - compute_pesq(c, x, self.sample_rate)
+            m["stoi_improvement"] = m["stoi"] - compute_stoi(c, x, self.sample_rate)
+            m["sisdr_improvement"] = m["sisdr"] - float(noi["sisdr"][i])
+            m["snr_improvement"] = m["snr"] - float(noi["snr"][i])
+            out.append(m)
+        return out
 
     def evaluate_pair(self, noisy_path: Path, clean_path: Path) -> Dict[str, float]:
         """reference evaluator.py:119-155"""
@@ -43,11 +69,13 @@ class Evaluator:
         clean, _ = load_audio(clean_path, sr=self.sample_rate, mono=True)
         n = min(len(noisy), len(clean))
         noisy, clean = noisy[:n], clean[:n]
-        return self._score(noisy, clean, self.enhance_audio(noisy))
+        host, dev, lens = self._enh.enhance_varlen([noisy], return_device=True)
+        return self._score_batch([noisy], [clean], host, dev, lens)[0]
 
     def evaluate_dataset(self, noisy_dir: Path, clean_dir: Path, output_dir: Optional[Path] = None,
                          save_enhanced: bool = False, batch_size: int = 64) -> Dict[str, object]:
-        """reference evaluator.py:157-231 (same result dictionary), with the enhancement run in mixed-length batches."""
+        """reference evaluator.py:157-231 (same result dictionary), with the enhancement run in mixed-length batches and
+        the signal metrics computed on the device from the enhancer's output buffer."""
         noisy_files = sorted(Path(noisy_dir).glob("*.wav"))
         if len(noisy_files) == 0:
             raise ValueError(f"No .wav files found in {noisy_dir}")
@@ -65,21 +93,19 @@ class Evaluator:
             clean, _ = load_audio(clean_path, sr=self.sample_rate, mono=True)
             n = min(len(noisy), len(clean))
             pairs.append((noisy_path.name, noisy[:n], clean[:n]))
-        # enhance in mixed-length batches (clips sorted by length; every clip is processed exactly as if alone)
-        enhanced = {}
+        # mixed-length batches (clips sorted by length; every clip is processed exactly as if alone)
+        per_file = {}
         order = sorted(range(len(pairs)), key=lambda i: (len(pairs[i][1]), i))
         for s in range(0, len(order), batch_size):
             idx = order[s:s + batch_size]
-            outs = self._enh.enhance_varlen([pairs[i][1] for i in idx])
-            for i, y in zip(idx, outs):
-                enhanced[pairs[i][0]] = y
-        all_metrics, per_file = [], {}
-        for name, noisy, clean in pairs:
-            m = self._score(noisy, clean, enhanced[name])
-            per_file[name] = m
-            all_metrics.append(m)
-            if save_enhanced and output_dir:
-                save_audio(output_dir / name, enhanced[name], self.sample_rate)
+            noisy_b, clean_b = [pairs[i][1] for i in idx], [pairs[i][2] for i in idx]
+            host, dev, lens = self._enh.enhance_varlen(noisy_b, return_device=True)
+            for i, m, y in zip(idx, self._score_batch(noisy_b, clean_b, host, dev, lens), host):
+                per_file[pairs[i][0]] = m
+                if save_enhanced and output_dir:
+                    save_audio(output_dir / pairs[i][0], y, self.sample_rate)
+        all_metrics = [per_file[name] for name, _, _ in pairs]
+        per_file = {name: per_file[name] for name, _, _ in pairs}
         average = {}
         if all_metrics:
             for k in all_metrics[0].keys():

@@ -94,6 +94,33 @@ def compute_lsd(clean: np.ndarray, enhanced: np.ndarray, sr: int = 16000, n_fft:
     return float(np.mean(np.sqrt(np.mean((np.log(a + eps) - np.log(b + eps)) ** 2, axis=0))))
 
 
+def compute_metrics_device(clean, enhanced, lengths=None) -> Dict[str, np.ndarray]:
+    """SI-SDR / SNR / segmental SNR / LSD of a whole batch ON THE GPU (``hvit_metrics``, csrc/metrics.cu): ``clean`` and
+    ``enhanced`` are float32 CUDA tensors [B, n] (zero-padded to a common length, ``lengths`` = true sample counts), so
+    scoring the enhancer's device output needs no device -> host -> numpy trip.  Returns per-clip numpy float64 arrays
+    under the reference's keys.  Same arithmetic as the host functions above (which stay the reference-pinned checker)."""
+    import ctypes as C
+    import torch
+    from .. import _lib
+    if clean.shape != enhanced.shape or clean.dim() != 2 or not clean.is_cuda or not enhanced.is_cuda:
+        raise ValueError("compute_metrics_device expects two float32 CUDA tensors [B, n] of the same shape")
+    clean, enhanced = clean.contiguous().float(), enhanced.contiguous().float()
+    B, n = clean.shape
+    lib = _lib.load()
+    with torch.cuda.device(clean.device):
+        nbytes = lib.hvit_metrics_scratch_bytes(B, n)
+        scratch = torch.empty(nbytes + 256, dtype=torch.uint8, device=clean.device)
+        off = (-scratch.data_ptr()) % 256
+        out = torch.empty((B, 4), dtype=torch.float64, device=clean.device)
+        nv = None
+        if lengths is not None:
+            nv = torch.as_tensor(list(lengths), dtype=torch.int32).to(clean.device)
+        _lib.check(lib.hvit_metrics(clean.data_ptr(), enhanced.data_ptr(), B, n, _lib.ptr(nv), scratch.data_ptr() + off,
+                                    nbytes, out.data_ptr(), _lib.current_stream_ptr()), "hvit_metrics")
+        res = out.cpu().numpy()
+    return {"sisdr": res[:, 0], "snr": res[:, 1], "segsnr": res[:, 2], "lsd": res[:, 3]}
+
+
 def compute_all_metrics(clean: np.ndarray, enhanced: np.ndarray, noisy: np.ndarray = None, sr: int = 16000) -> Dict[str, float]:
     """reference metrics.py:299-349: same keys (pesq, stoi, sisdr, snr, segsnr, lsd and the *_improvement entries when
     the noisy input is given)."""

@@ -207,7 +207,8 @@ class AudioEnhancer:
         print(f"Enhanced audio saved to {output_path}")
 
     @torch.no_grad()
-    def enhance_varlen(self, clips: Sequence[np.ndarray], normalize: bool = True, pad_multiple: int = 8000) -> list:
+    def enhance_varlen(self, clips: Sequence[np.ndarray], normalize: bool = True, pad_multiple: int = 8000,
+                       return_device: bool = False):
         """Mixed-length batch: clips of different lengths share ONE batch and every result
         equals ``enhance(clip)`` of that clip alone.  The clips are zero-padded to a common length (rounded up to
         ``pad_multiple`` samples so that a stream of batches reuses a small set of plans) and ``hvit_enhance_varlen`` is
@@ -239,7 +240,10 @@ class AudioEnhancer:
             pin_out.copy_(d_out, non_blocking=True)
             torch.cuda.current_stream().synchronize()
         out = pin_out.numpy()
-        return [out[i, :lens[i]].copy() for i in range(B)]
+        host = [out[i, :lens[i]].copy() for i in range(B)]
+        if return_device:   # (+ the padded device batch [B, n_max] - valid until the next call with this shape - and lengths)
+            return host, d_out, lens
+        return host
 
     def enhance_files(self, input_paths: Sequence, output_paths: Sequence, normalize: bool = True,
                       batch_size: int = 64, pad_multiple: int = 8000) -> None:

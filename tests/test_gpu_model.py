@@ -7,6 +7,7 @@ Parity modes: "fp32" (CUDA cores) and "fp16" (the 16-bit tensor-core mode: fp16 
 kernels also run with bf16 operands (``precision="bf16"``), but that mode is RETIRED as a parity mode: its measured
 error (0.6-2.2e-2) is the bf16 rounding floor and does not meet the north star's 1e-2 - it is only smoke-tested here
 (test_bf16_range_mode_is_not_a_parity_mode) and covered per kernel in test_gpu_kernels.py."""
+import os
 import numpy as np
 import pytest
 import torch
@@ -475,3 +476,88 @@ def test_c_host_enhances_golden_clip(oracle, golden, precision, tmp_path):
     assert out.returncode == 0, out.stderr
     err = float(out.stdout.split("max_rel=")[1])
     assert err <= TOL[precision] * 2
+
+
+# ------------------------------------------------------------------------------------------------ CLI, device metrics
+def test_enhance_cli_single_file_and_directory(oracle, tmp_path):
+    """enhance.py (the reference's CLI, enhance.py:23-169): YAML config dir + checkpoint + WAV in -> WAV out, in both
+    modes; outputs are compared with the CPU oracle on the decoded input."""
+    import subprocess
+    import sys
+    import yaml
+    from hvit_b200.models import HybridViT
+    from hvit_b200.utils.audio_processing import load_audio, save_audio
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = oracle.full_cfg(TINY)
+    sd = oracle.make_state_dict(cfg, seed=21)
+    cdir = tmp_path / "config"
+    cdir.mkdir()
+    model_yaml = {"model": {"encoder": {"channels": cfg["encoder_channels"], "kernel_sizes": [3, 3, 3], "pool_sizes": [2, 2, 1]},
+                            "transformer": {"embed_dim": 128, "num_heads": 2, "num_layers": 2, "mlp_ratio": 4, "patch_size": 4},
+                            "decoder": {"channels": cfg["decoder_channels"], "kernel_sizes": [3, 3, 3, 3],
+                                        "upsample_factors": [1, 2, 2, 1], "use_skip_connections": True}}}
+    (cdir / "model_config.yaml").write_text(yaml.safe_dump(model_yaml))
+    (cdir / "data_config.yaml").write_text(yaml.safe_dump({"audio": {"sample_rate": 16000, "n_fft": 512, "hop_length": 128,
+                                                                     "win_length": 512}}))
+    torch.save({"model_state_dict": sd}, tmp_path / "ckpt.pth")
+    src = tmp_path / "in"
+    lengths = [8000, 12345, 9001]
+    for i, n in enumerate(lengths):
+        save_audio(src / f"c{i}.wav", 0.5 * oracle.synth_clip(seed=900 + i, n_samples=n)[1], 16000, subtype="FLOAT")
+    base = [sys.executable, os.path.join(root, "enhance.py"), "--checkpoint", str(tmp_path / "ckpt.pth"), "--config-dir", str(cdir)]
+    r1 = subprocess.run(base + ["--input", str(src / "c1.wav"), "--output", str(tmp_path / "one.wav")], capture_output=True,
+                        text=True, timeout=600)
+    assert r1.returncode == 0, r1.stderr[-2000:]
+    assert "Enhancement complete!" in r1.stdout
+    r2 = subprocess.run(base + ["--input-dir", str(src), "--output-dir", str(tmp_path / "out"), "--batch-size", "2"],
+                        capture_output=True, text=True, timeout=600)
+    assert r2.returncode == 0, r2.stderr[-2000:]
+    assert "Found 3 audio files to enhance" in r2.stdout and "All files enhanced successfully!" in r2.stdout
+    for i, n in enumerate(lengths):
+        x, _ = load_audio(src / f"c{i}.wav")
+        ref = oracle.enhance(sd, x, cfg)
+        ref_pcm = np.rint(np.clip(ref, -1.0, 1.0) * 32767.0).astype(np.float32) / 32768.0
+        y, _ = load_audio(tmp_path / "out" / f"c{i}.wav")
+        assert y.shape == (n,)
+        assert np.abs(y - ref_pcm).max() <= TOL["fp16"] * 2 * max(np.abs(ref).max(), 1e-6) + 2.0 / 32768.0, i
+    one, _ = load_audio(tmp_path / "one.wav")
+    both, _ = load_audio(tmp_path / "out" / "c1.wav")
+    assert np.array_equal(one, both)           # directory (mixed-length batch) == single-file path, bit for bit
+    bad = subprocess.run(base + ["--input", "a.wav", "--output", "b.wav", "--device", "cpu"], capture_output=True, text=True)
+    assert bad.returncode != 0 and "no CPU path" in bad.stderr
+
+
+def test_device_metrics_match_reference_golden():
+    """hvit_metrics (SI-SDR / SNR / segmental SNR / LSD reduced on the GPU) against the values the REFERENCE's own
+    evaluation/metrics.py produced for the same seeded signals (tests/golden/metrics_v1.json), one clip at a time and as
+    one zero-padded mixed-length batch."""
+    import json
+    from hvit_b200.evaluation.metrics import compute_metrics_device
+    with open(os.path.join(os.path.dirname(__file__), "golden", "metrics_v1.json")) as f:
+        cases = json.load(f)["cases"]
+    rng = np.random.default_rng(123)
+    sigs = []
+    for case in cases:
+        n = case["n"]
+        t = np.arange(n) / 16000.0
+        clean = (0.3 * np.sin(2 * np.pi * 220 * t) * (0.5 + 0.5 * np.sin(2 * np.pi * 2 * t))
+                 + 0.01 * rng.standard_normal(n)).astype(np.float32)
+        noisy = (clean + 0.1 * rng.standard_normal(n)).astype(np.float32)
+        enh = (0.9 * clean + 0.02 * rng.standard_normal(n)).astype(np.float32)
+        sigs.append((clean, noisy, enh))
+
+    def check(m, i, case, noisy=False):
+        sfx = "_noisy" if noisy else ""
+        assert abs(m["sisdr"][i] - case["sisdr" + sfx]) < 1e-3 and abs(m["snr"][i] - case["snr" + sfx]) < 1e-3
+        if not noisy:
+            assert abs(m["segsnr"][i] - case["segsnr"]) < 1e-3
+            assert abs(m["lsd"][i] - case["lsd"]) < 2e-3
+    for (clean, noisy, enh), case in zip(sigs, cases):
+        c = torch.from_numpy(clean)[None].cuda()
+        check(compute_metrics_device(c, torch.from_numpy(enh)[None].cuda()), 0, case)
+        check(compute_metrics_device(c, torch.from_numpy(noisy)[None].cuda()), 0, case, noisy=True)
+    lens = [len(s[0]) for s in sigs]
+    pad = lambda k: torch.from_numpy(np.stack([np.pad(s[k], (0, max(lens) - len(s[k]))) for s in sigs])).cuda()  # noqa: E731
+    m = compute_metrics_device(pad(0), pad(2), lens)
+    for i, case in enumerate(cases):
+        check(m, i, case)
