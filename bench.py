@@ -256,6 +256,8 @@ def kernel_table(plan, d_in, d_out, pk, reps=5):
     total_ms = sum(acc)
     rows = []
     for name, v in shapes.items():
+        if v["launches"] == 0 or (v["kernel"] == "resize" and v["ms"] < 0.004):   # varlen-only masks / fused-away resize
+            continue
         row = dict(name=name, kernel=v["kernel"], launches=v["launches"], us_per_launch=v["ms"] * 1e3 / max(v["launches"], 1),
                    share_of_step=v["ms"] / total_ms)
         if v["algo_flops"] > 0:
@@ -322,8 +324,14 @@ def run_ours(args):
     if sampler:
         sampler.window[0] = time.perf_counter()
     dev_ms = max_over_ranks(device_leg(enh, d_in, d_out, args.steps, 0, barrier))
-    # ---- host-to-host leg (e2e): pinned H2D + enhance + D2H every step, through the public API
-    for _ in range(min(args.warmup, 3)):
+    # ---- host-to-host leg (e2e): pinned H2D + enhance + D2H every step, through the public API.
+    # Both legs start from the same power state: the board is power-capped under this workload (NVML: sw_power_cap), and a
+    # leg that starts right after the other inherits its spent power budget - measured at N = 2 with 20-step legs: device
+    # leg 2.93 ms/step, e2e leg right after it 3.15 ms/step, but 3.19 vs 3.21 ms/step when both run 100 steps (profiles/
+    # r2_e2e_order.json).  So: idle pause, the same W warm-up steps, then the timed K steps - exactly like the first leg.
+    barrier()
+    time.sleep(1.0)
+    for _ in range(args.warmup):
         enh.enhance_pinned(pin_in, pin_out)
     barrier()
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -409,6 +417,30 @@ def run_ours(args):
             os.makedirs(os.path.dirname(os.path.abspath(args.latency_sweep)), exist_ok=True)
             with open(args.latency_sweep, "w") as f:
                 json.dump(dict(api=latency["api"], precision=args.precision, sweep=sweep), f, indent=1)
+
+    # ---- SURVEY.md section 8 f rank 2: a mixed-length batch (lengths spread over 3..4 s, zero-padded to 4 s) through
+    # hvit_enhance_varlen; the rate counts VALID audio only
+    if extras and not args.widened and args.seconds == 4.0:
+        lens = np.linspace(48000, n, B).astype(np.int32)
+        d_len = torch.from_numpy(lens).cuda()
+        d_var = d_in.clone()
+        for i, L in enumerate(lens):
+            d_var[i, int(L):] = 0.0
+        for _ in range(3):
+            enh.enhance_varlen_device(d_var, d_len, out=d_out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            enh.enhance_varlen_device(d_var, d_len, out=d_out)
+        e1.record()
+        torch.cuda.synchronize()
+        vms = e0.elapsed_time(e1) / 10
+        configs["varlen"] = dict(workload=f"mixed-length batch: {B} clips, lengths linspace(3 s, 4 s), zero-padded to 4 s, "
+                                          "hvit_enhance_varlen (device-resident)",
+                                 value=float(lens.sum()) / 16000.0 / (vms / 1e3), unit=UNIT + " (valid audio)", ms_per_step=vms,
+                                 padded_fraction=1.0 - float(lens.sum()) / (B * n), ratio_to_fixed_length=None)
+        configs["varlen"]["ratio_to_fixed_length"] = configs["varlen"]["value"] / value
 
     # ---- BASELINE.json configs[4]: the widened model (12 L / 768-d / 12 h) at the same batch, on this one GPU
     if extras and not args.widened and args.seconds == 4.0:

@@ -137,6 +137,12 @@ __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, in
                : "memory");
 }
 
+__device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* m, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(m), "r"(c0), "r"(c1),
+               "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+
 // ---- TMA store (shared -> global, bulk async group) ----
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(m),

@@ -408,6 +408,20 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
             } else {  // IG_PATCH
               const int ky = tap / p.patch, kx = tap % p.patch;
               tma_load_5d_2sm(sa, &maps.a, &full_bar[stage], c0, kx, c.w0, ky, c.b * p.Hq + c.h0);
+              // the patch gather streams the whole last encoder map from HBM (262 MB at 64 x 4 s) through this ring:
+              // pull the box the ring will ask for a_prefetch k-blocks from now into L2 (same reason as for fc2 above)
+              if (p.a_prefetch > 0) {
+                const int pk = kb + p.a_prefetch;
+                if (pk < kblocks) {
+                  const int t2 = pk / cblocks;
+                  tma_prefetch_5d(&maps.a, (pk - t2 * cblocks) * BLOCK_K, t2 % p.patch, c.w0, t2 / p.patch, c.b * p.Hq + c.h0);
+                } else if (ct + num_clusters < num_ctiles) {
+                  const TileCoord cn = decode_ctile(p, ct + num_clusters, n_tiles_n, BLOCK_N, pairs_per_group, rank);
+                  const int pk2 = pk - kblocks, t2 = pk2 / cblocks;
+                  if (cn.b != c.b || cn.h0 != c.h0 || cn.w0 != c.w0)
+                    tma_prefetch_5d(&maps.a, (pk2 - t2 * cblocks) * BLOCK_K, t2 % p.patch, cn.w0, t2 / p.patch, cn.b * p.Hq + cn.h0);
+                }
+              }
             }
           }
           tma_load_2d_2sm(sb, &maps.b, &full_bar[stage], kb * BLOCK_K, b_row);
@@ -1128,11 +1142,12 @@ int launch_igemm_tc2(const IgemmParams& p, const IgemmMaps& maps, int block_n, i
     return -1;
   }
   IgemmParams pp = p;
-  // A operand larger than what survives in L2 next to the rest of the step's traffic (fc2's 130 MB hidden activation):
-  // L2-prefetch it a few k-blocks ahead of the ring (measured: fc2 69.3 -> 65.3 us; an L2-resident A gets slower)
+  // L2 prefetch of an HBM-streamed A operand a few k-blocks ahead of the ring (IG_PLAIN and IG_PATCH producers): OFF by
+  // default.  Round 1 measured a gain for fc2 (69.3 -> 65.3 us at distance 4); with the residual stream pinned in L2 and
+  // the current ring depths it now costs time - round 2, same box, back to back: fc2 64.6 us without vs 68.6-70.7 us with
+  // (distance 2 / 4 / 8 / 12), patch embedding 143.6 vs 170-181 us (profiles/r2_a_prefetch.json): the prefetched boxes
+  // compete with the ring's own loads for the same L2 request slots.  HVIT_A_PREFETCH=k re-enables it for experiments.
   pp.a_prefetch = 0;
-  if (p.mode == IG_PLAIN && p.K >= 1024 && p.N / block_n <= 2 && static_cast<double>(p.M) * p.K * 2.0 >= 96e6)
-    pp.a_prefetch = 4;  // (few N tiles per A tile: every A byte really comes from HBM)
   if (const char* e = getenv("HVIT_A_PREFETCH")) pp.a_prefetch = atoi(e);
   pp.res_inplace = (p.residual != nullptr && p.residual == p.out && p.ldr == p.ldc && p.res_mod == 0 &&
                     !(p.dbg & 32)) ? 1 : 0;

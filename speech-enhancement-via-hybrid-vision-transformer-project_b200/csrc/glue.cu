@@ -381,10 +381,10 @@ __global__ void istft_ola_kernel(const float* __restrict__ frames, const unsigne
 // Per warp: load + window two frames (real / imaginary part of one complex buffer) -> forward FFT -> per bin: untangle
 // the two spectra, E = mo * mag_max * S / |S| for both, re-tangle as Z = Ea + i Eb (in place: bin f and N - f belong to
 // the same lane) -> inverse FFT; then the block overlap-adds its hop range.
-constexpr int OLA_HOPS = FRAMES - 3;
-constexpr int EI_SMEM = FR * XS * sizeof(float2) + NBIN * (sizeof(int2) + sizeof(float));
-
-__global__ void __launch_bounds__(FR * 32, 4) enhance_istft_kernel(const float* __restrict__ wave, int n_pitch, int T_pitch,
+// FRI = warps per block (each transforms a pair of frames): 2 * FRI frames per block, 2 * FRI - 3 hops of output.
+// FRI = 16: 29 of 32 transformed frames are "new" (1.10x redundant FFT work; 1.23x at FRI = 8).
+template <int FRI>
+__global__ void __launch_bounds__(FRI * 32, FRI == 16 ? 2 : 4) enhance_istft_kernel(const float* __restrict__ wave, int n_pitch, int T_pitch,
                                                                 const unsigned* __restrict__ max_bits,
                                                                 const unsigned* __restrict__ mag_max_bits,
                                                                 const float* __restrict__ lowres, int Hs, int Ws_pitch,
@@ -393,11 +393,13 @@ __global__ void __launch_bounds__(FR * 32, 4) enhance_istft_kernel(const float* 
                                                                 const int* __restrict__ geo, int geo_ws_idx) {
   griddep_launch_dependents();
   griddep_wait();
+  constexpr int NFR = 2 * FRI, HOPS = NFR - 3;
   extern __shared__ float2 sm[];
-  float2* xs = sm;                                            // [FR][XS]
-  int2* lyi = reinterpret_cast<int2*>(xs + FR * XS);          // [NBIN] row offsets (i0 * Ws, i1 * Ws) of the resize
+  float2* xs = sm;                                            // [FRI][XS]
+  int2* lyi = reinterpret_cast<int2*>(xs + FRI * XS);         // [NBIN] source rows (i0, i1) of the frequency resize
   float* lyw = reinterpret_cast<float*>(lyi + NBIN);          // [NBIN] weight of row i1
-  const int b = blockIdx.y, t0 = blockIdx.x * OLA_HOPS;
+  float* cols = lyw + NBIN + 3;                               // [NFR][Hs] decoder map resized along time, per frame
+  const int b = blockIdx.y, t0 = blockIdx.x * HOPS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float mv = guard_scalar(max_bits[b]);
   const float inv_mv = 1.0f / mv;
@@ -407,10 +409,26 @@ __global__ void __launch_bounds__(FR * 32, 4) enhance_istft_kernel(const float* 
   const int n = geo != nullptr ? geo[b * GEO_STRIDE + GEO_N] : n_pitch;
   const int T = geo != nullptr ? geo[b * GEO_STRIDE + GEO_T] : T_pitch;
   const int Ws = geo != nullptr ? geo[b * GEO_STRIDE + geo_ws_idx] : Ws_pitch;
-  for (int f = threadIdx.x; f < NBIN; f += FR * 32) {
+  for (int f = threadIdx.x; f < NBIN; f += FRI * 32) {
     const Lerp ly = make_lerp(f, Hs, NBIN);
-    lyi[f] = make_int2(ly.i0 * Ws_pitch, ly.i1 * Ws_pitch);
+    lyi[f] = make_int2(ly.i0, ly.i1);
     lyw[f] = ly.l1;
+  }
+  {
+    // HybridViT's final bilinear resize (hybrid_vit.py:458-465), time axis first: cols[t][h] = the decoder map's row h
+    // interpolated at frame t0 + t - every (bin, frame) below then needs two shared-memory reads instead of four global
+    // ones (same association as the stand-alone resize: ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11))
+    const float* src = lowres + static_cast<long long>(b) * Hs * Ws_pitch;
+    for (int i = threadIdx.x; i < NFR * Hs; i += FRI * 32) {
+      const int t = i / Hs, h = i - t * Hs;
+      float v = 0.f;
+      if (t0 + t < T) {
+        const Lerp lx = make_lerp(t0 + t, Ws, T);
+        const float* r = src + h * Ws_pitch;
+        v = lx.l0 * __ldg(r + lx.i0) + lx.l1 * __ldg(r + lx.i1);
+      }
+      cols[i] = v;
+    }
   }
   const int ta = t0 + 2 * warp;
   const bool live = ta < T, has_b = ta + 1 < T;
@@ -439,10 +457,10 @@ __global__ void __launch_bounds__(FR * 32, 4) enhance_istft_kernel(const float* 
     __syncwarp();
     fft512_warp<false>(x, lane);
   }
-  __syncthreads();  // resize table complete
+  __syncthreads();  // resize tables complete
   if (live) {
-    const Lerp lxa = make_lerp(ta, Ws, T), lxb = make_lerp(has_b ? ta + 1 : ta, Ws, T);
-    const float* src = lowres + static_cast<long long>(b) * Hs * Ws_pitch;
+    const float* ca = cols + (2 * warp) * Hs;
+    const float* cb = ca + Hs;
     // E = (model_out * mag_max) * S / |S| of one bin (z = S, mo = model output)
     auto bin = [&](float2 z, float mo, int f) -> float2 {
       const float zz = z.x * z.x + z.y * z.y;
@@ -466,14 +484,8 @@ __global__ void __launch_bounds__(FR * 32, 4) enhance_istft_kernel(const float* 
       const float2 zb = make_float2(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x));
       const int2 ro = lyi[f];
       const float wy1 = lyw[f], wy0 = 1.0f - wy1;
-      const float* r0 = src + ro.x;
-      const float* r1 = src + ro.y;
-      const float moa = wy0 * (lxa.l0 * __ldg(r0 + lxa.i0) + lxa.l1 * __ldg(r0 + lxa.i1)) +
-                        wy1 * (lxa.l0 * __ldg(r1 + lxa.i0) + lxa.l1 * __ldg(r1 + lxa.i1));
-      float mob = 0.f;
-      if (has_b)
-        mob = wy0 * (lxb.l0 * __ldg(r0 + lxb.i0) + lxb.l1 * __ldg(r0 + lxb.i1)) +
-              wy1 * (lxb.l0 * __ldg(r1 + lxb.i0) + lxb.l1 * __ldg(r1 + lxb.i1));
+      const float moa = wy0 * ca[ro.x] + wy1 * ca[ro.y];
+      const float mob = has_b ? wy0 * cb[ro.x] + wy1 * cb[ro.y] : 0.f;
       if (model_out != nullptr) {  // debug / test builds of the plan only: the resized model output [B,257,T]
         float* mp = model_out + (static_cast<long long>(b) * NBIN + f) * T_pitch + ta;
         mp[0] = moa;
@@ -490,9 +502,9 @@ __global__ void __launch_bounds__(FR * 32, 4) enhance_istft_kernel(const float* 
   __syncthreads();
   // ---- overlap-add of this block's hop range straight out of shared memory, envelope division, de-normalisation
   const int j_lo = blockIdx.x == 0 ? NFFT / 2 : HOP * (t0 + 3);
-  const int j_hi = min(HOP * (t0 + FRAMES), NFFT / 2 + n_pitch);
+  const int j_hi = min(HOP * (t0 + NFR), NFFT / 2 + n_pitch);
   float* out = wave_out + static_cast<long long>(b) * n_pitch - NFFT / 2;
-  for (int j = j_lo + threadIdx.x; j < j_hi; j += FR * 32) {
+  for (int j = j_lo + threadIdx.x; j < j_hi; j += FRI * 32) {
     if (j >= NFFT / 2 + n) {  // padding of a shorter clip (variable-length batch)
       out[j] = 0.f;
       continue;
@@ -1161,21 +1173,43 @@ int launch_stft(const float* wave, int B, int n, int T, const float* max_val, fl
 
 static void fft_smem_config() {}
 
-int launch_enhance_istft(const float* wave_in, const float* max_val, const unsigned* mag_max_bits, const float* lowres,
-                         int Hs, int Ws, float* model_out, float* wave_out, int B, int n, int T, cudaStream_t s,
-                         const int* geo, int geo_ws_idx) {
-  if (n <= 0) return 0;
+template <int FRI>
+static int launch_enhance_istft_t(const float* wave_in, const float* max_val, const unsigned* mag_max_bits, const float* lowres,
+                                  int Hs, int Ws, float* model_out, float* wave_out, int B, int n, int T, cudaStream_t s,
+                                  const int* geo, int geo_ws_idx) {
+  constexpr int HOPS = 2 * FRI - 3;
+  const size_t smem = static_cast<size_t>(FRI) * XS * sizeof(float2) + NBIN * (sizeof(int2) + sizeof(float)) + 16 +
+                      static_cast<size_t>(2 * FRI) * Hs * sizeof(float);
+  if (smem > 200 * 1024) {
+    set_error("enhance_istft: decoder map too tall (%d rows)", Hs);
+    return -1;
+  }
+  static PerDeviceOnce once;
+  if (once.first() && cudaFuncSetAttribute(enhance_istft_kernel<FRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+    once.retry();
+    return check_launch("enhance_istft(attr)");
+  }
   const int hops = (NFFT / 2 - 1 + n) >> 7;                        // index of the last hop that holds output
-  const int blocks = hops >= 3 ? (hops - 3) / OLA_HOPS + 1 : 1;
-  dim3 grid(blocks, B);
-  launch_pdl(enhance_istft_kernel, dim3(grid), dim3(FR * 32), EI_SMEM, s, wave_in, n, T,
+  const int blocks = hops >= 3 ? (hops - 3) / HOPS + 1 : 1;
+  launch_pdl(enhance_istft_kernel<FRI>, dim3(blocks, B), dim3(FRI * 32), smem, s, wave_in, n, T,
              reinterpret_cast<const unsigned*>(max_val), mag_max_bits, lowres, Hs, Ws, model_out, wave_out, geo, geo_ws_idx);
   return check_launch("enhance_istft");
 }
 
+int launch_enhance_istft(const float* wave_in, const float* max_val, const unsigned* mag_max_bits, const float* lowres,
+                         int Hs, int Ws, float* model_out, float* wave_out, int B, int n, int T, cudaStream_t s,
+                         const int* geo, int geo_ws_idx) {
+  if (n <= 0) return 0;
+  // 16 frames per block by default (measured at 64 x 4 s: 106-109 us; 32-frame blocks - HVIT_ISTFT_FR=16, 10 % less
+  // redundant FFT work but half the blocks per SM - 112-114 us)
+  static const int fri = getenv("HVIT_ISTFT_FR") != nullptr ? atoi(getenv("HVIT_ISTFT_FR")) : 8;
+  if (fri == 16)
+    return launch_enhance_istft_t<16>(wave_in, max_val, mag_max_bits, lowres, Hs, Ws, model_out, wave_out, B, n, T, s, geo, geo_ws_idx);
+  return launch_enhance_istft_t<8>(wave_in, max_val, mag_max_bits, lowres, Hs, Ws, model_out, wave_out, B, n, T, s, geo, geo_ws_idx);
+}
+
 int launch_istft_frames(float* model_out, const float* lowres, int Hs, int Ws, const float2* spec,
                         const unsigned* mag_max_bits, float* frames, int B, int T, cudaStream_t s) {
-  fft_smem_config();
   dim3 grid((T + FRAMES - 1) / FRAMES, B);
   launch_pdl(istft_frames_kernel, dim3(grid), dim3(FR * 32), FFT_SMEM, s, model_out, lowres, Hs, Ws, spec, mag_max_bits, T, frames);
   return check_launch("istft_frames");

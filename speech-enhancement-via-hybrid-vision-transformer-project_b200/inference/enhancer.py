@@ -189,14 +189,16 @@ class AudioEnhancer:
     # ------------------------------------------------------------------ reference API
     @torch.no_grad()
     def enhance(self, noisy_audio: np.ndarray, normalize: bool = True) -> np.ndarray:
-        """Enhance one noisy waveform (reference enhancer.py:55-135).  float32 in / float32 out
-        (the reference follows the input dtype; inputs are cast to float32 here)."""
+        """Enhance one noisy waveform (reference enhancer.py:55-135).  The result has the input's floating dtype like the
+        reference's (float32 in -> float32 out, float64 in -> float64 out); the arithmetic itself is the plan's
+        (fp32 / fp16 on the device) - a float64 input is rounded to float32 first."""
         x = np.asarray(noisy_audio)
         if x.ndim != 1:
             raise ValueError(f"expected a 1-D waveform, got shape {x.shape}")
         if x.size == 0:
             raise ValueError("zero-size array to reduction operation maximum which has no identity")
-        return self.enhance_batch(x[None, :], normalize=normalize)[0]
+        y = self.enhance_batch(x[None, :], normalize=normalize)[0]
+        return y.astype(np.float64) if x.dtype == np.float64 else y
 
     def enhance_file(self, input_path, output_path, normalize: bool = True) -> None:
         """reference enhancer.py:137-162 - 16-bit / float PCM WAV I/O without librosa/soundfile."""
@@ -205,6 +207,24 @@ class AudioEnhancer:
         out = self.enhance(audio, normalize=normalize)
         save_audio(output_path, out, self.sample_rate)
         print(f"Enhanced audio saved to {output_path}")
+
+    def enhance_varlen_device(self, wave: torch.Tensor, n_valid: torch.Tensor, normalize: bool = True,
+                              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Device-resident mixed-length batch: ``wave`` fp32 CUDA [B, n_max] zero-padded clips, ``n_valid`` int32 CUDA [B]
+        true lengths -> enhanced fp32 CUDA [B, n_max] (zero beyond each clip's length).  See :meth:`enhance_varlen`."""
+        if wave.dim() != 2 or not wave.is_cuda or wave.dtype != torch.float32:
+            raise ValueError("enhance_varlen_device expects a float32 CUDA tensor [B, n]")
+        if n_valid.dtype != torch.int32 or not n_valid.is_cuda or n_valid.numel() != wave.shape[0]:
+            raise ValueError("n_valid must be an int32 CUDA tensor with one length per clip")
+        wave = wave.contiguous()
+        B, n = wave.shape
+        plan = self.model.plan_for(B, N_FFT // 2 + 1, 1 + n // HOP, n_samples=n)
+        if out is None:
+            out = torch.empty_like(wave)
+        with torch.cuda.device(self._dev):
+            _lib.check(plan.lib.hvit_enhance_varlen(plan.handle, wave.data_ptr(), out.data_ptr(), n_valid.data_ptr(),
+                                                    1 if normalize else 0, _lib.current_stream_ptr()), "hvit_enhance_varlen")
+        return out
 
     @torch.no_grad()
     def enhance_varlen(self, clips: Sequence[np.ndarray], normalize: bool = True, pad_multiple: int = 8000,

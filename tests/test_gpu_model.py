@@ -220,9 +220,10 @@ def test_enhance_edge_cases(oracle, precision):
         enh.enhance(np.zeros(0, dtype=np.float32))
     with pytest.raises(Exception):
         enh.enhance(np.zeros(300, dtype=np.float32))   # too short for the 16x downsampling + 4x4 patches
-    # float64 input is accepted and cast
+    # float64 input is accepted; the output follows the input dtype like the reference's (enhancer.py:72-133)
     _, noisy = oracle.synth_clip(seconds=0.5, seed=9)
-    assert np.array_equal(enh.enhance(noisy.astype(np.float64)), enh.enhance(noisy))
+    y64 = enh.enhance(noisy.astype(np.float64))
+    assert y64.dtype == np.float64 and np.array_equal(y64, enh.enhance(noisy).astype(np.float64))
 
 
 def test_batch_properties_16bit(oracle):
@@ -561,3 +562,67 @@ def test_device_metrics_match_reference_golden():
     m = compute_metrics_device(pad(0), pad(2), lens)
     for i, case in enumerate(cases):
         check(m, i, case)
+
+
+# ------------------------------------------------------------------------------------------------ memory discipline
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_workspace_poison_and_canaries(oracle, precision):
+    """compute-sanitizer is closed on the GPU pool (profiles/r2_compute_sanitizer_closed.log), so the two properties it
+    would check are asserted directly through the C ABI on a caller-owned workspace:
+      * no read of uninitialised workspace: every byte of the workspace (except the plan-creation constants "stem_a") is
+        overwritten with 0xFF (NaN patterns in every float type) between two runs - the results stay bit-identical, for
+        the fixed-length and the variable-length path;
+      * no write outside [workspace, workspace + hvit_workspace_bytes): 64 KB canaries on both sides stay intact."""
+    import ctypes as C
+    from hvit_b200 import _lib
+    cfg, sd, model = _model(oracle, TINY, seed=17, precision=precision)
+    lib = _lib.load()
+    prec = {"fp32": _lib.PREC_FP32, "fp16": _lib.PREC_FP16}[precision]
+    ccfg = model._c_cfg(prec)
+    packed = model._get_packed(prec)
+    B, n = 3, 12000
+    T = 1 + n // 128
+    nbytes = lib.hvit_workspace_bytes(C.byref(ccfg), B, 257, T, n)
+    guard = 65536
+    raw = torch.full((nbytes + 2 * guard + 1024,), 0xA5, dtype=torch.uint8, device="cuda")
+    off = guard + (-(raw.data_ptr() + guard)) % 1024
+    ws = raw[off:off + nbytes]
+    handle = C.c_void_p()
+    _lib.check(lib.hvit_plan_create(C.byref(ccfg), C.byref(packed.c), B, 257, T, n, ws.data_ptr(), nbytes,
+                                    _lib.current_stream_ptr(), C.byref(handle)), "hvit_plan_create")
+    try:
+        clips = np.stack([oracle.synth_clip(seed=40 + i, n_samples=n)[1] for i in range(B)])
+        x = torch.from_numpy(clips).cuda()
+        lens = torch.tensor([n, 5000, 2047], dtype=torch.int32, device="cuda")
+        keep = None
+        o, dims, es = C.c_size_t(), (C.c_int * 4)(), C.c_int()
+        if lib.hvit_plan_buffer(handle, b"stem_a", C.byref(o), C.byref(dims), C.byref(es)) >= 0:
+            keep = (o.value, dims[0] * es.value)
+
+        def poison():
+            saved = ws[keep[0]:keep[0] + keep[1]].clone() if keep else None
+            ws.fill_(0xFF)
+            if keep:
+                ws[keep[0]:keep[0] + keep[1]] = saved
+
+        def run(varlen):
+            y = torch.empty_like(x)
+            if varlen:
+                _lib.check(lib.hvit_enhance_varlen(handle, x.data_ptr(), y.data_ptr(), lens.data_ptr(), 1,
+                                                   _lib.current_stream_ptr()), "hvit_enhance_varlen")
+            else:
+                _lib.check(lib.hvit_enhance(handle, x.data_ptr(), y.data_ptr(), 1, _lib.current_stream_ptr()), "hvit_enhance")
+            torch.cuda.synchronize()
+            return y
+        for varlen in (False, True):
+            torch.cuda.synchronize()
+            y1 = run(varlen)
+            poison()
+            y2 = run(varlen)
+            assert bool(torch.isfinite(y2).all()) and torch.equal(y1, y2), ("poison", varlen)
+        ref = oracle.enhance(sd, clips[1][:5000], cfg)
+        assert oracle.max_rel_err(y2[1, :5000].cpu().numpy(), ref) <= TOL[precision] * 2
+        assert bool((y2[1, 5000:] == 0).all())
+        assert bool((raw[:off] == 0xA5).all()) and bool((raw[off + nbytes:] == 0xA5).all()), "write outside the workspace"
+    finally:
+        lib.hvit_plan_destroy(handle)
