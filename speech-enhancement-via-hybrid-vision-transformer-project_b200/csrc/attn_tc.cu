@@ -132,7 +132,8 @@ __device__ __forceinline__ float exp_pack_row(uint32_t (&s)[128], float scale_lo
 template <bool PROF>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out, int N,
-               int D, int heads, int n_items, float scale_log2, int f16, long long* prof, const int* __restrict__ geo) {
+               int D, int heads, int n_items, float scale_log2, int f16, long long* prof, const int* __restrict__ geo,
+               int pingpong) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B swizzle needs 1024-byte aligned tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -354,6 +355,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
     const float ebias = f16 ? 112.0f : 0.0f;   // see exp_pack_row
     const uint32_t emul = f16 ? 8u : 1u;
     const float unbias = f16 ? 1.925929944387236e-34f /* 2^-112 */ : 1.0f;
+    if (pingpong && w == 1) named_bar_arrive(3, 256);  // group A holds the token first
     uint32_t blk = 0, itw = 0;
     long long t_sfull = 0, t_ld = 0, t_max = 0, t_pv = 0, t_exp = 0, t_arr = 0, t_fin = 0;
     auto tick = [&]() -> long long { return PROF ? clock64() : 0ll; };
@@ -433,7 +435,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
         }
         const long long c4 = tick();
         if (PROF && prof != nullptr && row == 0 && blk >= 1 && blk <= 6) prof[blockIdx.x * 32 + w * 16 + 9 + blk] = c4;
+        // Exp-phase token (named barriers 3 / 4, FA3-style ping-pong): the MUFU unit of a scheduler serves one softmax
+        // warp at its full rate (10 cycles per score alone, 17 each when both groups' exp phases overlap), so the groups
+        // take strict turns - group A's exp phase runs while group B loads / reduces its next block and vice versa.
+        // (measured: 74.9 -> 67.0 us stand-alone at 64 x 496 tokens, 397 -> 341 us at 1 248; a NON-strict variant - a shared-
+        // memory lock taken with atomicCAS, per scheduler or per group - ran at 133 us: the spinning lanes cost more than
+        // the strict order loses at item boundaries)
+        if (pingpong) named_bar_sync(3 + w, 256);
         l_run += exp_pack_row(s, scale_log2, m_used + ebias, emul, p_row, sw);
+        // (group B's very last hand-over has no taker: skipped, so no barrier is left half-arrived at exit)
+        if (pingpong && !(w == 1 && j + 1 == nkv && item + static_cast<int>(gridDim.x) >= n_items))
+          named_bar_arrive(3 + (w ^ 1), 256);
         const long long c5 = tick();
         fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor-core async proxy
         tc_fence_before();
@@ -515,11 +527,16 @@ int launch_attn_tc(const CUtensorMap& tmap_qkv, const CUtensorMap& tmap_out, int
     return -1;
   }
   const int grid = items < sms ? static_cast<int>(items) : sms;
+  // exp-phase ping-pong needs both softmax groups to see the same number of key blocks: every query-tile pair must
+  // have its second tile, and (variable-length batches aside, where the count is per clip but equal for both groups)
+  // that is a property of N alone
+  static const int pp_env = [] { const char* e = getenv("HVIT_ATTN_PINGPONG"); return e != nullptr ? atoi(e) : 1; }();
+  const int pingpong = (pp_env != 0 && ((N + 255) / 256 - 1) * 256 + 128 < N) ? 1 : 0;
   const cudaError_t le =
       prof != nullptr ? launch_pdl(attn_tc_kernel<true>, dim3(grid), dim3(AT_THREADS), AT_SMEM, stream, tmap_qkv, tmap_out,
-                                   N, D, heads, static_cast<int>(items), scale * 1.4426950408889634f, f16, prof, geo)
+                                   N, D, heads, static_cast<int>(items), scale * 1.4426950408889634f, f16, prof, geo, pingpong)
                       : launch_pdl(attn_tc_kernel<false>, dim3(grid), dim3(AT_THREADS), AT_SMEM, stream, tmap_qkv, tmap_out,
-                                   N, D, heads, static_cast<int>(items), scale * 1.4426950408889634f, f16, prof, geo);
+                                   N, D, heads, static_cast<int>(items), scale * 1.4426950408889634f, f16, prof, geo, pingpong);
   if (le != cudaSuccess) {
     set_error("attn_tc: %s", cudaGetErrorString(le));
     return -4;

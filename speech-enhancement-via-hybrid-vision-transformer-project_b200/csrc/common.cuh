@@ -162,6 +162,9 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 // ---- CTA-pair (cta_group::2) variants: the transaction bytes are signalled on the LEADER CTA's mbarrier (same
 // shared-memory offset, peer bit of the shared::cluster address cleared), the data lands in the issuing CTA.
