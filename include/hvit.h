@@ -226,6 +226,21 @@ int hvit_plan_tokens(const hvit_plan* plan, int* hp, int* wp);
 int hvit_gemm_16(const void* a_dev, int lda, const void* w_dev, const float* scale_dev, const float* shift_dev,
                  int act, const float* residual_dev, int ldr, void* out_dev, int ldc, int out_f32, int M, int N,
                  int K, int f16, void* stream);
+/* nn.LayerNorm folded into the linears on either side of it (attention.py:152-153,258-262 pre-norm blocks;
+ * hybrid_vit.py:343 final norm + to_feature_map) - what the 16-bit plans run instead of a LayerNorm kernel:
+ *   producer  x[M,N] += a[M,K] * w[N,K]^T + bias  (fp32, in place), plus x16_out = 16-bit(x) and, per row and per
+ *             128-column slot, the slot's (mean, centred sum of squares) in stats_out [M, N/128, 2]; N % 256 == 0
+ *   consumer  out = act(LayerNorm(x; gamma, beta, eps) * w[N,K]^T + bias) from x16 and the statistics; w_scratch
+ *             ([N,K] 16-bit) and gc_scratch ([2N] fp32) receive the gamma-scaled weights and the g / c vectors
+ *   rowstats  x16 and statistics of an existing fp32 matrix (the first block's input) */
+int hvit_linear_ln_producer_16(const void* a_dev, int lda, const void* w_dev, const float* bias_dev, float* x_dev,
+                               void* x16_out_dev, float* stats_out_dev, int M, int N, int K, int f16, void* stream);
+int hvit_linear_ln_consumer_16(const void* x16_dev, const float* stats_dev, int slots, const void* w_dev,
+                               const float* gamma_dev, const float* beta_dev, const float* bias_dev, float eps, int act,
+                               void* out_dev, int ldc, int M, int N, int K, int f16, void* w_scratch_dev,
+                               float* gc_scratch_dev, void* stream);
+int hvit_rowstats_16(const float* x_dev, void* x16_out_dev, float* stats_out_dev, int rows, int D, int slots, int f16,
+                     void* stream);
 /* Same contract on CUDA cores in fp32 (a, w, out fp32). */
 int hvit_gemm_f32(const float* a_dev, int lda, const float* w_dev, const float* scale_dev, const float* shift_dev,
                   int act, const float* residual_dev, int ldr, float* out_dev, int ldc, int M, int N, int K,

@@ -90,6 +90,9 @@ SYMBOLS = {
                                  C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I)]),
     "hvit_enhance_profiled": (_I, [_VP, _VP, _VP, _I, _VP, C.POINTER(C.c_float), _I]),
     "hvit_gemm_16": (_I, [_VP, _I, _VP, _VP, _VP, _I, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, _VP]),
+    "hvit_linear_ln_producer_16": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
+    "hvit_linear_ln_consumer_16": (_I, [_VP, _VP, _I, _VP, _VP, _VP, _VP, _F, _I, _VP, _I, _I, _I, _I, _I, _VP, _VP, _VP]),
+    "hvit_rowstats_16": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "hvit_gemm_f32": (_I, [_VP, _I, _VP, _VP, _VP, _I, _VP, _I, _VP, _I, _I, _I, _I, _VP]),
     "hvit_conv3x3_16": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP, _I, _I, _I, _I, _I, _I, _VP]),
     "hvit_conv3x3_f32": (_I, [_VP, _VP, _VP, _VP, _I, _I, _VP, _I, _I, _I, _I, _I, _VP]),

@@ -222,6 +222,18 @@ static int mlp_panels(int M, int hidden, int es, int tensor_core) {
   return 1;
 }
 
+// LayerNorm folded into the GEMMs around it (16-bit modes): needs 256-column producer tiles (statistics slots of 128
+// columns) and the register-resident row-statistics kernel.  OFF by default - measured slower at 64 x 4 s (3.15 vs 2.90
+// ms per step, profiles/r2_experiments.json): the 13 LayerNorm launches it removes cost 39 us per layer, but the
+// residual update then has to LOAD the old rows (proj 33.6 -> 57.9 us, fc2 68.9 -> 78.2 us; the TMA reduce-add of the
+// unfolded path never brings them into the SM) and the consumers' epilogues grow (qkv +12 us, fc1 +27 us).
+// HVIT_LN_FOLD=1 builds plans with it (read at plan creation; parity-tested both ways).
+static bool ln_fold_enabled(int precision, int D, int layers) {
+  const char* e = getenv("HVIT_LN_FOLD");
+  const bool on = e != nullptr && e[0] == '1';
+  return on && precision != HVIT_PREC_FP32 && layers > 0 && D % 256 == 0 && D <= 1024;
+}
+
 static int pick_block_n(int N) { return N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64); }
 
 static void pick_tile(int H, int W, int* Wt, int* Ht) {
@@ -291,6 +303,10 @@ int num_sms() {
   if (d.sms == 0) {
     cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
     if (d.sms <= 0) d.sms = 148;
+    if (const char* e = getenv("HVIT_NUM_SMS")) {  // diagnostics: run the persistent kernels on fewer SMs
+      const int v = atoi(e);
+      if (v >= 2 && v < d.sms) d.sms = v & ~1;
+    }
   }
   return d.sms;
 }
@@ -493,6 +509,15 @@ static int build_geometry(const hvit_model_cfg& c, int B, int F, int T, int n_sa
   const size_t M = g.M;
   add("tokens", 4, 2, g.M, c.embed_dim, 0, 0, M * c.embed_dim);
   add("ln", g.es, 2, g.M, c.embed_dim, 0, 0, M * c.embed_dim);
+  if (ln_fold_enabled(c.precision, c.embed_dim, c.num_layers)) {
+    // folded LayerNorm: "ln" holds the 16-bit copy of the residual stream; per-row statistics; gamma-scaled weight
+    // copies of qkv / fc1 (per layer) and to_feature_map, their g and c vectors
+    const size_t D_ = c.embed_dim, wl = 3 * D_ * D_ + static_cast<size_t>(c.mlp_hidden) * D_;
+    const size_t Cx0 = g.cat[0].Cx;
+    add("lnstats", 4, 3, g.M, c.embed_dim / 128, 2, 0, M * (c.embed_dim / 128) * 2);
+    add("lnfold_w", 2, 1, 0, 0, 0, 0, c.num_layers * wl + Cx0 * D_);
+    add("lnfold_v", 4, 1, 0, 0, 0, 0, 2 * (c.num_layers * (3 * D_ + c.mlp_hidden) + Cx0));
+  }
   add("qkv", g.es, 2, g.M, 3 * c.embed_dim, 0, 0, M * 3 * c.embed_dim);
   add("attn", g.es, 2, g.M, c.embed_dim, 0, 0, M * c.embed_dim);
   add("mlp", g.es, 2, g.M, c.mlp_hidden, 0, 0, M * c.mlp_hidden);
@@ -539,9 +564,20 @@ static IgemmParams ig_zero() {
 }
 
 // plain GEMM step (both precisions)
+struct LnFold {
+  // consumer
+  const float* stats_in = nullptr;
+  const float* g = nullptr;
+  int slots = 0;
+  float eps = 0.f;
+  // producer
+  void* x16_out = nullptr;
+  int ld16 = 0;
+  float* stats_out = nullptr;
+};
 static int add_linear(hvit_plan* p, const std::string& name, const void* A, int lda, const void* W,
                       const float* shift, int act, const float* residual, int ldr, int res_mod, void* out, int ldc,
-                      int out_f32, int M, int N, int K, double algo_flops = -1.0) {
+                      int out_f32, int M, int N, int K, double algo_flops = -1.0, const LnFold* lf = nullptr) {
   const double fl = 2.0 * M * N * K;
   const int es_ = p->cfg.precision == HVIT_PREC_FP32 ? 4 : 2;
   const double by = (static_cast<double>(M) * K + static_cast<double>(N) * K) * es_ +
@@ -552,6 +588,10 @@ static int add_linear(hvit_plan* p, const std::string& name, const void* A, int 
   q.shift = shift; q.act = act; q.residual = residual; q.ldr = ldr; q.res_mod = res_mod;
   q.out = out; q.ldc = ldc; q.out_f32 = out_f32;
   q.f16 = p->cfg.precision == HVIT_PREC_FP16;
+  if (lf != nullptr) {
+    q.ln_stats_in = lf->stats_in; q.ln_g = lf->g; q.ln_slots = lf->slots; q.ln_eps = lf->eps;
+    q.ln_x16_out = lf->x16_out; q.ld16 = lf->ld16; q.ln_stats_out = lf->stats_out;
+  }
   if (p->cfg.precision != HVIT_PREC_FP32) {
     IgemmMaps mp;
     const int bn = pick_block_n(N);
@@ -810,14 +850,51 @@ static int build_steps(hvit_plan* p) {
     r = tmap_attn_out(&to, att, f16, B, Np, D);
     if (r) return r;
   }
+  // LayerNorm folded into the GEMMs on either side of it (16-bit modes; kernels.h IgemmParams::ln_*):
+  // proj / fc2 (the residual updates) also write the 16-bit copy of the new residual rows and their per-slot statistics,
+  // qkv / fc1 / to_feature_map read that copy with gamma-scaled weights and finish the normalisation in their
+  // epilogues.  Only the first block needs a stand-alone pass (rowstats) over the patch embedding's output.
+  const bool fold = bf && ln_fold_enabled(c.precision, D, c.num_layers);
+  float* lnstats = fold ? at<float>(p, "lnstats") : nullptr;
+  const int slots = D / 128;
+  uint8_t* fold_w = fold ? at<uint8_t>(p, "lnfold_w") : nullptr;
+  float* fold_v = fold ? at<float>(p, "lnfold_v") : nullptr;
+  // gamma / beta folded copies of a consumer's weights, derived once on the setup stream (like the stem's matrices)
+  auto fold_weights = [&](const void* W, const float* gamma, const float* beta, const float* bias, int N, const void** Wp,
+                          LnFold* lf) -> int {
+    float* gv = fold_v;
+    float* cv = fold_v + N;
+    const int e = launch_ln_fold(W, gamma, beta, bias, fold_w, gv, cv, dt, N, D, p->setup_stream);
+    *Wp = fold_w;
+    lf->stats_in = lnstats; lf->g = gv; lf->slots = slots; lf->eps = eps;
+    lf->x16_out = nullptr; lf->ld16 = 0; lf->stats_out = nullptr;
+    fold_w += static_cast<size_t>(N) * D * 2;
+    fold_v += 2 * N;
+    return e;
+  };
+  LnFold prod;  // producer side of proj / fc2
+  prod.x16_out = ln; prod.ld16 = D; prod.stats_out = lnstats;
   for (int l = 0; l < c.num_layers; ++l) {
     const float *g1 = w.ln1_g[l], *b1 = w.ln1_b[l], *g2 = w.ln2_g[l], *b2 = w.ln2_b[l];
     const std::string L = "blocks." + std::to_string(l);
     const double ln_bytes = static_cast<double>(M) * D * (4 + g.es);
-    p->steps.push_back([=](const Ctx& k) { return launch_layernorm(tok, g1, b1, ln, dt, M, D, eps, k.stream); });
-    p->tag(L + ".norm1", "layernorm", 0, 0, ln_bytes);
-    r = add_linear(p, L + ".qkv", ln, D, w.qkv_w[l], w.qkv_b[l], ACT_NONE, nullptr, 0, 0, qkv, 3 * D, !bf, M, 3 * D, D);
-    if (r) return r;
+    if (fold) {
+      if (l == 0) {
+        p->steps.push_back([=](const Ctx& k) { return launch_rowstats(tok, ln, lnstats, dt, M, D, slots, k.stream); });
+        p->tag(L + ".norm1", "rowstats", 0, 0, ln_bytes);
+      }
+      const void* Wq;
+      LnFold cq;
+      r = fold_weights(w.qkv_w[l], g1, b1, w.qkv_b[l], 3 * D, &Wq, &cq);
+      if (r) return r;
+      r = add_linear(p, L + ".qkv", ln, D, Wq, cq.g + 3 * D, ACT_NONE, nullptr, 0, 0, qkv, 3 * D, 0, M, 3 * D, D, -1.0, &cq);
+      if (r) return r;
+    } else {
+      p->steps.push_back([=](const Ctx& k) { return launch_layernorm(tok, g1, b1, ln, dt, M, D, eps, k.stream); });
+      p->tag(L + ".norm1", "layernorm", 0, 0, ln_bytes);
+      r = add_linear(p, L + ".qkv", ln, D, w.qkv_w[l], w.qkv_b[l], ACT_NONE, nullptr, 0, 0, qkv, 3 * D, !bf, M, 3 * D, D);
+      if (r) return r;
+    }
     const size_t probs_off = static_cast<size_t>(l) * B * heads * Np * Np;
     if (bf) {
       p->steps.push_back([=](const Ctx& k) {
@@ -837,13 +914,23 @@ static int build_steps(hvit_plan* p) {
       p->tag(L + ".attn", "attn_f32", 4.0 * B * heads * Np * Np * 64.0, 4.0 * B * heads * Np * Np * 64.0,
              static_cast<double>(M) * 4 * D * g.es);
     }
-    r = add_linear(p, L + ".proj", att, D, w.proj_w[l], w.proj_b[l], ACT_NONE, tok, D, 0, tok, D, 1, M, D, D);
+    r = add_linear(p, L + ".proj", att, D, w.proj_w[l], w.proj_b[l], ACT_NONE, tok, D, 0, tok, D, 1, M, D, D, -1.0,
+                   fold ? &prod : nullptr);
     if (r) return r;
-    p->steps.push_back([=](const Ctx& k) { return launch_layernorm(tok, g2, b2, ln, dt, M, D, eps, k.stream); });
-    p->tag(L + ".norm2", "layernorm", 0, 0, ln_bytes);
+    const void* W1 = w.fc1_w[l];
+    const float* c1 = w.fc1_b[l];
+    LnFold cf;
+    if (fold) {
+      r = fold_weights(w.fc1_w[l], g2, b2, w.fc1_b[l], c.mlp_hidden, &W1, &cf);
+      if (r) return r;
+      c1 = cf.g + c.mlp_hidden;
+    } else {
+      p->steps.push_back([=](const Ctx& k) { return launch_layernorm(tok, g2, b2, ln, dt, M, D, eps, k.stream); });
+      p->tag(L + ".norm2", "layernorm", 0, 0, ln_bytes);
+    }
     // MLP in row panels: fc1(panel) is followed directly by fc2(panel), so the 16-bit hidden activation of a panel
     // (M/P x hidden) is still in L2 when fc2 reads it instead of making the round trip through HBM (130 MB per layer at
-    // 64 x 4 s).  Panels are multiples of 256 rows (one CTA-pair tile).
+    // 64 x 4 s).  Panels are multiples of 256 rows (one CTA-pair tile).  (Measured slower than one panel: default 1.)
     {
       const int es = g.es;
       int panels = mlp_panels(M, c.mlp_hidden, es, bf);
@@ -853,9 +940,17 @@ static int build_steps(hvit_plan* p) {
         const uint8_t* a1 = reinterpret_cast<const uint8_t*>(ln) + static_cast<size_t>(r0) * D * es;
         uint8_t* h1 = reinterpret_cast<uint8_t*>(mlp) + static_cast<size_t>(r0) * c.mlp_hidden * es;
         float* x1 = tok + static_cast<size_t>(r0) * D;
-        r = add_linear(p, L + ".fc1", a1, D, w.fc1_w[l], w.fc1_b[l], ACT_GELU, nullptr, 0, 0, h1, c.mlp_hidden, !bf, rows, c.mlp_hidden, D);
+        LnFold cfp = cf, pp = prod;
+        if (fold) {
+          cfp.stats_in = lnstats + static_cast<size_t>(r0) * slots * 2;
+          pp.stats_out = lnstats + static_cast<size_t>(r0) * slots * 2;
+          pp.x16_out = reinterpret_cast<uint8_t*>(ln) + static_cast<size_t>(r0) * D * es;
+        }
+        r = add_linear(p, L + ".fc1", a1, D, W1, c1, ACT_GELU, nullptr, 0, 0, h1, c.mlp_hidden, !bf, rows, c.mlp_hidden, D,
+                       -1.0, fold ? &cfp : nullptr);
         if (r) return r;
-        r = add_linear(p, L + ".fc2", h1, c.mlp_hidden, w.fc2_w[l], w.fc2_b[l], ACT_NONE, x1, D, 0, x1, D, 1, rows, D, c.mlp_hidden);
+        r = add_linear(p, L + ".fc2", h1, c.mlp_hidden, w.fc2_w[l], w.fc2_b[l], ACT_NONE, x1, D, 0, x1, D, 1, rows, D,
+                       c.mlp_hidden, -1.0, fold ? &pp : nullptr);
         if (r) return r;
       }
     }
@@ -863,10 +958,20 @@ static int build_steps(hvit_plan* p) {
   // 5. final LayerNorm + to_feature_map, written straight into the first decoder concat buffer (NHWC == [B,N,C])
   {
     const float *gf = w.lnf_g, *bfp = w.lnf_b;
-    p->steps.push_back([=](const Ctx& k) { return launch_layernorm(tok, gf, bfp, ln, dt, M, D, eps, k.stream); });
-    p->tag("transformer.norm", "layernorm", 0, 0, static_cast<double>(M) * D * (4 + g.es));
     const CatGeo& k0 = g.cat[0];
-    r = add_linear(p, "to_feature_map", ln, D, w.tofm_w, w.tofm_b, ACT_NONE, nullptr, 0, 0, at<void>(p, "cat0"), k0.Ccat, !bf, M, k0.Cx, D);
+    const void* Wt = w.tofm_w;
+    const float* ct = w.tofm_b;
+    LnFold ctf;
+    if (fold) {
+      r = fold_weights(w.tofm_w, gf, bfp, w.tofm_b, k0.Cx, &Wt, &ctf);
+      if (r) return r;
+      ct = ctf.g + k0.Cx;
+    } else {
+      p->steps.push_back([=](const Ctx& k) { return launch_layernorm(tok, gf, bfp, ln, dt, M, D, eps, k.stream); });
+      p->tag("transformer.norm", "layernorm", 0, 0, static_cast<double>(M) * D * (4 + g.es));
+    }
+    r = add_linear(p, "to_feature_map", ln, D, Wt, ct, ACT_NONE, nullptr, 0, 0, at<void>(p, "cat0"), k0.Ccat, !bf, M, k0.Cx, D,
+                   -1.0, fold ? &ctf : nullptr);
     if (r) return r;
     if (g.n_samples > 0) {
       // variable-length batch: rows are in each clip's own token order -> scatter them back onto the [Hp, Wp] grid
@@ -874,7 +979,8 @@ static int build_steps(hvit_plan* p) {
       tmp.cfg = p->cfg;
       void* rows = at<void>(p, "tofm_rows");
       void* cat0 = at<void>(p, "cat0");
-      r = add_linear(&tmp, "to_feature_map", ln, D, w.tofm_w, w.tofm_b, ACT_NONE, nullptr, 0, 0, rows, k0.Cx, !bf, M, k0.Cx, D);
+      r = add_linear(&tmp, "to_feature_map", ln, D, Wt, ct, ACT_NONE, nullptr, 0, 0, rows, k0.Cx, !bf, M, k0.Cx, D, -1.0,
+                     fold ? &ctf : nullptr);
       if (r) return r;
       const Step fixed = p->steps.back(), var = tmp.steps[0];
       const int Hp = g.Hp, Wp = g.Wp, Cx = k0.Cx, Ccat = k0.Ccat;
@@ -1292,6 +1398,60 @@ int hvit_gemm_16(const void* a, int lda, const void* w, const float* scale, cons
   r = make_out_maps(q, &mp);
   if (r) return r;
   return launch_igemm_tc2(q, mp, bn, num_sms(), reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hvit_linear_ln_producer_16(const void* a, int lda, const void* w, const float* bias, float* x, void* x16_out,
+                               float* stats_out, int M, int N, int K, int f16, void* stream) {
+  int r = require_sm100();
+  if (r) return r;
+  IgemmParams q = ig_zero();
+  q.f16 = f16 ? 1 : 0;
+  q.mode = IG_PLAIN;
+  q.M = M; q.N = N; q.K = K;
+  q.shift = bias; q.act = ACT_NONE; q.residual = x; q.ldr = N;
+  q.out = x; q.ldc = N; q.out_f32 = 1;
+  q.ln_x16_out = x16_out; q.ld16 = N; q.ln_stats_out = stats_out;
+  IgemmMaps mp;
+  const int bn = pick_block_n(N);
+  r = tmap_matrix(&mp.a, a, q.f16, M, K, lda, 128);
+  if (r) return r;
+  r = tmap_matrix(&mp.b, w, q.f16, N, K, K, bn / 2);
+  if (r) return r;
+  r = make_out_maps(q, &mp);
+  if (r) return r;
+  return launch_igemm_tc2(q, mp, bn, num_sms(), reinterpret_cast<cudaStream_t>(stream));
+}
+
+int hvit_linear_ln_consumer_16(const void* x16, const float* stats, int slots, const void* w, const float* gamma,
+                               const float* beta, const float* bias, float eps, int act, void* out, int ldc, int M, int N,
+                               int K, int f16, void* w_scratch, float* gc_scratch, void* stream) {
+  int r = require_sm100();
+  if (r) return r;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  r = launch_ln_fold(w, gamma, beta, bias, w_scratch, gc_scratch, gc_scratch + N, f16 ? DT_F16 : DT_BF16, N, K, st);
+  if (r) return r;
+  IgemmParams q = ig_zero();
+  q.f16 = f16 ? 1 : 0;
+  q.mode = IG_PLAIN;
+  q.M = M; q.N = N; q.K = K;
+  q.shift = gc_scratch + N; q.act = act;
+  q.out = out; q.ldc = ldc; q.out_f32 = 0;
+  q.ln_stats_in = stats; q.ln_g = gc_scratch; q.ln_slots = slots; q.ln_eps = eps;
+  IgemmMaps mp;
+  const int bn = pick_block_n(N);
+  r = tmap_matrix(&mp.a, x16, q.f16, M, K, K, 128);
+  if (r) return r;
+  r = tmap_matrix(&mp.b, w_scratch, q.f16, N, K, K, bn / 2);
+  if (r) return r;
+  r = make_out_maps(q, &mp);
+  if (r) return r;
+  return launch_igemm_tc2(q, mp, bn, num_sms(), st);
+}
+
+int hvit_rowstats_16(const float* x, void* x16_out, float* stats_out, int rows, int D, int slots, int f16, void* stream) {
+  int r = require_sm100();
+  if (r) return r;
+  return launch_rowstats(x, x16_out, stats_out, f16 ? DT_F16 : DT_BF16, rows, D, slots, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int hvit_gemm_f32(const float* a, int lda, const float* w, const float* scale, const float* shift, int act,

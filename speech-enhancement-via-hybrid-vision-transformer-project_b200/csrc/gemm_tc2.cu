@@ -58,7 +58,7 @@ struct Cfg2 {
   // the plain 16-bit one (EPI_LIN16: qkv, to_feature_map, skip projections) and the fp32 one of long-K GEMMs
   // (EPI_F32D: fc2) - each epilogue group gives up its second staging buffer (it waits for the previous TMA store
   // to release the buffer).
-  static constexpr bool DEEP = BLOCK_N == 256 && (EPI == 1 || EPI == 8);
+  static constexpr bool DEEP = BLOCK_N == 256 && (EPI == 1 || EPI == 8 || EPI == 9);
   static constexpr int NBUF = DEEP ? 1 : 2;                   // staging buffers per epilogue group
   static constexpr bool HAS_SCALE = EPI == 0 || EPI == 3 || EPI == 4;  // epilogues with a per-channel multiplier
   static constexpr int STAGES = BLOCK_N == 256 ? (HAS_SCALE ? 4 : (DEEP ? 6 : 5)) : (BLOCK_N == 128 ? 6 : 7);
@@ -111,7 +111,9 @@ enum {
   EPI_F32 = 5,       // + shift (+ fp32 residual), fp32 out (proj, fc2, patch embedding)
   EPI_SH16 = 6,      // + shift, max(., lo), 16-bit out: 3x3 convs whose BN scale is folded into the weights
   EPI_SHPOOL16 = 7,  // EPI_SH16 + fused 2x2 max-pool
-  EPI_F32D = 8       // EPI_F32 without a TMA-loaded residual and K >= 1024 (fc2): deep-ring configuration
+  EPI_F32D = 8,      // EPI_F32 without a TMA-loaded residual and K >= 1024 (fc2): deep-ring configuration
+  EPI_LNLIN16 = 9,   // EPI_LIN16 with the preceding LayerNorm folded in (IgemmParams::ln_stats_in): qkv, to_feature_map
+  EPI_LNGELU16 = 10  // EPI_GELU16 with the preceding LayerNorm folded in: fc1
 };
 
 // GELU(v) = relu(v) - 0.5*|v|*erfc(|v|/sqrt2), erfc(u/sqrt2) = 2^q(u) with a weighted-minimax degree-5 q on [0, 6]
@@ -170,12 +172,22 @@ __device__ __forceinline__ uint32_t max_16x2(uint32_t a, uint32_t b) {
 template <int EPI, bool F16>
 __device__ __forceinline__ void emit16(const uint32_t (&cur)[32], const float* sc, const float* sh,
                                        const IgemmParams& p, float relu_lo, uint8_t* row, int half, int sw,
-                                       bool writer, int hxor = 16) {
+                                       bool writer, int hxor = 16, float ln_rs = 0.f, float ln_nmr = 0.f,
+                                       const float* ln_g = nullptr) {
   float v[32];
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const float4 b = *reinterpret_cast<const float4*>(sh + 4 * q);
-    if (EPI == EPI_LIN16 || EPI == EPI_GELU16 || EPI == EPI_SH16 || EPI == EPI_SHPOOL16) {
+    if (EPI == EPI_LNLIN16 || EPI == EPI_LNGELU16) {
+      // folded LayerNorm: rs_m * acc + (c_n - rs_m * mu_m * g_n); g is read through L1 (warp-uniform address)
+      const float4 gg = __ldg(reinterpret_cast<const float4*>(ln_g + 4 * q));
+      const float2 r2 = make_float2(ln_rs, ln_rs), m2 = make_float2(ln_nmr, ln_nmr);
+      const float2 t0 = __ffma2_rn(make_float2(gg.x, gg.y), m2, make_float2(b.x, b.y));
+      const float2 t1 = __ffma2_rn(make_float2(gg.z, gg.w), m2, make_float2(b.z, b.w));
+      const float2 s0 = __ffma2_rn(make_float2(__uint_as_float(cur[4 * q + 0]), __uint_as_float(cur[4 * q + 1])), r2, t0);
+      const float2 s1 = __ffma2_rn(make_float2(__uint_as_float(cur[4 * q + 2]), __uint_as_float(cur[4 * q + 3])), r2, t1);
+      v[4 * q + 0] = s0.x; v[4 * q + 1] = s0.y; v[4 * q + 2] = s1.x; v[4 * q + 3] = s1.y;
+    } else if (EPI == EPI_LIN16 || EPI == EPI_GELU16 || EPI == EPI_SH16 || EPI == EPI_SHPOOL16) {
       const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(cur[4 * q + 0]), __uint_as_float(cur[4 * q + 1])),
                                    make_float2(b.x, b.y));
       const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(cur[4 * q + 2]), __uint_as_float(cur[4 * q + 3])),
@@ -213,7 +225,7 @@ __device__ __forceinline__ void emit16(const uint32_t (&cur)[32], const float* s
     }
     return;
   }
-  if (EPI == EPI_GELU16) {
+  if (EPI == EPI_GELU16 || EPI == EPI_LNGELU16) {
 #pragma unroll
     for (int e = 0; e < 32; e += 2) {
       const float2 g = gelu_erfc5_x2(make_float2(v[e], v[e + 1]));
@@ -257,9 +269,21 @@ __device__ __forceinline__ void emit16(const uint32_t (&cur)[32], const float* s
 
 // 32 accumulator columns -> this thread's whole 128-byte staging row (fp32 output); the residual tile, when present,
 // has been TMA-loaded into the same (swizzled) staging row and is added in place.
-template <int EPI>
+// LNP (LayerNorm producer, IgemmParams::ln_stats_out): the final values x_new of these 32 columns also go out as 16-bit
+// (x16_dst: this row's 64 bytes, two 32-byte stores = whole sectors) and their mean / centred sum of squares is merged
+// into the running statistics (cnt, mean, M2) of this thread's row (Chan's update; two passes within the chunk).
+struct LnRun {
+  float cnt, mean, m2;
+};
+__device__ __forceinline__ void st_global_v8(void* dst, const uint32_t (&u)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(u[0]), "r"(u[1]), "r"(u[2]),
+               "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
+               : "memory");
+}
+template <int EPI, bool LNP = false>
 __device__ __forceinline__ void emit32(const uint32_t (&cur)[32], const float* sc, const float* sh,
-                                       const IgemmParams& p, float relu_lo, uint8_t* row, int sw, bool has_res) {
+                                       const IgemmParams& p, float relu_lo, uint8_t* row, int sw, bool has_res,
+                                       LnRun* ln = nullptr, uint8_t* x16_dst = nullptr) {
   float v[32];
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
@@ -292,13 +316,42 @@ __device__ __forceinline__ void emit32(const uint32_t (&cur)[32], const float* s
     for (int q = 0; q < 8; ++q) {
       float4* d = reinterpret_cast<float4*>(row + ((q ^ sw) << 4));
       const float4 r = *d;
-      *d = make_float4(v[4 * q + 0] + r.x, v[4 * q + 1] + r.y, v[4 * q + 2] + r.z, v[4 * q + 3] + r.w);
+      v[4 * q + 0] += r.x; v[4 * q + 1] += r.y; v[4 * q + 2] += r.z; v[4 * q + 3] += r.w;
+      *d = make_float4(v[4 * q + 0], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     }
   } else {
 #pragma unroll
     for (int q = 0; q < 8; ++q)
       *reinterpret_cast<float4*>(row + ((q ^ sw) << 4)) =
           make_float4(v[4 * q + 0], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+  if (LNP) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 32; ++e) a[e & 3] += v[e];
+    const float mc = ((a[0] + a[1]) + (a[2] + a[3])) * (1.0f / 32.0f);
+    float b2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      const float d = v[e] - mc;
+      b2[e & 3] = fmaf(d, d, b2[e & 3]);
+    }
+    const float m2c = (b2[0] + b2[1]) + (b2[2] + b2[3]);
+    const float tot = ln->cnt + 32.0f;
+    const float delta = mc - ln->mean;
+    const float f = 32.0f / tot;
+    ln->mean = fmaf(delta, f, ln->mean);
+    ln->m2 += fmaf(delta * delta, ln->cnt * f, m2c);
+    ln->cnt = tot;
+    if (x16_dst != nullptr) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t u[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) u[e] = pack_16x2(v[16 * h + 2 * e], v[16 * h + 2 * e + 1], p.f16);
+        st_global_v8(x16_dst + 32 * h, u);
+      }
+    }
   }
 }
 
@@ -554,6 +607,27 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
         cshift[e] = p.shift != nullptr ? __ldg(p.shift + c.n0 + e) : 0.0f;
       }
       constexpr int cbase = 0;
+      // folded LayerNorm (consumer): this thread's row statistics from the producer's per-slot partials (equal counts:
+      // the mean is the mean of the slot means, M2 adds the between-slot term)
+      constexpr bool kLnIn = EPI == EPI_LNLIN16 || EPI == EPI_LNGELU16;
+      float ln_rs = 0.f, ln_nmr = 0.f;
+      if (kLnIn && c.m0 + m < p.M) {
+        const float2* st = reinterpret_cast<const float2*>(p.ln_stats_in) + static_cast<long long>(c.m0 + m) * p.ln_slots;
+        float mean = 0.f, m2 = 0.f;
+        for (int i = 0; i < p.ln_slots; ++i) mean += __ldg(&st[i]).x;
+        mean /= static_cast<float>(p.ln_slots);
+        const float per = static_cast<float>(p.K / p.ln_slots);
+        for (int i = 0; i < p.ln_slots; ++i) {
+          const float2 t = __ldg(&st[i]);
+          const float d = t.x - mean;
+          m2 += fmaf(per * d, d, t.y);
+        }
+        ln_rs = 1.0f / sqrtf(m2 / static_cast<float>(p.K) + p.ln_eps);
+        ln_nmr = -mean * ln_rs;
+      }
+      const bool lnp = EPI == EPI_F32 && p.ln_stats_out != nullptr;  // LayerNorm producer (see emit32)
+      const bool ln_row_ok = c.m0 + m < p.M;
+      LnRun ln_run = {0.f, 0.f, 0.f};
       if (has_res && issuer && J > 0) {
         // residual tile of the first block -> staging buffer; the NEXT tile's residual blocks -> L2, so that the
         // per-block TMA loads of the next tile are L2 hits instead of exposed HBM latency
@@ -611,12 +685,13 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
           }
           tmem_ld_wait(ra);
           tmem_ld32(t_base + blk * 64 + 32, rb);
-          if (p.f16) emit16<EPI, true>(ra, sc, sh, p, relu_lo, row, 0, sw, writer);
-          else emit16<EPI, false>(ra, sc, sh, p, relu_lo, row, 0, sw, writer);
+          const float* lg = kLnIn ? p.ln_g + c.n0 + blk * 64 : nullptr;
+          if (p.f16) emit16<EPI, true>(ra, sc, sh, p, relu_lo, row, 0, sw, writer, 16, ln_rs, ln_nmr, lg);
+          else emit16<EPI, false>(ra, sc, sh, p, relu_lo, row, 0, sw, writer, 16, ln_rs, ln_nmr, lg);
           tmem_ld_wait(rb);
           if (j + 1 < J) tmem_ld32(t_base + (blk + 2) * 64, ra);
-          if (p.f16) emit16<EPI, true>(rb, sc + 32, sh + 32, p, relu_lo, row, 1, sw, writer);
-          else emit16<EPI, false>(rb, sc + 32, sh + 32, p, relu_lo, row, 1, sw, writer);
+          if (p.f16) emit16<EPI, true>(rb, sc + 32, sh + 32, p, relu_lo, row, 1, sw, writer, 16, ln_rs, ln_nmr, lg + 32);
+          else emit16<EPI, false>(rb, sc + 32, sh + 32, p, relu_lo, row, 1, sw, writer, 16, ln_rs, ln_nmr, lg + 32);
           finish_block(j, buf, c.n0 + blk * 64);
         }
       } else {
@@ -631,14 +706,25 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
           if (has_res) mbar_wait(&res_bar[grp * 2 + (it & 1)], (it >> 1) & 1);
           tmem_ld_wait(cur);
           if (j + 1 < J) tmem_ld32(t_base + (blk + 2) * 32, nxt);
-          emit32<EPI>(cur, cscale + cbase + blk * 32, cshift + cbase + blk * 32, p, relu_lo, buf + srow * 128, sw,
-                      has_res);
+          if (EPI == EPI_F32 && lnp) {
+            uint8_t* x16 = ln_row_ok ? reinterpret_cast<uint8_t*>(p.ln_x16_out) +
+                                           (static_cast<long long>(c.m0 + m) * p.ld16 + c.n0 + blk * 32) * 2
+                                     : nullptr;
+            emit32<EPI, true>(cur, cscale + cbase + blk * 32, cshift + cbase + blk * 32, p, relu_lo, buf + srow * 128, sw,
+                              has_res, &ln_run, x16);
+          } else {
+            emit32<EPI>(cur, cscale + cbase + blk * 32, cshift + cbase + blk * 32, p, relu_lo, buf + srow * 128, sw,
+                        has_res);
+          }
           finish_block(j, buf, c.n0 + blk * 32);
         };
         for (int j = 0; j < J; j += 2) {
           block32(j, ra, rb);
           if (j + 1 < J) block32(j + 1, rb, ra);
         }
+        if (lnp && ln_row_ok)  // this group's 128 columns of the row: slot = 2 * n_tile + group
+          reinterpret_cast<float2*>(p.ln_stats_out)[static_cast<long long>(c.m0 + m) * (p.N >> 7) + 2 * (c.n0 / BLOCK_N) + grp] =
+              make_float2(ln_run.mean, ln_run.m2);
       }
       tc_fence_before();
       __syncwarp();
@@ -1100,6 +1186,7 @@ int pick_epi(const IgemmParams& p) {
     return (p.K >= 1024 && p.mode == IG_PLAIN && (p.residual == nullptr || p.res_inplace)) ? EPI_F32D : EPI_F32;
   }
   if (p.residual != nullptr) return EPI_GENERIC;
+  if (p.ln_stats_in != nullptr) return p.act == ACT_GELU ? EPI_LNGELU16 : EPI_LNLIN16;
   if (p.pool) return (p.act != ACT_GELU) ? EPI_BNPOOL16 : EPI_GENERIC;
   if (p.scale != nullptr) return (p.act != ACT_GELU) ? EPI_BN16 : EPI_GENERIC;
   if (p.act == ACT_GELU) return EPI_GELU16;
@@ -1117,6 +1204,8 @@ int launch_n(const IgemmParams& p, const IgemmMaps& maps, int a, int n_tiles_n, 
     case EPI_BNPOOL16: return launch_impl2<BLOCK_N, EPI_BNPOOL16>(p, maps, a, n_tiles_n, b, num_sms, stream);
     case EPI_F32: return launch_impl2<BLOCK_N, EPI_F32>(p, maps, a, n_tiles_n, b, num_sms, stream);
     case EPI_F32D: return launch_impl2<BLOCK_N, EPI_F32D>(p, maps, a, n_tiles_n, b, num_sms, stream);
+    case EPI_LNLIN16: return launch_impl2<BLOCK_N, EPI_LNLIN16>(p, maps, a, n_tiles_n, b, num_sms, stream);
+    case EPI_LNGELU16: return launch_impl2<BLOCK_N, EPI_LNGELU16>(p, maps, a, n_tiles_n, b, num_sms, stream);
     default: return launch_impl2<BLOCK_N, EPI_GENERIC>(p, maps, a, n_tiles_n, b, num_sms, stream);
   }
 }
@@ -1150,7 +1239,19 @@ int launch_igemm_tc2(const IgemmParams& p, const IgemmMaps& maps, int block_n, i
   pp.a_prefetch = 0;
   if (const char* e = getenv("HVIT_A_PREFETCH")) pp.a_prefetch = atoi(e);
   pp.res_inplace = (p.residual != nullptr && p.residual == p.out && p.ldr == p.ldc && p.res_mod == 0 &&
-                    !(p.dbg & 32)) ? 1 : 0;
+                    !(p.dbg & 32) && p.ln_stats_out == nullptr) ? 1 : 0;
+  if (p.ln_stats_out != nullptr &&
+      !(p.mode == IG_PLAIN && p.out_f32 && p.residual != nullptr && p.act == ACT_NONE && p.scale == nullptr && !p.pool &&
+        block_n == 256 && p.ln_x16_out != nullptr && p.ld16 % 16 == 0)) {
+    set_error("igemm_tc2: the LayerNorm-producer epilogue needs a plain fp32 GEMM with a residual and 256-column tiles");
+    return -1;
+  }
+  if (p.ln_stats_in != nullptr &&
+      !(p.mode == IG_PLAIN && !p.out_f32 && p.residual == nullptr && p.scale == nullptr && !p.pool && p.ln_g != nullptr &&
+        p.shift != nullptr && p.ln_slots > 0 && p.K % p.ln_slots == 0 && (p.act == ACT_NONE || p.act == ACT_GELU))) {
+    set_error("igemm_tc2: the folded-LayerNorm epilogue needs a plain 16-bit GEMM with bias, g vector and row statistics");
+    return -1;
+  }
   const int n_tiles_n = p.N / block_n;
   long long group_tiles;
   int groups = 1;

@@ -734,6 +734,66 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
   }
 }
 
+// LayerNorm folded into the GEMMs (IgemmParams::ln_*): what is left of a stand-alone nn.LayerNorm is the 16-bit copy of
+// the row and its statistics in the producer epilogue's format - `slots` (mean, M2) pairs per row, each standing for
+// D / slots columns; here every slot carries the row's exact two-pass mean and an equal share of its M2.  Used for the
+// first block (the residual stream comes from the patch embedding / the variable-length token compaction).
+template <typename T, int V>
+__global__ void rowstats_kernel(const float* __restrict__ x, T* __restrict__ x16, float2* __restrict__ stats, int rows,
+                                int D, int slots) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + static_cast<long long>(row) * D;
+  T* orow = x16 + static_cast<long long>(row) * D;
+  float4 v[V];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    v[k] = *reinterpret_cast<const float4*>(xr + k * 128 + lane * 4);
+    s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    const float yv[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+    st4<T>(orow + k * 128 + lane * 4, yv);
+  }
+  const float mean = warp_sum(s) / D;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  q = warp_sum(q);
+  if (lane < slots) stats[static_cast<long long>(row) * slots + lane] = make_float2(mean, q / slots);
+}
+
+// Weights of a linear layer that follows a LayerNorm, for the folded form (one warp per output feature n):
+//   W'[n,k] = 16-bit(gamma[k] * W[n,k]),  g[n] = sum_k W'[n,k] (of the ROUNDED values the GEMM multiplies with),
+//   c[n] = bias[n] + sum_k beta[k] * W[n,k]
+template <typename T>
+__global__ void ln_fold_kernel(const T* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ bias, T* __restrict__ wp, float* __restrict__ g,
+                               float* __restrict__ c, int N, int K) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float gs = 0.f, cs = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float wv = static_cast<float>(w[static_cast<long long>(n) * K + k]);
+    const T r = static_cast<T>(gamma[k] * wv);
+    wp[static_cast<long long>(n) * K + k] = r;
+    gs += static_cast<float>(r);
+    cs = fmaf(beta[k], wv, cs);
+  }
+  gs = warp_sum(gs);
+  cs = warp_sum(cs);
+  if (lane == 0) {
+    g[n] = gs;
+    c[n] = (bias != nullptr ? bias[n] : 0.f) + cs;
+  }
+}
+
 // skip feature [B, Hs(pitch), Ws, C] -> bilinear sample at decoder resolution [B*Hd*Wd, C]
 // (the 1x1 projection is applied AFTER sampling; exact because bilinear weights sum to 1 - hybrid_vit.py:377-386)
 template <typename T>
@@ -1270,6 +1330,48 @@ int launch_layernorm(const float* x, const float* g, const float* b, void* out, 
   else if (dt == DT_F16) ln_dispatch<__half>(x, g, b, out, rows, D, eps, s);
   else ln_dispatch<float>(x, g, b, out, rows, D, eps, s);
   return check_launch("layernorm");
+}
+
+int launch_rowstats(const float* x, void* x16, float* stats, int dt, int rows, int D, int slots, cudaStream_t s) {
+  if (dt == DT_F32 || D % 128 != 0 || D > 1024 || slots < 1 || slots > 32) {
+    set_error("rowstats: needs a 16-bit output, D a multiple of 128 (<= 1024) and 1..32 slots (D=%d slots=%d)", D, slots);
+    return -1;
+  }
+  const int grid = (rows + 7) / 8;
+  float2* st = reinterpret_cast<float2*>(stats);
+#define HVIT_RS(TT, VV) launch_pdl(rowstats_kernel<TT, VV>, dim3(grid), dim3(256), 0, s, x, reinterpret_cast<TT*>(x16), st, rows, D, slots)
+  const int V = D / 128;
+  if (dt == DT_F16) {
+    switch (V) {
+      case 1: HVIT_RS(__half, 1); break; case 2: HVIT_RS(__half, 2); break; case 3: HVIT_RS(__half, 3); break;
+      case 4: HVIT_RS(__half, 4); break; case 5: HVIT_RS(__half, 5); break; case 6: HVIT_RS(__half, 6); break;
+      case 7: HVIT_RS(__half, 7); break; default: HVIT_RS(__half, 8); break;
+    }
+  } else {
+    switch (V) {
+      case 1: HVIT_RS(bf16, 1); break; case 2: HVIT_RS(bf16, 2); break; case 3: HVIT_RS(bf16, 3); break;
+      case 4: HVIT_RS(bf16, 4); break; case 5: HVIT_RS(bf16, 5); break; case 6: HVIT_RS(bf16, 6); break;
+      case 7: HVIT_RS(bf16, 7); break; default: HVIT_RS(bf16, 8); break;
+    }
+  }
+#undef HVIT_RS
+  return check_launch("rowstats");
+}
+
+int launch_ln_fold(const void* w, const float* gamma, const float* beta, const float* bias, void* wp, float* g, float* c,
+                   int dt, int N, int K, cudaStream_t s) {
+  const int grid = (N + 7) / 8;
+  if (dt == DT_F16)
+    ln_fold_kernel<__half><<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(w), gamma, beta, bias,
+                                                reinterpret_cast<__half*>(wp), g, c, N, K);
+  else if (dt == DT_BF16)
+    ln_fold_kernel<bf16><<<grid, 256, 0, s>>>(reinterpret_cast<const bf16*>(w), gamma, beta, bias,
+                                              reinterpret_cast<bf16*>(wp), g, c, N, K);
+  else {
+    set_error("ln_fold: 16-bit weights only");
+    return -1;
+  }
+  return check_launch("ln_fold");
 }
 
 int launch_skip_sample(const void* src, int dt, int B, int Hs, int HsPitch, int Ws, int C, int Hd, int Wd,

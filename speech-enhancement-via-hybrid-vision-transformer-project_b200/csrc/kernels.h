@@ -81,6 +81,20 @@ struct IgemmParams {
   int halo;             // IG_CONV3 on the tensor-core path: input tile + halo staged once in shared memory (8x16 tile;
                         // maps.a is then the 5-D un-swizzled halo map), see igemm_halo_kernel
   long long* prof;      // diagnostics only (HVIT_PROF): per-CTA cycle counters [gridDim.x][16], or null
+  // ---- LayerNorm folded into the GEMMs on either side of it (IG_PLAIN, tcgen05 path)
+  // producer (fp32 output WITH a loaded residual: x_new = x + f(..)): besides x_new the epilogue writes the 16-bit copy
+  // x16 and, per row and per 128-column slot (slot = 2 * n_tile + epilogue group), the slot's mean and centred sum of
+  // squares M2 - the partial statistics nn.LayerNorm needs, merged exactly (Chan) by the consumer
+  void* ln_x16_out;     // [M, ld16] 16-bit or null
+  int ld16;
+  float* ln_stats_out;  // [M, N / 128, 2] or null
+  // consumer (16-bit output): A = x16, weights pre-multiplied by gamma; the epilogue evaluates
+  //   LN(x) W^T + b = rs_m * acc_mn - (rs_m * mu_m) * g_n + c_n,   g_n = sum_k W'_nk,  c_n = b_n + sum_k beta_k W_nk
+  // with (mu_m, rs_m) from ln_stats_in; c is passed as `shift`
+  const float* ln_stats_in;  // [M, ln_slots, 2] or null
+  const float* ln_g;         // [N]
+  int ln_slots;
+  float ln_eps;
   FastDiv fd_ntn, fd_ppg, fd_tw, fd_th;  // set by launch_igemm_tc2: n tiles, pairs per group, tiles_w, tiles_h
 };
 
@@ -138,6 +152,12 @@ int launch_stem_tc(const float* x, const unsigned* mag_max_bits, const void* apa
                    const CUtensorMap& tmap_out, int f16, int B, int H, int W, int num_sms, cudaStream_t s);
 int launch_layernorm(const float* x, const float* g, const float* b, void* out, int dt, int rows, int D,
                      float eps, cudaStream_t s);
+// LayerNorm folded into the neighbouring GEMMs (IgemmParams::ln_*): 16-bit copy + per-slot row statistics of an fp32
+// matrix, and the gamma / beta folding of the consumer's weights
+int launch_rowstats(const float* x, void* x16, float* stats /*[rows, slots, 2]*/, int dt, int rows, int D, int slots,
+                    cudaStream_t s);
+int launch_ln_fold(const void* w /*[N,K] 16-bit*/, const float* gamma, const float* beta, const float* bias /*nullable*/,
+                   void* wp /*[N,K] 16-bit*/, float* g /*[N]*/, float* c /*[N]*/, int dt, int N, int K, cudaStream_t s);
 int launch_skip_sample(const void* src, int dt, int B, int Hs, int HsPitch, int Ws, int C, int Hd, int Wd,
                        void* dst, cudaStream_t s, const int* geo = nullptr, int geo_src_idx = 0, int geo_dst_idx = 0);
 int launch_head(const void* x, int dt, const float* w /*[9][C]*/, int B, int H, int W, int C, float* logits,

@@ -219,6 +219,63 @@ def test_layernorm(rows, D):
         assert U.rel_err(out16.float(), ref) < OUT_TOL[kind]
 
 
+def _ln_merge(st, D):
+    """(mean, var) of every row from the per-slot (mean, M2) partials, as the consumer epilogue merges them."""
+    S = st.shape[1]
+    mean = st[..., 0].double().mean(1)
+    m2 = st[..., 1].double().sum(1) + (D / S) * ((st[..., 0].double() - mean[:, None]) ** 2).sum(1)
+    return mean, m2 / D
+
+
+@pytest.mark.parametrize("kind", ["bf16", "fp16"])
+@pytest.mark.parametrize("M,D,K,N2,act", [(1000, 512, 512, 1536, 0), (300, 512, 2048, 2048, 2), (257, 768, 768, 256, 0),
+                                          (31744, 512, 512, 1536, 0)])
+def test_layernorm_folded_into_gemms(M, D, K, N2, act, kind):
+    """x += a W^T + b (producer: fp32 x, 16-bit copy, row statistics) followed by act(LN(x) W2^T + b2) (consumer)
+    against fp64 nn.LayerNorm / nn.Linear: attention.py:258-262 (x = x + attn(norm1(x)); x = x + mlp(norm2(x)))."""
+    f16 = 1 if kind == "fp16" else 0
+    a = _rand(M, K, seed=40).to(DT16[kind])
+    w = _rand(D, K, seed=41, scale=K ** -0.5).to(DT16[kind])
+    bias = _rand(D, seed=42)
+    x0 = _rand(M, D, seed=43, scale=2.0) + 0.7          # non-zero row means
+    x = x0.clone()
+    x16 = torch.full((M, D), float("nan"), dtype=DT16[kind], device=DEV)
+    S = D // 128
+    stats = torch.full((M, S, 2), float("nan"), dtype=torch.float32, device=DEV)
+    _lib.check(U.lib().hvit_linear_ln_producer_16(U.P(a), K, U.P(w), U.P(bias), U.P(x), U.P(x16), U.P(stats), M, D, K, f16,
+                                                  U.stream()), "ln_producer")
+    U.sync()
+    xref = x0.double() + a.double() @ w.double().T + bias.double()
+    assert U.rel_err(x, xref) < 1e-5
+    assert torch.equal(x16, x.to(DT16[kind]))                       # the 16-bit copy is the rounded fp32 result
+    mean, var = _ln_merge(stats, D)
+    assert (mean - x.double().mean(1)).abs().max() < 1e-5 * (1 + x.double().mean(1).abs().max())
+    assert ((var - x.double().var(1, unbiased=False)).abs() / var).max() < 1e-4
+    # rowstats of the same matrix must merge to the same statistics
+    x16b = torch.empty_like(x16); stats_b = torch.empty_like(stats)
+    _lib.check(U.lib().hvit_rowstats_16(U.P(x), U.P(x16b), U.P(stats_b), M, D, S, f16, U.stream()), "rowstats")
+    U.sync()
+    mean_b, var_b = _ln_merge(stats_b, D)
+    assert torch.equal(x16b, x16)
+    assert (mean_b - mean).abs().max() < 1e-5 and ((var_b - var).abs() / var).max() < 1e-4
+    # consumer
+    g, be = 1.0 + 0.3 * _rand(D, seed=44), 0.2 * _rand(D, seed=45)
+    w2 = _rand(N2, D, seed=46, scale=D ** -0.5).to(DT16[kind])
+    b2 = _rand(N2, seed=47)
+    out = torch.full((M, N2), float("nan"), dtype=DT16[kind], device=DEV)
+    wsc = torch.empty((N2, D), dtype=DT16[kind], device=DEV)
+    gc = torch.empty(2 * N2, dtype=torch.float32, device=DEV)
+    _lib.check(U.lib().hvit_linear_ln_consumer_16(U.P(x16), U.P(stats), S, U.P(w2), U.P(g), U.P(be), U.P(b2), 1e-5, act,
+                                                  U.P(out), N2, M, N2, D, f16, U.P(wsc), U.P(gc), U.stream()), "ln_consumer")
+    U.sync()
+    ln = F.layer_norm(x.double(), (D,), g.double(), be.double(), 1e-5)
+    ref = ln @ w2.double().T + b2.double()
+    if act == 2:
+        ref = F.gelu(ref)
+    assert torch.isfinite(out.float()).all()
+    assert U.rel_err(out.float(), ref) < OUT_TOL[kind]
+
+
 @pytest.mark.parametrize("n", [64000, 16000, 9001, 2048])
 def test_stft_istft_against_oracle(oracle, n):
     _, noisy = oracle.synth_clip(seed=n, n_samples=n)
