@@ -199,6 +199,14 @@ size_t hvit_metrics_scratch_bytes(int B, int n_samples);
 int hvit_metrics(const float* clean_dev, const float* enhanced_dev, int B, int n_samples, const int* n_valid_dev,
                  void* scratch_dev, size_t scratch_bytes, double* out_dev, void* stream);
 
+/* Spectrogram losses of the validation forward (training/trainer.py:207-251 Trainer.validate with
+ * training/losses.py:286-387 CombinedLoss): pred / target fp32 [B, n_per] on the device -> sums_dev [B,5] fp64 =
+ * {sum |p' - t'|, sum (p' - t')^2, sum p^2, sum t^2, sum p t} per sample, p' = ln(p + 1e-8) when use_log (losses.py:46-57),
+ * from which L1 / MSE (mean over all elements) and the reference's STOI proxy (1 - cosine similarity per sample,
+ * losses.py:126-141) follow on the host. */
+int hvit_spec_loss(const float* pred_dev, const float* target_dev, int B, long long n_per, int use_log, double* sums_dev,
+                   void* stream);
+
 /* Introspection for tests: byte offset (into the workspace), and dims of a named internal buffer.
  * Names: "enc<i>", "tokens", "ln", "qkv", "attn", "mlp", "cat<i>", "logits" (debug mode), "tanh", and for enhance
  * plans "model_out" (debug mode), "mag", "max_val", "mag_max".  dims receives up to 4 ints; returns the rank or

@@ -82,6 +82,7 @@ SYMBOLS = {
     "hvit_varlen_min_samples": (_I, [_VP]),
     "hvit_metrics_scratch_bytes": (_SZ, [_I, _I]),
     "hvit_metrics": (_I, [_VP, _VP, _I, _I, _VP, _VP, _SZ, _VP, _VP]),
+    "hvit_spec_loss": (_I, [_VP, _VP, _I, C.c_longlong, _I, _VP, _VP]),
     "hvit_plan_buffer": (_I, [_VP, C.c_char_p, C.POINTER(_SZ), C.POINTER(_I * 4), C.POINTER(_I)]),
     "hvit_plan_launch_count": (_I, [_VP, _I]),
     "hvit_plan_tokens": (_I, [_VP, C.POINTER(_I), C.POINTER(_I)]),

@@ -898,11 +898,15 @@ static int build_steps(hvit_plan* p) {
     const size_t probs_off = static_cast<size_t>(l) * B * heads * Np * Np;
     if (bf) {
       p->steps.push_back([=](const Ctx& k) {
-        if (k.probs != nullptr) {
-          const int e = launch_attn_probs_16(qkv, f16, k.probs + probs_off, B, Np, heads, D, scale, k.stream);
+        // return_attentions=True: the tensor-core kernel writes the maps itself up to 1 280 tokens; beyond that the
+        // CUDA-core kernel materialises them next to it
+        float* pr = k.probs != nullptr ? k.probs + probs_off : nullptr;
+        if (pr != nullptr && Np > 1280) {
+          const int e = launch_attn_probs_16(qkv, f16, pr, B, Np, heads, D, scale, k.stream);
           if (e) return e;
+          pr = nullptr;
         }
-        return launch_attn_tc(tq, to, f16, B, Np, heads, D, scale, k.stream, nullptr, k.geo);
+        return launch_attn_tc(tq, to, f16, B, Np, heads, D, scale, k.stream, nullptr, k.geo, pr);
       });
       p->tag(L + ".attn", "attn_tc", 4.0 * B * heads * Np * Np * 64.0, 4.0 * B * heads * Np * Np * 64.0,
              static_cast<double>(M) * 4 * D * g.es);

@@ -129,11 +129,16 @@ __device__ __forceinline__ float exp_pack_row(uint32_t (&s)[128], float scale_lo
   return (sum0.x + sum0.y) + (sum1.x + sum1.y);
 }
 
-template <bool PROF>
+// PROBS (return_attentions=True, hybrid_vit.py:422-450): the softmax groups also write the attention probabilities
+// [B, heads, N, N] fp32 - un-normalised p = 2^(s - m_used) while the key blocks stream by (m_used is the lazily updated
+// maximum of that block), then, once the row's final maximum and sum are known, each thread rescales its own row in
+// place (its 2 KB are still in L2).  At most PROBS_MAX_KV key blocks.
+constexpr int PROBS_MAX_KV = 10;
+template <bool PROF, bool PROBS = false>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out, int N,
                int D, int heads, int n_items, float scale_log2, int f16, long long* prof, const int* __restrict__ geo,
-               int pingpong) {
+               int pingpong, float* __restrict__ probs) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B swizzle needs 1024-byte aligned tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -369,6 +374,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
       const int Nb = clip_tokens(b);
       const int nkv = (Nb + 127) / 128;
       float m_used = -INFINITY, l_run = 0.f;
+      float mhist[PROBS ? PROBS_MAX_KV : 1];
+      const int qrow = q0 + w * 128 + row;
+      float* prow = PROBS ? probs + ((static_cast<long long>(b) * heads + h) * N + qrow) * N : nullptr;
       for (int j = 0; j < nkv; ++j, ++blk) {
         const int nvalid = min(128, Nb - j * 128);
         const long long c0 = tick();
@@ -441,6 +449,31 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
         // (measured: 74.9 -> 67.0 us stand-alone at 64 x 496 tokens, 397 -> 341 us at 1 248; a NON-strict variant - a shared-
         // memory lock taken with atomicCAS, per scheduler or per group - ran at 133 us: the spinning lanes cost more than
         // the strict order loses at item boundaries)
+        if (PROBS) {
+          mhist[j] = m_used;
+          if (qrow < N) {
+            // (the same biased exponent as exp_pack_row, so exactly the terms that enter l_run - the 2^-112 is undone by
+            // normalising with 1 / l_run below)
+            const float mb = m_used + ebias;
+            const int kmax = min(128, N - j * 128);   // keys of this block that exist in the [N, N] map
+            float* dst = prow + j * 128;
+            if ((N & 3) == 0) {
+#pragma unroll
+              for (int i = 0; i < 128; i += 4) {
+                if (i < kmax)
+                  *reinterpret_cast<float4*>(dst + i) =
+                      make_float4(ex2_approx(fmaf(__uint_as_float(s[i]), scale_log2, -mb)),
+                                  ex2_approx(fmaf(__uint_as_float(s[i + 1]), scale_log2, -mb)),
+                                  ex2_approx(fmaf(__uint_as_float(s[i + 2]), scale_log2, -mb)),
+                                  ex2_approx(fmaf(__uint_as_float(s[i + 3]), scale_log2, -mb)));
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 128; ++i)
+                if (i < kmax) dst[i] = ex2_approx(fmaf(__uint_as_float(s[i]), scale_log2, -mb));
+            }
+          }
+        }
         if (pingpong) named_bar_sync(3 + w, 256);
         l_run += exp_pack_row(s, scale_log2, m_used + ebias, emul, p_row, sw);
         // (group B's very last hand-over has no taker: skipped, so no barrier is left half-arrived at exit)
@@ -486,6 +519,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
         tma_store_3d(&tmap_out, o_stage, h * 64, q0 + w * 128, b);
         tma_store_commit();
       }
+      if (PROBS && qrow < N) {  // normalise this thread's row of the map: p_j * 2^(m_j - m_final) / l
+        for (int j = 0; j < nkv; ++j) {
+          const float f = ex2_approx(mhist[j] - m_used) * (1.0f / l_run);
+          const int kmax = min(128, N - j * 128);
+          float* dst = prow + j * 128;
+          if ((N & 3) == 0) {
+            for (int i = 0; i < kmax; i += 4) {
+              float4 v = *reinterpret_cast<float4*>(dst + i);
+              v.x *= f; v.y *= f; v.z *= f; v.w *= f;
+              *reinterpret_cast<float4*>(dst + i) = v;
+            }
+          } else {
+            for (int i = 0; i < kmax; ++i) dst[i] *= f;
+          }
+        }
+      }
       ++itw;
       t_fin += tick() - f0;
     }
@@ -505,7 +554,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
 }  // namespace
 
 int launch_attn_tc(const CUtensorMap& tmap_qkv, const CUtensorMap& tmap_out, int f16, int B, int N, int heads, int D,
-                   float scale, cudaStream_t stream, long long* prof, const int* geo) {
+                   float scale, cudaStream_t stream, long long* prof, const int* geo, float* probs) {
   if (D != heads * 64) {
     set_error("attention: head_dim must be 64 (D=%d heads=%d)", D, heads);
     return -1;
@@ -514,6 +563,8 @@ int launch_attn_tc(const CUtensorMap& tmap_qkv, const CUtensorMap& tmap_out, int
   if (once.first()) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     if (e != cudaSuccess) {
       once.retry();
       set_error("attn_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -532,11 +583,22 @@ int launch_attn_tc(const CUtensorMap& tmap_qkv, const CUtensorMap& tmap_out, int
   // that is a property of N alone
   static const int pp_env = [] { const char* e = getenv("HVIT_ATTN_PINGPONG"); return e != nullptr ? atoi(e) : 1; }();
   const int pingpong = (pp_env != 0 && ((N + 255) / 256 - 1) * 256 + 128 < N) ? 1 : 0;
-  const cudaError_t le =
-      prof != nullptr ? launch_pdl(attn_tc_kernel<true>, dim3(grid), dim3(AT_THREADS), AT_SMEM, stream, tmap_qkv, tmap_out,
-                                   N, D, heads, static_cast<int>(items), scale * 1.4426950408889634f, f16, prof, geo, pingpong)
-                      : launch_pdl(attn_tc_kernel<false>, dim3(grid), dim3(AT_THREADS), AT_SMEM, stream, tmap_qkv, tmap_out,
-                                   N, D, heads, static_cast<int>(items), scale * 1.4426950408889634f, f16, prof, geo, pingpong);
+  if (probs != nullptr && (N + 127) / 128 > PROBS_MAX_KV) {
+    set_error("attn_tc: attention maps on the tensor-core path need N <= %d (N=%d)", PROBS_MAX_KV * 128, N);
+    return -1;
+  }
+  const float sl2 = scale * 1.4426950408889634f;
+  const int ni = static_cast<int>(items);
+  cudaError_t le;
+  if (probs != nullptr)
+    le = launch_pdl(attn_tc_kernel<false, true>, dim3(grid), dim3(AT_THREADS), AT_SMEM, stream, tmap_qkv, tmap_out, N, D,
+                    heads, ni, sl2, f16, prof, geo, pingpong, probs);
+  else if (prof != nullptr)
+    le = launch_pdl(attn_tc_kernel<true>, dim3(grid), dim3(AT_THREADS), AT_SMEM, stream, tmap_qkv, tmap_out, N, D, heads,
+                    ni, sl2, f16, prof, geo, pingpong, probs);
+  else
+    le = launch_pdl(attn_tc_kernel<false>, dim3(grid), dim3(AT_THREADS), AT_SMEM, stream, tmap_qkv, tmap_out, N, D, heads,
+                    ni, sl2, f16, prof, geo, pingpong, probs);
   if (le != cudaSuccess) {
     set_error("attn_tc: %s", cudaGetErrorString(le));
     return -4;

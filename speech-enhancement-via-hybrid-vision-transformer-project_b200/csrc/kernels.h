@@ -116,7 +116,8 @@ int launch_igemm_f32(const IgemmParams& p, const float* A, int lda, const float*
 // ---------------------------------------------------------------------------------------------
 // geo (nullable): per-clip valid token count geo[b][GEO_NTOK] - keys >= N_b are masked, whole key blocks beyond it skipped
 int launch_attn_tc(const CUtensorMap& tmap_qkv, const CUtensorMap& tmap_out /*[B*N, D] 16-bit*/, int f16, int B, int N, int heads, int D, float scale,
-                   cudaStream_t stream, long long* prof = nullptr, const int* geo = nullptr);
+                   cudaStream_t stream, long long* prof = nullptr, const int* geo = nullptr,
+                   float* probs /*nullable [B,h,N,N]: attention maps from the same kernel, N <= 1280*/ = nullptr);
 int launch_attn_f32(const float* qkv, float* out, float* probs /*nullable [B,h,N,N]*/, int B, int N, int heads, int D,
                     float scale, cudaStream_t stream, const int* geo = nullptr);
 // probabilities only (return_attentions=True slow path) from bf16 qkv

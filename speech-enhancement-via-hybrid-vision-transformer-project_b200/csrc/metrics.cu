@@ -147,6 +147,35 @@ __global__ void metrics_finalize_kernel(const double* __restrict__ acc, int B, i
 
 using namespace hvit;
 
+namespace hvit {
+namespace {
+// Spectrogram losses of the validation forward (training/losses.py:15-85 SpectrogramLoss, :88-141 STOILoss as the
+// reference defines it - one minus the cosine similarity of the flattened spectrograms -, :286-387 CombinedLoss):
+// per sample b, fp64 sums {sum |p' - t'|, sum (p' - t')^2, sum p^2, sum t^2, sum p t}, p' / t' = ln(. + 1e-8) with
+// log compression, the raw values otherwise.
+__global__ void spec_loss_kernel(const float* __restrict__ pred, const float* __restrict__ target, long long n_per,
+                                 int use_log, double* __restrict__ sums) {
+  const int b = blockIdx.y;
+  const float* p = pred + b * n_per;
+  const float* t = target + b * n_per;
+  double s1 = 0, s2 = 0, pp = 0, tt = 0, pt = 0;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_per;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float pv = p[i], tv = t[i];
+    const float a = use_log ? logf(pv + 1e-8f) : pv, c = use_log ? logf(tv + 1e-8f) : tv;
+    const double d = static_cast<double>(a) - static_cast<double>(c);
+    s1 += fabs(d); s2 += d * d;
+    pp += static_cast<double>(pv) * pv; tt += static_cast<double>(tv) * tv; pt += static_cast<double>(pv) * tv;
+  }
+  s1 = warp_sum_d(s1); s2 = warp_sum_d(s2); pp = warp_sum_d(pp); tt = warp_sum_d(tt); pt = warp_sum_d(pt);
+  if ((threadIdx.x & 31) == 0) {
+    double* a = sums + b * 5;
+    atomicAdd(a + 0, s1); atomicAdd(a + 1, s2); atomicAdd(a + 2, pp); atomicAdd(a + 3, tt); atomicAdd(a + 4, pt);
+  }
+}
+}  // namespace
+}  // namespace hvit
+
 extern "C" {
 
 size_t hvit_metrics_scratch_bytes(int B, int n_samples) {
@@ -198,6 +227,24 @@ int hvit_metrics(const float* clean_dev, const float* enhanced_dev, int B, int n
   metrics_lsd_kernel<<<dim3(T, B), 128, 0, s>>>(mag_a, mag_b, T, n_samples, n_valid_dev, acc);
   metrics_finalize_kernel<<<(B + 127) / 128, 128, 0, s>>>(acc, B, n_samples, n_valid_dev, out_dev);
   return check_launch("hvit_metrics");
+}
+
+
+int hvit_spec_loss(const float* pred_dev, const float* target_dev, int B, long long n_per, int use_log,
+                   double* sums_dev, void* stream) {
+  using namespace hvit;
+  if (pred_dev == nullptr || target_dev == nullptr || sums_dev == nullptr || B <= 0 || n_per <= 0) {
+    set_error("hvit_spec_loss: bad arguments (B=%d n_per=%lld)", B, n_per);
+    return HVIT_E_ARG;
+  }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(sums_dev, 0, static_cast<size_t>(B) * 5 * sizeof(double), s) != cudaSuccess)
+    return check_launch("hvit_spec_loss(memset)");
+  const long long per_block = 256 * 8;
+  long long bx = (n_per + per_block - 1) / per_block;
+  if (bx > 64) bx = 64;
+  spec_loss_kernel<<<dim3(static_cast<unsigned>(bx), B), 256, 0, s>>>(pred_dev, target_dev, n_per, use_log, sums_dev);
+  return check_launch("hvit_spec_loss");
 }
 
 }  // extern "C"

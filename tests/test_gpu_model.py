@@ -138,6 +138,22 @@ def test_return_attentions(oracle, precision):
     assert torch.equal(y, y2)
 
 
+def test_return_attentions_default_model_4s(oracle):
+    """Attention maps from the tensor-core kernel itself (fast path of return_attentions=True, hybrid_vit.py:422-450) at
+    the headline geometry: 496 tokens = four key blocks with a partial tail, lazy rescales included."""
+    cfg, sd, model = _model(oracle, {}, seed=8, precision="fp16")
+    x = torch.rand(1, 1, 257, 501, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        ref, rattn = oracle.hybrid_vit_forward(sd, x, cfg, return_attentions=True)
+    y, attn = model(x.cuda(), return_attentions=True)
+    assert len(attn) == cfg["num_layers"] and attn[0].shape == rattn[0].shape == (1, 8, 496, 496)
+    for a, r in zip(attn, rattn):
+        assert float((a.cpu() - r).abs().max()) < 1e-3
+        assert torch.allclose(a.sum(-1).cpu(), torch.ones(a.shape[:-1]), atol=1e-4)
+    assert oracle.max_rel_err(y.cpu().numpy(), ref.numpy()) <= TOL["fp16"]
+    assert torch.equal(y, model(x.cuda()))
+
+
 @pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("name", ["tiny_0p5s", "tiny_ragged", "default_1s", "default_2s"])
 def test_enhance_matches_reference_golden(oracle, golden, precision, name):
@@ -663,3 +679,78 @@ def test_workspace_poison_and_canaries(oracle, precision):
         assert bool((raw[:off] == 0xA5).all()) and bool((raw[off + nbytes:] == 0xA5).all()), "write outside the workspace"
     finally:
         lib.hvit_plan_destroy(handle)
+
+
+# ------------------------------------------------------------------------------------------------ validation forward (f4)
+def _loss_pair(seed, shape):
+    g = torch.Generator().manual_seed(seed)
+    target = torch.rand(*shape, generator=g)
+    pred = (target + 0.1 * torch.randn(*shape, generator=g)).clamp_min(0.0)
+    return pred, target
+
+
+def test_losses_match_reference_goldens():
+    """Device-reduced spectrogram losses against values produced by the reference's own training/losses.py
+    (tests/golden/make_golden_losses.py)."""
+    import json
+    from hvit_b200.training import CombinedLoss, SpectrogramLoss, STOILoss
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "losses_v1.json")))
+    n = 0
+    for c in gold["cases"]:
+        if c["kind"] == "validate_loop":
+            continue
+        pred, target = _loss_pair(c["seed"], c["shape"])
+        pred, target = pred.cuda(), target.cuda()
+        if c["kind"] == "combined":
+            total, comps = CombinedLoss(**c["kwargs"])(pred, target, return_components=True)
+            assert set(comps) == set(c["components"])
+            for k, v in c["components"].items():
+                assert abs(comps[k] - v) <= 2e-6 * max(1.0, abs(v)), (c, k, comps[k], v)
+            assert abs(float(total) - c["total"]) <= 2e-6 * max(1.0, abs(c["total"]))
+        elif c["kind"] == "spectrogram":
+            v = float(SpectrogramLoss(c["loss_type"], c["reduction"], c["use_log_compression"])(pred, target))
+            assert abs(v - c["value"]) <= 3e-6 * max(1.0, abs(c["value"])), (c, v)   # fp32 'sum' in the reference
+        else:
+            v = float(STOILoss(c["reduction"])(pred, target))
+            assert abs(v - c["value"]) <= 2e-6, (c, v)
+        n += 1
+    assert n >= 29
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_validator_matches_reference_loop(oracle, precision):
+    """Trainer.validate re-host: mean over batches of CombinedLoss(model(noisy_spec), clean_spec) - the model through
+    the CUDA plan, against the oracle forward + the reference's loss arithmetic restated with torch on the CPU."""
+    import torch.nn.functional as F
+    from hvit_b200.training import Validator, create_loss_function
+    cfg, sd, model = _model(oracle, TINY, seed=3, precision=precision)
+    g = torch.Generator().manual_seed(5)
+    batches = [dict(noisy_spec=torch.rand(b, 1, 257, 63, generator=g), clean_spec=torch.rand(b, 1, 257, 63, generator=g))
+               for b in (2, 2, 1)]
+    crit = create_loss_function({"loss": {"l1_weight": 1.0, "mse_weight": 0.5, "stoi_weight": 0.1}})
+    got = Validator(model, batches, crit, device="cuda").validate()
+    tot = 0.0
+    for bt in batches:
+        with torch.no_grad():
+            y = oracle.hybrid_vit_forward(sd, bt["noisy_spec"], cfg)
+        t = bt["clean_spec"]
+        stoi = (1.0 - (F.normalize(y.flatten(1), dim=1) * F.normalize(t.flatten(1), dim=1)).sum(1)).mean()
+        tot += float(F.l1_loss(y, t) + 0.5 * F.mse_loss(y, t) + 0.1 * stoi)
+    ref = tot / len(batches)
+    assert set(got) == {"loss"}
+    assert abs(got["loss"] - ref) <= ({"fp32": 2e-5, "fp16": 2e-3}[precision]) * abs(ref)
+    assert Validator(model, None).validate() == {}
+
+
+def test_validate_loop_golden_averaging():
+    """The averaging of trainer.py:229-249 on fixed (pred, target) batches against the reference-generated value."""
+    import json
+    from hvit_b200.training import create_loss_function
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "losses_v1.json")))
+    c = [x for x in gold["cases"] if x["kind"] == "validate_loop"][0]
+    crit = create_loss_function({"loss": {"l1_weight": 1.0, "mse_weight": 0.0, "stoi_weight": 0.1}})
+    tot = 0.0
+    for seed, shape in zip(c["seeds"], c["shapes"]):
+        pred, target = _loss_pair(seed, shape)
+        tot += float(crit(pred.cuda(), target.cuda()))
+    assert abs(tot / len(c["seeds"]) - c["loss"]) <= 2e-6

@@ -165,3 +165,31 @@ def test_metrics_match_reference_golden():
         allm = M.compute_all_metrics(clean, enh, noisy)
         assert set(allm) == {"pesq", "stoi", "sisdr", "snr", "segsnr", "lsd", "pesq_improvement", "stoi_improvement",
                              "sisdr_improvement", "snr_improvement"}
+
+
+def test_loss_goldens_are_reproduced_by_the_formulas_the_device_path_uses():
+    """tests/golden/losses_v1.json (values from the reference's training/losses.py) against the closed forms the CUDA
+    reduction implements (L1 / MSE means, 1 - cosine similarity), in fp64 on the CPU: pins the arithmetic of the
+    validation forward without a GPU."""
+    import json
+    import os
+    import torch
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "losses_v1.json")))
+
+    def pair(seed, shape):
+        g = torch.Generator().manual_seed(seed)
+        target = torch.rand(*shape, generator=g)
+        pred = (target + 0.1 * torch.randn(*shape, generator=g)).clamp_min(0.0)
+        return pred.double(), target.double()
+
+    for c in gold["cases"]:
+        if c["kind"] != "combined":
+            continue
+        kw = dict(l1_weight=1.0, mse_weight=0.0, stoi_weight=0.1, perceptual_weight=0.0, use_log_compression=False)
+        kw.update(c["kwargs"])
+        p, t = pair(c["seed"], c["shape"])
+        a, b = (torch.log(p.float() + 1e-8).double(), torch.log(t.float() + 1e-8).double()) if kw["use_log_compression"] else (p, t)
+        cos = (p.flatten(1) * t.flatten(1)).sum(1) / (p.flatten(1).norm(dim=1).clamp_min(1e-12) * t.flatten(1).norm(dim=1).clamp_min(1e-12))
+        total = (kw["l1_weight"] * (a - b).abs().mean() + kw["mse_weight"] * ((a - b) ** 2).mean()
+                 + kw["stoi_weight"] * (1.0 - cos).mean() + kw["perceptual_weight"] * (p - t).abs().mean())
+        assert abs(float(total) - c["total"]) <= 2e-6 * max(1.0, abs(c["total"])), (c["kwargs"], float(total), c["total"])
