@@ -594,7 +594,13 @@ static int add_linear(hvit_plan* p, const std::string& name, const void* A, int 
   }
   if (p->cfg.precision != HVIT_PREC_FP32) {
     IgemmMaps mp;
-    const int bn = pick_block_n(N);
+    int bn = pick_block_n(N);
+    if (K >= 1024 && out_f32 && lf == nullptr) {
+      if (const char* e = getenv("HVIT_FC2_BN")) {  // experiment: narrower tiles for the long-K fp32 GEMM (fc2)
+        const int v = atoi(e);
+        if ((v == 64 || v == 128 || v == 256) && N % v == 0) bn = v;
+      }
+    }
     int r = tmap_matrix(&mp.a, A, q.f16, M, K, lda, 128);
     if (r) return r;
     r = tmap_matrix(&mp.b, W, q.f16, N, K, K, bn / 2);
@@ -725,7 +731,11 @@ static int add_patch_embed(hvit_plan* p, const void* in, int B, int H, int Hpitc
     q.tiles_w = (q.Wp + q.Wt - 1) / q.Wt;
     q.tiles_h = (q.Hp + q.Ht - 1) / q.Ht;
     IgemmMaps mp;
-    const int bn = pick_block_n(D);
+    int bn = pick_block_n(D);
+    if (const char* e = getenv("HVIT_PATCH_BN")) {  // experiment: narrower tiles -> finer wave quantisation
+      const int v = atoi(e);
+      if ((v == 64 || v == 128 || v == 256) && D % v == 0) bn = v;
+    }
     int r = tmap_patch(&mp.a, in, q.f16, B, q.Hq, W, C, patch, q.Wp, q.Wt, q.Ht);
     if (r) return r;
     r = tmap_matrix(&mp.b, pw, q.f16, D, q.K, q.K, bn / 2);
