@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 2400 python -m pytest tests -m gpu -q -x > gpurun_out/r2v_tests.log 2>&1
+echo "rc=$?" >> gpurun_out/r2v_tests.log
+tail -5 gpurun_out/r2v_tests.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+bash tools/r2_profile.sh r2
