@@ -239,7 +239,7 @@ int hvit_gemm_16(const void* a_dev, int lda, const void* w_dev, const float* sca
  *   producer  x[M,N] += a[M,K] * w[N,K]^T + bias  (fp32, in place), plus x16_out = 16-bit(x) and, per row and per
  *             128-column slot, the slot's (mean, centred sum of squares) in stats_out [M, N/128, 2]; N % 256 == 0
  *   consumer  out = act(LayerNorm(x; gamma, beta, eps) * w[N,K]^T + bias) from x16 and the statistics; w_scratch
- *             ([N,K] 16-bit) and gc_scratch ([2N] fp32) receive the gamma-scaled weights and the g / c vectors
+ *             ([N,K] 16-bit) and gc_scratch ([N] fp32) receive the gamma-scaled, k-centred weights and the c vector
  *   rowstats  x16 and statistics of an existing fp32 matrix (the first block's input) */
 int hvit_linear_ln_producer_16(const void* a_dev, int lda, const void* w_dev, const float* bias_dev, float* x_dev,
                                void* x16_out_dev, float* stats_out_dev, int M, int N, int K, int f16, void* stream);

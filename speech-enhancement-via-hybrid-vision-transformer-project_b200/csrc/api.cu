@@ -223,10 +223,11 @@ static int mlp_panels(int M, int hidden, int es, int tensor_core) {
 }
 
 // LayerNorm folded into the GEMMs around it (16-bit modes): needs 256-column producer tiles (statistics slots of 128
-// columns) and the register-resident row-statistics kernel.  OFF by default - measured slower at 64 x 4 s (3.15 vs 2.90
-// ms per step, profiles/r2_experiments.json): the 13 LayerNorm launches it removes cost 39 us per layer, but the
-// residual update then has to LOAD the old rows (proj 33.6 -> 57.9 us, fc2 68.9 -> 78.2 us; the TMA reduce-add of the
-// unfolded path never brings them into the SM) and the consumers' epilogues grow (qkv +12 us, fc1 +27 us).
+// columns) and the register-resident row-statistics kernel.  OFF by default - measured a wash at 64 x 4 s (device leg
+// 2.96 vs 3.01 ms per step, end-to-end leg 85.7k vs 86.4k audio-s/s; profiles/r2_experiments.json): the 13 LayerNorm
+// launches it removes cost 37 us per layer, but the residual update then has to LOAD the old rows - 65 MB more L2 -> SM
+// traffic per GEMM on kernels that already sit on that delivery rate (proj 32 -> 51 us, fc2 65 -> 78 us; the TMA
+// reduce-add of the unfolded path never brings them into the SM) - and the consumers' epilogues grow (qkv +3, fc1 +10 us).
 // HVIT_LN_FOLD=1 builds plans with it (read at plan creation; parity-tested both ways).
 static bool ln_fold_enabled(int precision, int D, int layers) {
   const char* e = getenv("HVIT_LN_FOLD");
@@ -516,7 +517,7 @@ static int build_geometry(const hvit_model_cfg& c, int B, int F, int T, int n_sa
     const size_t Cx0 = g.cat[0].Cx;
     add("lnstats", 4, 3, g.M, c.embed_dim / 128, 2, 0, M * (c.embed_dim / 128) * 2);
     add("lnfold_w", 2, 1, 0, 0, 0, 0, c.num_layers * wl + Cx0 * D_);
-    add("lnfold_v", 4, 1, 0, 0, 0, 0, 2 * (c.num_layers * (3 * D_ + c.mlp_hidden) + Cx0));
+    add("lnfold_v", 4, 1, 0, 0, 0, 0, c.num_layers * (3 * D_ + c.mlp_hidden) + Cx0);
   }
   add("qkv", g.es, 2, g.M, 3 * c.embed_dim, 0, 0, M * 3 * c.embed_dim);
   add("attn", g.es, 2, g.M, c.embed_dim, 0, 0, M * c.embed_dim);
@@ -567,7 +568,7 @@ static IgemmParams ig_zero() {
 struct LnFold {
   // consumer
   const float* stats_in = nullptr;
-  const float* g = nullptr;
+  const float* c = nullptr;   // folded bias vector (passed to the GEMM as its shift)
   int slots = 0;
   float eps = 0.f;
   // producer
@@ -589,7 +590,7 @@ static int add_linear(hvit_plan* p, const std::string& name, const void* A, int 
   q.out = out; q.ldc = ldc; q.out_f32 = out_f32;
   q.f16 = p->cfg.precision == HVIT_PREC_FP16;
   if (lf != nullptr) {
-    q.ln_stats_in = lf->stats_in; q.ln_g = lf->g; q.ln_slots = lf->slots; q.ln_eps = lf->eps;
+    q.ln_stats_in = lf->stats_in; q.ln_slots = lf->slots; q.ln_eps = lf->eps;
     q.ln_x16_out = lf->x16_out; q.ld16 = lf->ld16; q.ln_stats_out = lf->stats_out;
   }
   if (p->cfg.precision != HVIT_PREC_FP32) {
@@ -872,14 +873,13 @@ static int build_steps(hvit_plan* p) {
   // gamma / beta folded copies of a consumer's weights, derived once on the setup stream (like the stem's matrices)
   auto fold_weights = [&](const void* W, const float* gamma, const float* beta, const float* bias, int N, const void** Wp,
                           LnFold* lf) -> int {
-    float* gv = fold_v;
-    float* cv = fold_v + N;
-    const int e = launch_ln_fold(W, gamma, beta, bias, fold_w, gv, cv, dt, N, D, p->setup_stream);
+    float* cv = fold_v;
+    const int e = launch_ln_fold(W, gamma, beta, bias, fold_w, cv, dt, N, D, p->setup_stream);
     *Wp = fold_w;
-    lf->stats_in = lnstats; lf->g = gv; lf->slots = slots; lf->eps = eps;
+    lf->stats_in = lnstats; lf->c = cv; lf->slots = slots; lf->eps = eps;
     lf->x16_out = nullptr; lf->ld16 = 0; lf->stats_out = nullptr;
     fold_w += static_cast<size_t>(N) * D * 2;
-    fold_v += 2 * N;
+    fold_v += N;
     return e;
   };
   LnFold prod;  // producer side of proj / fc2
@@ -897,7 +897,7 @@ static int build_steps(hvit_plan* p) {
       LnFold cq;
       r = fold_weights(w.qkv_w[l], g1, b1, w.qkv_b[l], 3 * D, &Wq, &cq);
       if (r) return r;
-      r = add_linear(p, L + ".qkv", ln, D, Wq, cq.g + 3 * D, ACT_NONE, nullptr, 0, 0, qkv, 3 * D, 0, M, 3 * D, D, -1.0, &cq);
+      r = add_linear(p, L + ".qkv", ln, D, Wq, cq.c, ACT_NONE, nullptr, 0, 0, qkv, 3 * D, 0, M, 3 * D, D, -1.0, &cq);
       if (r) return r;
     } else {
       p->steps.push_back([=](const Ctx& k) { return launch_layernorm(tok, g1, b1, ln, dt, M, D, eps, k.stream); });
@@ -937,7 +937,7 @@ static int build_steps(hvit_plan* p) {
     if (fold) {
       r = fold_weights(w.fc1_w[l], g2, b2, w.fc1_b[l], c.mlp_hidden, &W1, &cf);
       if (r) return r;
-      c1 = cf.g + c.mlp_hidden;
+      c1 = cf.c;
     } else {
       p->steps.push_back([=](const Ctx& k) { return launch_layernorm(tok, g2, b2, ln, dt, M, D, eps, k.stream); });
       p->tag(L + ".norm2", "layernorm", 0, 0, ln_bytes);
@@ -979,7 +979,7 @@ static int build_steps(hvit_plan* p) {
     if (fold) {
       r = fold_weights(w.tofm_w, gf, bfp, w.tofm_b, k0.Cx, &Wt, &ctf);
       if (r) return r;
-      ct = ctf.g + k0.Cx;
+      ct = ctf.c;
     } else {
       p->steps.push_back([=](const Ctx& k) { return launch_layernorm(tok, gf, bfp, ln, dt, M, D, eps, k.stream); });
       p->tag("transformer.norm", "layernorm", 0, 0, static_cast<double>(M) * D * (4 + g.es));
@@ -1442,15 +1442,15 @@ int hvit_linear_ln_consumer_16(const void* x16, const float* stats, int slots, c
   int r = require_sm100();
   if (r) return r;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  r = launch_ln_fold(w, gamma, beta, bias, w_scratch, gc_scratch, gc_scratch + N, f16 ? DT_F16 : DT_BF16, N, K, st);
+  r = launch_ln_fold(w, gamma, beta, bias, w_scratch, gc_scratch, f16 ? DT_F16 : DT_BF16, N, K, st);
   if (r) return r;
   IgemmParams q = ig_zero();
   q.f16 = f16 ? 1 : 0;
   q.mode = IG_PLAIN;
   q.M = M; q.N = N; q.K = K;
-  q.shift = gc_scratch + N; q.act = act;
+  q.shift = gc_scratch; q.act = act;
   q.out = out; q.ldc = ldc; q.out_f32 = 0;
-  q.ln_stats_in = stats; q.ln_g = gc_scratch; q.ln_slots = slots; q.ln_eps = eps;
+  q.ln_stats_in = stats; q.ln_slots = slots; q.ln_eps = eps;
   IgemmMaps mp;
   const int bn = pick_block_n(N);
   r = tmap_matrix(&mp.a, x16, q.f16, M, K, K, 128);

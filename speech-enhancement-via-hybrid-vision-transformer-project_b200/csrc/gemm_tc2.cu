@@ -172,20 +172,19 @@ __device__ __forceinline__ uint32_t max_16x2(uint32_t a, uint32_t b) {
 template <int EPI, bool F16>
 __device__ __forceinline__ void emit16(const uint32_t (&cur)[32], const float* sc, const float* sh,
                                        const IgemmParams& p, float relu_lo, uint8_t* row, int half, int sw,
-                                       bool writer, int hxor = 16, float ln_rs = 0.f, float ln_nmr = 0.f,
-                                       const float* ln_g = nullptr) {
+                                       bool writer, int hxor = 16, float ln_rs = 0.f) {
   float v[32];
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const float4 b = *reinterpret_cast<const float4*>(sh + 4 * q);
     if (EPI == EPI_LNLIN16 || EPI == EPI_LNGELU16) {
-      // folded LayerNorm: rs_m * acc + (c_n - rs_m * mu_m * g_n); g is read through L1 (warp-uniform address)
-      const float4 gg = __ldg(reinterpret_cast<const float4*>(ln_g + 4 * q));
-      const float2 r2 = make_float2(ln_rs, ln_rs), m2 = make_float2(ln_nmr, ln_nmr);
-      const float2 t0 = __ffma2_rn(make_float2(gg.x, gg.y), m2, make_float2(b.x, b.y));
-      const float2 t1 = __ffma2_rn(make_float2(gg.z, gg.w), m2, make_float2(b.z, b.w));
-      const float2 s0 = __ffma2_rn(make_float2(__uint_as_float(cur[4 * q + 0]), __uint_as_float(cur[4 * q + 1])), r2, t0);
-      const float2 s1 = __ffma2_rn(make_float2(__uint_as_float(cur[4 * q + 2]), __uint_as_float(cur[4 * q + 3])), r2, t1);
+      // folded LayerNorm: rs_m * acc + c_n (the weights are gamma-scaled AND centred over k, so acc is already the
+      // contraction of x - mean(x))
+      const float2 r2 = make_float2(ln_rs, ln_rs);
+      const float2 s0 = __ffma2_rn(make_float2(__uint_as_float(cur[4 * q + 0]), __uint_as_float(cur[4 * q + 1])), r2,
+                                   make_float2(b.x, b.y));
+      const float2 s1 = __ffma2_rn(make_float2(__uint_as_float(cur[4 * q + 2]), __uint_as_float(cur[4 * q + 3])), r2,
+                                   make_float2(b.z, b.w));
       v[4 * q + 0] = s0.x; v[4 * q + 1] = s0.y; v[4 * q + 2] = s1.x; v[4 * q + 3] = s1.y;
     } else if (EPI == EPI_LIN16 || EPI == EPI_GELU16 || EPI == EPI_SH16 || EPI == EPI_SHPOOL16) {
       const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(cur[4 * q + 0]), __uint_as_float(cur[4 * q + 1])),
@@ -326,17 +325,24 @@ __device__ __forceinline__ void emit32(const uint32_t (&cur)[32], const float* s
           make_float4(v[4 * q + 0], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   }
   if (LNP) {
-    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    // (packed fp32 pipes: 16 FADD2 for the sum, 16 FADD2 + 16 FFMA2 for the centred squares)
+    float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int e = 0; e < 32; ++e) a[e & 3] += v[e];
-    const float mc = ((a[0] + a[1]) + (a[2] + a[3])) * (1.0f / 32.0f);
-    float b2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int e = 0; e < 32; ++e) {
-      const float d = v[e] - mc;
-      b2[e & 3] = fmaf(d, d, b2[e & 3]);
+    for (int e = 0; e < 32; e += 4) {
+      a0 = __fadd2_rn(a0, make_float2(v[e], v[e + 1]));
+      a1 = __fadd2_rn(a1, make_float2(v[e + 2], v[e + 3]));
     }
-    const float m2c = (b2[0] + b2[1]) + (b2[2] + b2[3]);
+    const float mc = ((a0.x + a0.y) + (a1.x + a1.y)) * (1.0f / 32.0f);
+    const float2 nm = make_float2(-mc, -mc);
+    float2 q0 = make_float2(0.f, 0.f), q1 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int e = 0; e < 32; e += 4) {
+      const float2 d0 = __fadd2_rn(make_float2(v[e], v[e + 1]), nm);
+      const float2 d1 = __fadd2_rn(make_float2(v[e + 2], v[e + 3]), nm);
+      q0 = __ffma2_rn(d0, d0, q0);
+      q1 = __ffma2_rn(d1, d1, q1);
+    }
+    const float m2c = (q0.x + q0.y) + (q1.x + q1.y);
     const float tot = ln->cnt + 32.0f;
     const float delta = mc - ln->mean;
     const float f = 32.0f / tot;
@@ -587,6 +593,11 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
     // epilogue thread loads one channel of the tile before it waits for the accumulator; one named barrier per tile.
     float* cbuf = reinterpret_cast<float*>(consts);
 
+    const float ln_inv_slots = p.ln_slots > 0 ? 1.0f / static_cast<float>(p.ln_slots) : 0.f;
+    const float ln_per = p.ln_slots > 0 ? static_cast<float>(p.K / p.ln_slots) : 0.f;
+    const float ln_inv_k = 1.0f / static_cast<float>(p.K);
+    float2 ln_pre[4];          // folded LayerNorm: the next tile's statistics partials of this thread's row
+    bool ln_have_pre = false;
     uint32_t it = 0;  // running column-block counter of this group: buffer = it & 1, residual phase = (it >> 1) & 1
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -610,20 +621,40 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
       // folded LayerNorm (consumer): this thread's row statistics from the producer's per-slot partials (equal counts:
       // the mean is the mean of the slot means, M2 adds the between-slot term)
       constexpr bool kLnIn = EPI == EPI_LNLIN16 || EPI == EPI_LNGELU16;
-      float ln_rs = 0.f, ln_nmr = 0.f;
-      if (kLnIn && c.m0 + m < p.M) {
-        const float2* st = reinterpret_cast<const float2*>(p.ln_stats_in) + static_cast<long long>(c.m0 + m) * p.ln_slots;
-        float mean = 0.f, m2 = 0.f;
-        for (int i = 0; i < p.ln_slots; ++i) mean += __ldg(&st[i]).x;
-        mean /= static_cast<float>(p.ln_slots);
-        const float per = static_cast<float>(p.K / p.ln_slots);
-        for (int i = 0; i < p.ln_slots; ++i) {
-          const float2 t = __ldg(&st[i]);
-          const float d = t.x - mean;
-          m2 += fmaf(per * d, d, t.y);
+      float ln_rs = 0.f;
+      if (kLnIn) {
+        // (all partials in flight at once; and the NEXT tile's partials are loaded now into four registers, a tile ahead:
+        // a load consumed right away costs a full L2 round trip under load - measured 1 700 cycles per tile in this
+        // phase, which put the fc1 epilogue on the critical path; prefetch.global.L1 did not help)
+        float2 t[8];
+        if (ln_have_pre) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[i] = i < 4 ? ln_pre[i] : make_float2(0.f, 0.f);
+        } else {
+          const float2* st = reinterpret_cast<const float2*>(p.ln_stats_in) +
+                             static_cast<long long>(min(c.m0 + m, p.M - 1)) * p.ln_slots;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[i] = i < p.ln_slots ? __ldg(&st[i]) : make_float2(0.f, 0.f);
         }
-        ln_rs = 1.0f / sqrtf(m2 / static_cast<float>(p.K) + p.ln_eps);
-        ln_nmr = -mean * ln_rs;
+        // short dependency chains and no IEEE division / square root: this runs once per tile on the epilogue's
+        // critical path (the serial form - div, 8 dependent FMAs, div, sqrt, div - measured ~1 000 cycles per tile)
+        const float mean = (((t[0].x + t[1].x) + (t[2].x + t[3].x)) + ((t[4].x + t[5].x) + (t[6].x + t[7].x))) * ln_inv_slots;
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float d = t[i].x - mean;
+          e[i] = i < p.ln_slots ? fmaf(ln_per * d, d, t[i].y) : 0.f;
+        }
+        const float m2 = ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+        ln_rs = c.m0 + m < p.M ? rsqrtf(fmaf(m2, ln_inv_k, p.ln_eps)) : 0.f;
+        ln_have_pre = p.ln_slots <= 4 && ct + num_clusters < num_ctiles;
+        if (ln_have_pre) {
+          const TileCoord cn = decode_ctile(p, ct + num_clusters, n_tiles_n, BLOCK_N, pairs_per_group, rank);
+          const float2* st = reinterpret_cast<const float2*>(p.ln_stats_in) +
+                             static_cast<long long>(min(cn.m0 + m, p.M - 1)) * p.ln_slots;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ln_pre[i] = i < p.ln_slots ? __ldg(&st[i]) : make_float2(0.f, 0.f);
+        }
       }
       const bool lnp = EPI == EPI_F32 && p.ln_stats_out != nullptr;  // LayerNorm producer (see emit32)
       const bool ln_row_ok = c.m0 + m < p.M;
@@ -660,11 +691,6 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
           if (red_add) tma_reduce_add_4d(omap, buf, col0, o1, o2, o3);
           else if (!(p.dbg & 1)) tma_store_4d(omap, buf, col0, o1, o2, o3);
           tma_store_commit();
-          if (has_res && j + 1 < J) {        // residual tile of the next block -> the other buffer
-            const uint32_t nb = (it + 1) & 1;
-            mbar_expect_tx(&res_bar[grp * 2 + nb], STG_BUF_BYTES);
-            tma_load_4d(stg0 + nb * STG_BUF_BYTES, &maps.res, &res_bar[grp * 2 + nb], col0 + 2 * wcols, o1, o2, r3);
-          }
         }
         ++it;
       };
@@ -685,13 +711,12 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
           }
           tmem_ld_wait(ra);
           tmem_ld32(t_base + blk * 64 + 32, rb);
-          const float* lg = kLnIn ? p.ln_g + c.n0 + blk * 64 : nullptr;
-          if (p.f16) emit16<EPI, true>(ra, sc, sh, p, relu_lo, row, 0, sw, writer, 16, ln_rs, ln_nmr, lg);
-          else emit16<EPI, false>(ra, sc, sh, p, relu_lo, row, 0, sw, writer, 16, ln_rs, ln_nmr, lg);
+          if (p.f16) emit16<EPI, true>(ra, sc, sh, p, relu_lo, row, 0, sw, writer, 16, ln_rs);
+          else emit16<EPI, false>(ra, sc, sh, p, relu_lo, row, 0, sw, writer, 16, ln_rs);
           tmem_ld_wait(rb);
           if (j + 1 < J) tmem_ld32(t_base + (blk + 2) * 64, ra);
-          if (p.f16) emit16<EPI, true>(rb, sc + 32, sh + 32, p, relu_lo, row, 1, sw, writer, 16, ln_rs, ln_nmr, lg + 32);
-          else emit16<EPI, false>(rb, sc + 32, sh + 32, p, relu_lo, row, 1, sw, writer, 16, ln_rs, ln_nmr, lg + 32);
+          if (p.f16) emit16<EPI, true>(rb, sc + 32, sh + 32, p, relu_lo, row, 1, sw, writer, 16, ln_rs);
+          else emit16<EPI, false>(rb, sc + 32, sh + 32, p, relu_lo, row, 1, sw, writer, 16, ln_rs);
           finish_block(j, buf, c.n0 + blk * 64);
         }
       } else {
@@ -702,6 +727,14 @@ igemm_tc2_kernel(const __grid_constant__ IgemmMaps maps, const IgemmParams p, in
           if (C::NBUF == 1) {  // single staging buffer: the previous TMA store must have finished reading it
             if (issuer) tma_store_wait_read0();
             named_bar_sync(1 + grp, 128);
+          }
+          if (has_res && issuer && j + 1 < J) {
+            // residual tile of the NEXT block -> the other buffer, issued before this block is processed so that the load
+            // overlaps it (the buffer's last reader is the TMA store of block j - 1, committed a moment ago)
+            tma_store_wait_read0();
+            const uint32_t nb = (it + 1) & 1;
+            mbar_expect_tx(&res_bar[grp * 2 + nb], STG_BUF_BYTES);
+            tma_load_4d(stg0 + nb * STG_BUF_BYTES, &maps.res, &res_bar[grp * 2 + nb], c.n0 + (blk + 2) * 32, o1, o2, r3);
           }
           if (has_res) mbar_wait(&res_bar[grp * 2 + (it & 1)], (it >> 1) & 1);
           tmem_ld_wait(cur);
@@ -1247,9 +1280,9 @@ int launch_igemm_tc2(const IgemmParams& p, const IgemmMaps& maps, int block_n, i
     return -1;
   }
   if (p.ln_stats_in != nullptr &&
-      !(p.mode == IG_PLAIN && !p.out_f32 && p.residual == nullptr && p.scale == nullptr && !p.pool && p.ln_g != nullptr &&
-        p.shift != nullptr && p.ln_slots > 0 && p.K % p.ln_slots == 0 && (p.act == ACT_NONE || p.act == ACT_GELU))) {
-    set_error("igemm_tc2: the folded-LayerNorm epilogue needs a plain 16-bit GEMM with bias, g vector and row statistics");
+      !(p.mode == IG_PLAIN && !p.out_f32 && p.residual == nullptr && p.scale == nullptr && !p.pool &&
+        p.shift != nullptr && p.ln_slots > 0 && p.ln_slots <= 8 && p.K % p.ln_slots == 0 && (p.act == ACT_NONE || p.act == ACT_GELU))) {
+    set_error("igemm_tc2: the folded-LayerNorm epilogue needs a plain 16-bit GEMM with the c vector as shift and row statistics");
     return -1;
   }
   const int n_tiles_n = p.N / block_n;

@@ -769,29 +769,28 @@ __global__ void rowstats_kernel(const float* __restrict__ x, T* __restrict__ x16
 }
 
 // Weights of a linear layer that follows a LayerNorm, for the folded form (one warp per output feature n):
-//   W'[n,k] = 16-bit(gamma[k] * W[n,k]),  g[n] = sum_k W'[n,k] (of the ROUNDED values the GEMM multiplies with),
-//   c[n] = bias[n] + sum_k beta[k] * W[n,k]
+//   W''[n,k] = 16-bit(gamma[k] W[n,k] - mean_k(gamma W[n,:]))   (centred over k: sum_k x_k W''[n,k] = sum_k (x_k - mean x) gamma_k W[n,k])
+//   c[n]     = bias[n] + sum_k beta[k] W[n,k]
 template <typename T>
 __global__ void ln_fold_kernel(const T* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
-                               const float* __restrict__ bias, T* __restrict__ wp, float* __restrict__ g,
-                               float* __restrict__ c, int N, int K) {
+                               const float* __restrict__ bias, T* __restrict__ wp, float* __restrict__ c, int N, int K) {
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
   float gs = 0.f, cs = 0.f;
   for (int k = lane; k < K; k += 32) {
     const float wv = static_cast<float>(w[static_cast<long long>(n) * K + k]);
-    const T r = static_cast<T>(gamma[k] * wv);
-    wp[static_cast<long long>(n) * K + k] = r;
-    gs += static_cast<float>(r);
+    gs = fmaf(gamma[k], wv, gs);
     cs = fmaf(beta[k], wv, cs);
   }
   gs = warp_sum(gs);
   cs = warp_sum(cs);
-  if (lane == 0) {
-    g[n] = gs;
-    c[n] = (bias != nullptr ? bias[n] : 0.f) + cs;
+  const float mean = gs / K;
+  for (int k = lane; k < K; k += 32) {
+    const float wv = static_cast<float>(w[static_cast<long long>(n) * K + k]);
+    wp[static_cast<long long>(n) * K + k] = static_cast<T>(fmaf(gamma[k], wv, -mean));
   }
+  if (lane == 0) c[n] = (bias != nullptr ? bias[n] : 0.f) + cs;
 }
 
 // skip feature [B, Hs(pitch), Ws, C] -> bilinear sample at decoder resolution [B*Hd*Wd, C]
@@ -1358,15 +1357,15 @@ int launch_rowstats(const float* x, void* x16, float* stats, int dt, int rows, i
   return check_launch("rowstats");
 }
 
-int launch_ln_fold(const void* w, const float* gamma, const float* beta, const float* bias, void* wp, float* g, float* c,
-                   int dt, int N, int K, cudaStream_t s) {
+int launch_ln_fold(const void* w, const float* gamma, const float* beta, const float* bias, void* wp, float* c, int dt,
+                   int N, int K, cudaStream_t s) {
   const int grid = (N + 7) / 8;
   if (dt == DT_F16)
     ln_fold_kernel<__half><<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(w), gamma, beta, bias,
-                                                reinterpret_cast<__half*>(wp), g, c, N, K);
+                                                reinterpret_cast<__half*>(wp), c, N, K);
   else if (dt == DT_BF16)
     ln_fold_kernel<bf16><<<grid, 256, 0, s>>>(reinterpret_cast<const bf16*>(w), gamma, beta, bias,
-                                              reinterpret_cast<bf16*>(wp), g, c, N, K);
+                                              reinterpret_cast<bf16*>(wp), c, N, K);
   else {
     set_error("ln_fold: 16-bit weights only");
     return -1;

@@ -88,11 +88,11 @@ struct IgemmParams {
   void* ln_x16_out;     // [M, ld16] 16-bit or null
   int ld16;
   float* ln_stats_out;  // [M, N / 128, 2] or null
-  // consumer (16-bit output): A = x16, weights pre-multiplied by gamma; the epilogue evaluates
-  //   LN(x) W^T + b = rs_m * acc_mn - (rs_m * mu_m) * g_n + c_n,   g_n = sum_k W'_nk,  c_n = b_n + sum_k beta_k W_nk
-  // with (mu_m, rs_m) from ln_stats_in; c is passed as `shift`
+  // consumer (16-bit output): A = x16, weights W''[n,k] = gamma[k] W[n,k] - mean_k(gamma W[n,:]) (scaled and centred over
+  // k, so the contraction of x equals the contraction of x - mean(x)); the epilogue evaluates
+  //   LN(x) W^T + b = rs_m * acc_mn + c_n,   c_n = b_n + sum_k beta_k W_nk   (c is passed as `shift`)
+  // with rs_m = 1 / sqrt(var_m + eps) from ln_stats_in
   const float* ln_stats_in;  // [M, ln_slots, 2] or null
-  const float* ln_g;         // [N]
   int ln_slots;
   float ln_eps;
   FastDiv fd_ntn, fd_ppg, fd_tw, fd_th;  // set by launch_igemm_tc2: n tiles, pairs per group, tiles_w, tiles_h
@@ -158,7 +158,7 @@ int launch_layernorm(const float* x, const float* g, const float* b, void* out, 
 int launch_rowstats(const float* x, void* x16, float* stats /*[rows, slots, 2]*/, int dt, int rows, int D, int slots,
                     cudaStream_t s);
 int launch_ln_fold(const void* w /*[N,K] 16-bit*/, const float* gamma, const float* beta, const float* bias /*nullable*/,
-                   void* wp /*[N,K] 16-bit*/, float* g /*[N]*/, float* c /*[N]*/, int dt, int N, int K, cudaStream_t s);
+                   void* wp /*[N,K] 16-bit*/, float* c /*[N]*/, int dt, int N, int K, cudaStream_t s);
 int launch_skip_sample(const void* src, int dt, int B, int Hs, int HsPitch, int Ws, int C, int Hd, int Wd,
                        void* dst, cudaStream_t s, const int* geo = nullptr, int geo_src_idx = 0, int geo_dst_idx = 0);
 int launch_head(const void* x, int dt, const float* w /*[9][C]*/, int B, int H, int W, int C, float* logits,
