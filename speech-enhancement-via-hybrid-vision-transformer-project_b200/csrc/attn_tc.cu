@@ -446,9 +446,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_consta
         // Exp-phase token (named barriers 3 / 4, FA3-style ping-pong): the MUFU unit of a scheduler serves one softmax
         // warp at its full rate (10 cycles per score alone, 17 each when both groups' exp phases overlap), so the groups
         // take strict turns - group A's exp phase runs while group B loads / reduces its next block and vice versa.
-        // (measured: 74.9 -> 67.0 us stand-alone at 64 x 496 tokens, 397 -> 341 us at 1 248; a NON-strict variant - a shared-
-        // memory lock taken with atomicCAS, per scheduler or per group - ran at 133 us: the spinning lanes cost more than
-        // the strict order loses at item boundaries)
+        // (measured: 74.9 -> 67.0 us stand-alone at 64 x 496 tokens, 397 -> 341 us at 1 248.  NON-strict variants - a
+        // shared-memory lock per scheduler, per group, per group and key block; waiting by atomicCAS + __nanosleep, by
+        // plain polling, or blocked on an mbarrier that completes a phase per release - all ran at 131-146 us, twice
+        // slower than no lock: only the strict order keeps one group's exp phase inside the other's load / max phase)
         if (PROBS) {
           mhist[j] = m_used;
           if (qrow < N) {
