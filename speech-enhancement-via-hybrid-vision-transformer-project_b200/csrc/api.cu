@@ -378,6 +378,13 @@ struct hvit_plan {
   cudaStream_t setup_stream = nullptr; // stream of the one-time setup kernels (hvit_plan_create's argument)
   int device = -1;                    // device whose persisting-L2 carve-out this plan counts against (-1: none)
   int debug = 0;                      // keep test-only intermediates ("model_out", "logits"), see hvit_plan_set_debug
+  // Skip path on a side stream: skip.i.sample / skip.i.proj depend only on the encoder outputs, so they are forked off
+  // after the last encoder step and joined before the first decoder conv - three small, launch-bound sample + 1x1-GEMM
+  // pairs (~110 us at 64 x 4 s) that run under the transformer's LayerNorm / attention launches instead of in line.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int side_fork = -1, side_join = -1;  // step indices: fork before step side_fork, join before step side_join
+  std::vector<char> is_side;
   // tag the most recently pushed step(s)
   void tag(const std::string& name, const char* kernel, double aflops, double eflops, double bytes, int launches = 1) {
     while (meta.size() < steps.size()) meta.push_back(hvit::StepMeta{name, kernel, 0.0, 0.0, 0.0, 1});
@@ -1080,6 +1087,37 @@ static int build_steps(hvit_plan* p) {
   while (p->meta.size() < p->steps.size()) p->meta.push_back(StepMeta{"op", "op", 0, 0, 0, 1});
   p->launches_forward = 0;
   for (const StepMeta& m : p->meta) p->launches_forward += m.launches;
+  // skip path on a side stream (see hvit_plan): fork before the patch embedding, join before the first step after the
+  // first skip step (= the first decoder block).  HVIT_SIDE_STREAM=0 keeps everything in line.
+  {
+    const char* e = getenv("HVIT_SIDE_STREAM");
+    const bool on = !(e != nullptr && e[0] == '0');
+    p->is_side.assign(p->steps.size(), 0);
+    int first_skip = -1, fork = -1;
+    for (size_t i = 0; i < p->meta.size(); ++i) {
+      if (p->meta[i].name.compare(0, 5, "skip.") == 0) {
+        p->is_side[i] = 1;
+        if (first_skip < 0) first_skip = static_cast<int>(i);
+      }
+      if (p->meta[i].name == "patch_embed" && fork < 0) fork = static_cast<int>(i);
+    }
+    if (on && first_skip >= 0 && fork >= 0 && fork < first_skip) {
+      int join = first_skip;
+      while (join < static_cast<int>(p->steps.size()) && p->is_side[join]) ++join;
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      if (join < static_cast<int>(p->steps.size()) &&
+          cudaStreamCreateWithPriority(&p->side, cudaStreamNonBlocking, hi) == cudaSuccess &&
+          cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+          cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) == cudaSuccess) {
+        p->side_fork = fork;
+        p->side_join = join;
+      } else {
+        cudaGetLastError();
+        p->side_fork = -1;
+      }
+    }
+  }
   return HVIT_OK;
 }
 
@@ -1164,6 +1202,11 @@ void hvit_plan_destroy(hvit_plan* plan) {
       cudaGetLastError();
     }
   }
+  if (plan != nullptr) {
+    if (plan->ev_fork != nullptr) cudaEventDestroy(plan->ev_fork);
+    if (plan->ev_join != nullptr) cudaEventDestroy(plan->ev_join);
+    if (plan->side != nullptr) cudaStreamDestroy(plan->side);
+  }
   delete plan;
 }
 
@@ -1189,7 +1232,31 @@ static int run_steps(hvit_plan* p, const Ctx& c) {
   // the fp32 residual stream ("tokens") stays in L2 across the transformer blocks when the device allows it
   if (p->l2_pin_bytes > 0 && p->l2_pin_ratio > 0.f) l2_window_set(p->l2_pin_base, p->l2_pin_bytes, p->l2_pin_ratio);
   int r = HVIT_OK;
-  for (size_t i = 0; i < p->steps.size() && r == HVIT_OK; ++i) r = p->steps[i](c);
+  if (p->side != nullptr && p->side_fork >= 0) {
+    Ctx cs = c;
+    cs.stream = p->side;
+    for (size_t i = 0; i < p->steps.size() && r == HVIT_OK; ++i) {
+      if (static_cast<int>(i) == p->side_fork) {
+        if (cudaEventRecord(p->ev_fork, c.stream) != cudaSuccess || cudaStreamWaitEvent(p->side, p->ev_fork, 0) != cudaSuccess) {
+          set_error("side stream fork failed: %s", cudaGetErrorString(cudaGetLastError()));
+          r = HVIT_E_LAUNCH;
+          break;
+        }
+        for (size_t j = 0; j < p->steps.size() && r == HVIT_OK; ++j)
+          if (p->is_side[j]) r = p->steps[j](cs);
+        if (r == HVIT_OK && cudaEventRecord(p->ev_join, p->side) != cudaSuccess) r = HVIT_E_LAUNCH;
+        if (r != HVIT_OK) break;
+      }
+      if (static_cast<int>(i) == p->side_join && cudaStreamWaitEvent(c.stream, p->ev_join, 0) != cudaSuccess) {
+        set_error("side stream join failed: %s", cudaGetErrorString(cudaGetLastError()));
+        r = HVIT_E_LAUNCH;
+        break;
+      }
+      if (!p->is_side[i]) r = p->steps[i](c);
+    }
+  } else {
+    for (size_t i = 0; i < p->steps.size() && r == HVIT_OK; ++i) r = p->steps[i](c);
+  }
   l2_window_set(nullptr, 0, 0.f);
   return r;
 }
