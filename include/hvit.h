@@ -170,7 +170,13 @@ int hvit_plan_set_debug(hvit_plan* plan, int on);
 /* HybridViT.forward (models/hybrid_vit.py:396-469), eval mode.
  *   x_dev: fp32 [B,1,F,T]   y_dev: fp32 [B,1,F,T]
  *   attn_probs_dev: null, or fp32 [num_layers][B][heads][N][N] to receive the softmax maps
- *                   (return_attentions=True, hybrid_vit.py:422-450). */
+ *                   (return_attentions=True, hybrid_vit.py:422-450; written by the tensor-core attention kernel itself
+ *                   up to 1 280 tokens).
+ * Stream semantics (this call and hvit_enhance / hvit_enhance_varlen): everything is enqueued on `stream`, except the
+ * skip-path kernels, which run on a side stream owned by the plan, forked from `stream` after the encoder and joined
+ * back into it (events) before the first decoder block - so all of the call's work is ordered before whatever the
+ * caller enqueues on `stream` next, the call never synchronises, and it can be captured into a CUDA graph.  A plan
+ * must not be run from two streams at the same time (one workspace). */
 int hvit_forward(hvit_plan* plan, const float* x_dev, float* y_dev, float* attn_probs_dev, void* stream);
 
 /* AudioEnhancer.enhance (inference/enhancer.py:55-135) for a batch of equal-length clips, everything on the
